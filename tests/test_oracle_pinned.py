@@ -1,0 +1,156 @@
+"""Pins ``oracle/dm_oracle.py`` (the CPU restatement): against the outputs recorded in the
+reference's own README / notebooks, against the committed golden fixtures generated from the
+unmodified reference, against the scheduler known answers of SURVEY.md appendix A, and --
+where /root/reference exists -- against the live reference on fresh random circuits."""
+import copy
+import math
+
+import numpy as np
+import pytest
+
+import cases
+from golden_check import check_against_golden
+from oracle import dm_oracle as O
+from oracle import ref_harness as R
+from qiskit_aakash_b200 import circuits as C
+
+
+def run_case(name):
+    case = cases.get(name)
+    cases.write_files(case, ".")
+    return O.run_oracle(case["n"], case["instrs"], case["options"], name=name)
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_oracle_matches_golden(name, golden, case_dir):
+    check_against_golden(golden, name, run_case(name), tol=1e-13)
+
+
+# ---- values recorded in the reference itself -----------------------
+
+def test_readme_example(case_dir):
+    d = run_case("readme_x_cx")["data"]          # README.md:44-62
+    assert np.allclose(d["coeffmatrix"], [.25, 0, 0, -.25, 0, 0, 0, 0, 0, 0, 0, 0, .25, 0, 0, -.25])
+    m = np.zeros((4, 4), complex); m[1, 1] = 1
+    assert np.allclose(d["densitymatrix"], m)
+
+
+def test_notebook_initialisation(case_dir):
+    assert np.allclose(run_case("init_max_mixed_1")["data"]["densitymatrix"], np.eye(2) / 2)
+    m = np.zeros((4, 4), complex); m[2, 2] = 1   # initialisation.ipynb cell 8
+    assert np.allclose(run_case("init_binary_01")["data"]["densitymatrix"], m)
+
+
+def test_notebook_measurement(case_dir):
+    assert np.allclose(run_case("nb_measure_x")["data"]["densitymatrix"], np.eye(2) / 2)
+    exp = np.array([[0.82142857, 0.10714286 - 0.21428571j], [0.10714286 + 0.21428571j, 0.17857143]])
+    assert np.allclose(run_case("nb_measure_n")["data"]["densitymatrix"], exp, atol=1e-8)
+    assert run_case("nb_bell_000")["data"]["bell_probabilities01"] == {
+        "Bell_1": 0.5, "Bell_2": 0.5, "Bell_3": 0.0, "Bell_4": 0.0}
+    p = run_case("nb_ghz_ensemble_x")["data"]["ensemble_probability"]
+    for k, v in p.items():
+        assert abs(v - (0.25 if k in ("000", "011", "101", "110") else 0.0)) < 1e-15
+    assert abs(run_case("nb_ghz_expect_ziz")["data"]["Pauli_string_expectation"] - 1.0) < 1e-15
+
+
+def test_notebook_noise_values(case_dir):
+    p = run_case("nb_noise_noisy")["data"]["ensemble_probability"]
+    exp = {"000": 0.013707333156544835, "001": 0.9185746827153851, "010": 0.00035427138363945676,
+           "011": 0.02374092174643047, "100": 0.0003500056168837945, "101": 0.02345505831118616,
+           "110": 0.00029137984293194086, "111": 0.019526347226998225}
+    for k in exp:
+        assert abs(p[k] - exp[k]) < 1e-14
+
+
+# ---- merge / partition known answers (partition.ipynb) --------------
+
+def _names(levels):
+    return [[(g.name, tuple(g.qubits)) for g in lv] for lv in levels]
+
+
+def test_u3_merge_kats():
+    b, a, g = O.u3_merge(0.7, 0.4, 1.1)
+    assert np.allclose([b, a, g], [1.4178514323015705, 0.6198495499898623, 0.25664125730160314], atol=1e-15)
+    b, a, g = O.u3_merge(math.pi, math.pi / 2, math.pi / 2)
+    assert np.allclose([b, a, g], [0.0, math.pi / 2, math.pi / 2], atol=1e-7)
+
+
+def test_merge_kats():
+    c = C.Circuit(1)
+    c.u1(.5, 0); c.u1(.25, 0); c.u3(.1, .2, .3, 0); c.u1(.125, 0); c.u2(.3, .4, 0)
+    out = O.single_gate_merge([O.as_instruction(i) for i in c.instructions], 1)
+    assert len(out) == 1 and out[0].name == "u3"
+    assert np.allclose(out[0].params, [1.6455912993793047, 0.3664375536449294, 1.7774866699020393], atol=1e-15)
+    c = C.Circuit(1); c.u3(.1, .2, .3, 0); c.iden(0); c.u3(.1, .2, .3, 0)
+    out = O.single_gate_merge([O.as_instruction(i) for i in c.instructions], 1)
+    assert np.allclose(out[0].params, [0.1937626418121086, 0.45120320789875784, 0.5512032078987579], atol=1e-15)
+    # partition.ipynb cell 4: u1(2.6) s y on qubit 2 -> U3 [3.141593, 1.570796, 5.741593]
+    c = C.Circuit(3); c.u1(3.6, 0); c.cx(0, 1); c.cx(1, 0); c.u1(2.6, 2); c.s(2); c.y(2)
+    out = O.single_gate_merge([O.as_instruction(i) for i in c.instructions], 3)
+    q2 = [g for g in out if g.qubits == [2]]
+    assert len(q2) == 1 and [round(x, 6) for x in q2[0].params] == [3.141593, 1.570796, 5.741593]
+    lv, n = O.partition(out, 3)
+    assert n == 3
+
+
+def test_partition_kats():
+    def levels(build, n):
+        c = C.Circuit(n); build(c)
+        ops = O.single_gate_merge([O.as_instruction(i) for i in c.instructions], n)
+        lv, cnt = O.partition(ops, n)
+        return _names(lv[:cnt]), cnt
+
+    u = lambda c, q: c.u3(.1, .2, .3, q)
+    lv, cnt = levels(lambda c: (u(c, 0), u(c, 1), c.cx(0, 1), u(c, 0), c.cx(1, 2), u(c, 2)), 3)
+    assert cnt == 4 and lv == [[("u3", (0,)), ("u3", (1,))], [("cx", (0, 1))],
+                               [("u3", (0,)), ("cx", (1, 2))], [("u3", (2,))]]
+    lv, cnt = levels(lambda c: (u(c, 0), c.measure(0, 0), u(c, 1), c.measure(1, 1)), 2)
+    assert cnt == 4 and [len(x) for x in lv] == [1, 1, 1, 1]
+    lv, cnt = levels(lambda c: (u(c, 0), c.cx(0, 1), c.measure(0, 0), c.measure(1, 1), c.measure(2, 2), u(c, 2)), 3)
+    assert cnt == 4 and [len(x) for x in lv] == [1, 1, 3, 1]
+    lv, cnt = levels(lambda c: (u(c, 0), c.reset(0), u(c, 0), c.reset(1)), 2)
+    assert cnt == 3 and [[g[0] for g in x] for x in lv] == [["u3"], ["reset", "reset"], ["u3"]]
+    lv, cnt = levels(lambda c: (c.cx(0, 1), c.cx(1, 2), c.cx(0, 2), u(c, 1)), 3)
+    assert cnt == 3 and lv[2] == [("cx", (0, 2)), ("u3", (1,))]
+    lv, cnt = levels(lambda c: (u(c, 0), c.barrier(), u(c, 1), c.barrier(), u(c, 0), u(c, 1)), 2)
+    assert cnt == 3
+    assert levels(lambda c: c.instructions.extend(C.qft(8).instructions), 8)[1] == 54
+    for n in (8, 9, 10):
+        assert levels(lambda c: c.instructions.extend(C.random_layered(n, 4, 1, readout=False).instructions), n)[1] == 8
+
+
+def test_partition_notebook_cell6(case_dir):
+    """partition.ipynb cell 6: 7 partitions with mixed measures."""
+    case = cases.get("nb_partition_mixed_measures")
+    ops = O.single_gate_merge([O.as_instruction(i) for i in case["instrs"]], 3)
+    lv, cnt = O.partition(ops, 3)
+    assert cnt == 7
+    got = [[(g.name, g.qubits[0]) for g in x] for x in lv[:7]]
+    assert got[2] == [("measure", 0), ("measure", 1)] and got[4] == [("measure", 1)]
+    assert got[6] == [("measure", 0), ("measure", 1), ("measure", 2)]
+
+
+# ---- live reference (build container only) ------------------------------------------------
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_matches_live_reference(seed, case_dir):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(2, 7))
+    circ = cases._rand_circuit(n, int(rng.integers(10, 40)), 2000 + seed)
+    mode = seed % 3
+    if mode == 0:
+        circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="XYZ"[seed % 3])
+    elif mode == 1:
+        qs = sorted(rng.choice(n, size=min(2, n), replace=False).tolist())
+        circ.measure(qs, qs, basis="Y")
+    opts = copy.deepcopy(cases.FULL_NOISE) if seed % 2 else {}
+    ref = R.run_reference(n, copy.deepcopy(circ.instructions), opts)
+    got = O.run_oracle(n, copy.deepcopy(circ.instructions), opts)
+    assert ref["number_of_clock_cycles"] == got["number_of_clock_cycles"]
+    assert set(ref["data"]) == set(got["data"])
+    for k, v in ref["data"].items():
+        a = np.array(list(v.values())) if isinstance(v, dict) else np.asarray(v)
+        w = got["data"][k]
+        b = np.array(list(w.values())) if isinstance(w, dict) else np.asarray(w)
+        assert np.max(np.abs(a - b)) <= 1e-14
