@@ -1,0 +1,161 @@
+/*
+ * dmb200.h -- C ABI of libdmb200.so, the B200 (sm_100a) implementation of the
+ * qiskit-aakash dm_simulator hot path (Pauli-basis density-matrix simulator).
+ *
+ * Everything numeric in the reference mutates one array, DmSimulatorPy._densitymatrix
+ * (a real float64 vector of 4^n Pauli coefficients, qubit 0 = most significant base-4
+ * digit; reference: qiskit/providers/basicaer/dm_simulator.py:61-68,376-377).  The entry
+ * points below are what a binding for that path needs; each cites the reference method(s)
+ * it replaces.  Conventions:
+ *   - plain C, no torch / C++ types; every function returns 0 on success, non-zero on
+ *     error, with the message available from dmb_last_error() (thread-local);
+ *   - the CALLER owns all state / scratch buffers (device pointers; PyTorch tensors in
+ *     the Python host) -- the library owns only a small per-context scratch area;
+ *   - all work is enqueued on the context's CUDA stream (dmb_set_stream); only the
+ *     functions documented as synchronous wait for it;
+ *   - "digit position" p means the base-4 digit with stride 4^p in the *local* buffer
+ *     (bits 2p, 2p+1 of the element index).  In the reference layout qubit q of an
+ *     n-qubit register sits at digit position n-1-q.
+ */
+#ifndef DMB200_H
+#define DMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMB_ABI_VERSION 1
+#define DMB_MAX_TILE_DIGITS 6   /* a tile holds 4^6 = 4096 doubles = 32 KiB of shared memory */
+#define DMB_MAX_OPS 16          /* fused ops per tile pass */
+#define DMB_MAX_QUBITS 32
+
+typedef struct dmb_ctx dmb_ctx;
+
+/* ---- fused two-digit op, applied inside a tile pass --------------------------------
+ * Acts on the 16-element blocks spanned by tile-local digits a and b (v[i][j], i = value
+ * of digit a, j = value of digit b).  Order of application inside one op:
+ *   1. if (flags & DMB_HAS_PA): rows 1..3 of a 4x4 real matrix along digit a
+ *      (row 0 of every trace-preserving single-qubit map is (1,0,0,0) and is implied);
+ *      this is where u1/u3 rotations (basicaertools.py:69-126), memory noise
+ *      (dm_simulator.py:397-425), projective measurements (:574-704), Pauli-string
+ *      projections (:553-566) and reset (:810-823) end up, pre-multiplied on the host;
+ *   2. if (flags & DMB_HAS_PB): the same along digit b;
+ *   3. the two-digit kernel selected by `kind`. */
+enum {
+  DMB_OP_MATS   = 0, /* nothing further (single-qubit work only)                         */
+  DMB_OP_CX     = 1, /* ideal CNOT, a = control digit, b = target digit: signed permutation
+                        of the 16 Pauli pairs (basicaertools.py:310-392 with [1,0])       */
+  DMB_OP_CX_TSP = 2, /* CNOT under the transition-selective-pulse error model; coef[0..4] =
+                        c, s, c2, s2, cs of basicaertools.py:329-336                      */
+  DMB_OP_DIAG2  = 3, /* v[i][j] *= coef[4*i+j]  (Bell-basis measurement mask,
+                        dm_simulator.py:749-756)                                          */
+  DMB_OP_SWAP   = 4  /* v[i][j] <-> v[j][i]: exchanges the two digits (layout remap)      */
+};
+enum { DMB_HAS_PA = 1, DMB_HAS_PB = 2 };
+
+typedef struct dmb_op {
+  int32_t kind;
+  int32_t flags;
+  int8_t a, b;      /* tile-local digit indices (indices into dmb_pass.tile_digit), a != b */
+  int8_t fd[4];     /* the other tile-local digits, in the order thread-index bit pairs are
+                       dealt to them (chosen by the host for conflict-free shared memory)  */
+  int8_t pad_[2];
+  double pa[12];    /* rows 1..3 of the matrix on digit a, row-major [3][4]                */
+  double pb[12];    /* rows 1..3 of the matrix on digit b                                  */
+  double coef[16];
+} dmb_op;           /* 336 bytes */
+
+/* One tile pass = one HBM round trip of the whole (local) state: every tile (all values
+ * of the n_tile_digits listed digits, for one value of all other index bits) is staged in
+ * shared memory, the ops are applied in order, and the tile is written back. */
+typedef struct dmb_pass {
+  int32_t n_tile_digits;                    /* K, 2..DMB_MAX_TILE_DIGITS                   */
+  int32_t n_ops;                            /* 1..DMB_MAX_OPS                              */
+  int32_t tile_digit[DMB_MAX_TILE_DIGITS];  /* ascending digit positions, tile_digit[0]==0 */
+  dmb_op ops[DMB_MAX_OPS];
+} dmb_pass;
+
+/* Per-context counters for roofline reporting. */
+typedef struct dmb_stats {
+  uint64_t tile_pass_launches;   /* launches of the fused tile kernel                      */
+  uint64_t other_launches;       /* every other kernel of this library                     */
+  uint64_t fused_ops;            /* dmb_op entries executed                                */
+  uint64_t state_bytes_moved;    /* algorithmic HBM bytes of tile passes: 16 B x elements  */
+} dmb_stats;
+
+/* ---- context ------------------------------------------------------------------------ */
+int dmb_abi_version(void);
+size_t dmb_sizeof_op(void);     /* layout checks for foreign-language bindings */
+size_t dmb_sizeof_pass(void);
+const char* dmb_last_error(void);
+/* Binds to CUDA device `device`; fails (non-zero) if no such device / not sm_100. */
+int dmb_create(int device, dmb_ctx** out);
+int dmb_destroy(dmb_ctx* ctx);
+/* cudaStream_t to enqueue on (e.g. torch.cuda.current_stream().cuda_stream); 0 = default. */
+int dmb_set_stream(dmb_ctx* ctx, void* cuda_stream);
+int dmb_sync(dmb_ctx* ctx);                                   /* synchronous */
+int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out);
+int dmb_reset_stats(dmb_ctx* ctx);
+/* Tile-kernel variant: 0 = register-staged 128-bit loads, one tile per CTA (default);
+ * other values are rejected unless the library was built with them. */
+int dmb_set_tile_variant(dmb_ctx* ctx, int variant);
+
+/* ---- state initialisation (replaces DmSimulatorPy._initialize_densitymatrix,
+ *      dm_simulator.py:284-349: every built-in initial state is a product state) --------
+ * state[idx] = scale * prod_q v[q][digit_q(g)],  g = (rank_bits << n_bits) | idx, where
+ * digit_q(g) = 2*bit(g, hi[q]) + bit(g, lo[q]).  n_bits = log2(#local elements).         */
+int dmb_init_product(dmb_ctx* ctx, double* state, int n_bits, uint64_t rank_bits,
+                     int n_qubits, const int32_t* hi, const int32_t* lo,
+                     const double* v /* [n_qubits][4] */, double scale);
+
+/* ---- gate / noise / projection application (replaces _add_unitary_single :367-384,
+ *      _add_unitary_two :386-395 + basicaertools.cx_gate_dm_matrix, _add_decoherence_and_
+ *      amp_decay :397-425, _add_qasm_measure_X/Y/Z/N :574-704, the projections of
+ *      _pauli_string_expectation :553-566, the mask of _add_bell_basis_measure :749-756,
+ *      _add_qasm_reset :810-823) -- pre-scheduled into tile passes by the host.
+ * `passes` is HOST memory; it is consumed before the call returns (kernel parameters). */
+int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits,
+                     const dmb_pass* passes, size_t n_passes);
+
+/* ---- readout ------------------------------------------------------------------------
+ * I/B-marginal of _add_ensemble_measure (:427-481) for basis X/Y/Z: for c in [0,2^n_qubits)
+ *   out[c] = sum over the listed digit values of  w * state[...],
+ * generalised so that pending single-qubit maps and sharded (global) qubits can be folded
+ * in: qubit k (result bit k of c) reads digit (hi[k], lo[k]) of the global index
+ * g = (rank_bits << n_bits) | idx and contributes weight wt[k][c_k][digit]  (wt is
+ * [n_qubits][2][4]); digits with zero weight are skipped, bits >= n_bits must match
+ * rank_bits or the term is dropped.  Then dmb_fwht turns the marginal into the 2^n
+ * probabilities  P(r) = sum_c (-1)^(r.c) out[c]. `out` is a device buffer of 2^n_qubits. */
+int dmb_marginal(dmb_ctx* ctx, const double* state, int n_bits, uint64_t rank_bits,
+                 int n_qubits, const int32_t* hi, const int32_t* lo,
+                 const double* wt /* [n_qubits][2][4] */, double* out);
+int dmb_fwht(dmb_ctx* ctx, double* vec, int n_qubits);
+/* One step of the 'N'-basis ensemble contraction (:457-462): in viewed as [H][4][L],
+ * out[h][0][l] = in[h][0][l], out[h][1][l] = nv . in[h][1..3][l].                        */
+int dmb_contract_digit(dmb_ctx* ctx, const double* in, double* out, uint64_t H, uint64_t L,
+                       const double nv[3]);
+/* Gather of a few coefficients to HOST memory (synchronous): expectation values
+ * (:569-570), Bell reduced matrix (:744-747, :758-760), trace check (:363).              */
+int dmb_read_coeffs(dmb_ctx* ctx, const double* state, const uint64_t* idx, size_t k,
+                    double* out_host);
+/* Pauli -> matrix basis (_compute_densitymatrix :1198-1255).  `work` and `out` are device
+ * buffers of 4^n_qubits complex doubles (interleaved re,im); out is the row-major
+ * 2^n x 2^n matrix, qubit 0 = MSB of row and column index.                               */
+int dmb_to_matrix(dmb_ctx* ctx, const double* state, int n_qubits, double* work, double* out);
+/* dot(a, b) (_state_overlap :1277-1282, without the 2^n factor); synchronous.            */
+int dmb_dot(dmb_ctx* ctx, const double* a, const double* b, uint64_t count, double* out_host);
+/* vec[|x| < thr] = 0 (_get_densitymatrix :1263).                                         */
+int dmb_chop(dmb_ctx* ctx, double* state, uint64_t count, double thr);
+
+/* ---- host <-> device transfer of coefficients ('stored_density_matrix' :337-343,
+ *      'coeffmatrix' :1181-1183); host memory should be pinned for full PCIe speed ------ */
+int dmb_upload(dmb_ctx* ctx, double* state, const double* host, uint64_t offset, uint64_t count);
+int dmb_download(dmb_ctx* ctx, const double* state, double* host, uint64_t offset, uint64_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMB200_H */

@@ -1,0 +1,185 @@
+"""ctypes binding of ``libdmb200.so`` (C ABI: ``include/dmb200.h``).
+
+The library is the product: if it cannot be loaded this module raises -- there is no
+CPU fallback.  ``load_library(path)`` accepts an explicit path only so that the build
+container's unit tests can inject the thread-by-thread CPU emulation of the kernels
+(``tests/emu``); nothing in the package ever passes one.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+MAX_TILE_DIGITS = 6
+MAX_OPS = 16
+MAX_QUBITS = 32
+
+OP_MATS, OP_CX, OP_CX_TSP, OP_DIAG2, OP_SWAP = 0, 1, 2, 3, 4
+HAS_PA, HAS_PB = 1, 2
+
+OP_DTYPE = np.dtype([("kind", "<i4"), ("flags", "<i4"), ("a", "i1"), ("b", "i1"), ("fd", "i1", (4,)),
+                     ("pad_", "i1", (2,)), ("pa", "<f8", (12,)), ("pb", "<f8", (12,)),
+                     ("coef", "<f8", (16,))])
+PASS_DTYPE = np.dtype([("n_tile_digits", "<i4"), ("n_ops", "<i4"), ("tile_digit", "<i4", (MAX_TILE_DIGITS,)),
+                       ("ops", OP_DTYPE, (MAX_OPS,))])
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("tile_pass_launches", ctypes.c_uint64), ("other_launches", ctypes.c_uint64),
+                ("fused_ops", ctypes.c_uint64), ("state_bytes_moved", ctypes.c_uint64)]
+
+
+class DmbError(RuntimeError):
+    pass
+
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_PKG_DIR, "libdmb200.so")
+
+_c = ctypes
+_vp, _i, _u64, _sz, _d = _c.c_void_p, _c.c_int, _c.c_uint64, _c.c_size_t, _c.c_double
+_SIGNATURES = {
+    "dmb_abi_version": (_i, []),
+    "dmb_sizeof_op": (_sz, []),
+    "dmb_sizeof_pass": (_sz, []),
+    "dmb_last_error": (_c.c_char_p, []),
+    "dmb_create": (_i, [_i, _c.POINTER(_vp)]),
+    "dmb_destroy": (_i, [_vp]),
+    "dmb_set_stream": (_i, [_vp, _vp]),
+    "dmb_sync": (_i, [_vp]),
+    "dmb_get_stats": (_i, [_vp, _c.POINTER(Stats)]),
+    "dmb_reset_stats": (_i, [_vp]),
+    "dmb_set_tile_variant": (_i, [_vp, _i]),
+    "dmb_init_product": (_i, [_vp, _vp, _i, _u64, _i, _vp, _vp, _vp, _d]),
+    "dmb_apply_passes": (_i, [_vp, _vp, _i, _vp, _sz]),
+    "dmb_marginal": (_i, [_vp, _vp, _i, _u64, _i, _vp, _vp, _vp, _vp]),
+    "dmb_fwht": (_i, [_vp, _vp, _i]),
+    "dmb_contract_digit": (_i, [_vp, _vp, _vp, _u64, _u64, _vp]),
+    "dmb_read_coeffs": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "dmb_to_matrix": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "dmb_dot": (_i, [_vp, _vp, _vp, _u64, _vp]),
+    "dmb_chop": (_i, [_vp, _vp, _u64, _d]),
+    "dmb_upload": (_i, [_vp, _vp, _vp, _u64, _u64]),
+    "dmb_download": (_i, [_vp, _vp, _vp, _u64, _u64]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load_library(path=None):
+    """dlopen the CUDA library and type its entry points.  Raises if it is missing."""
+    path = path or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise DmbError("CUDA library %s not found -- build it with `python -c 'import __graft_entry__ as g; "
+                       "g.build()'` (nvcc, sm_100a); this package has no CPU fallback" % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dmb_abi_version() != 1:
+        raise DmbError("ABI version mismatch")
+    if lib.dmb_sizeof_op() != OP_DTYPE.itemsize or lib.dmb_sizeof_pass() != PASS_DTYPE.itemsize:
+        raise DmbError("struct layout mismatch between capi.py and libdmb200.so")
+    return lib
+
+
+def _ptr(arr):
+    return arr.ctypes.data_as(ctypes.c_void_p)
+
+
+class Context:
+    """One ``dmb_ctx``: a device binding + stream + counters."""
+
+    def __init__(self, lib, device=0):
+        self.lib = lib
+        self._h = ctypes.c_void_p()
+        self._check(lib.dmb_create(int(device), ctypes.byref(self._h)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise DmbError(self.lib.dmb_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if self._h:
+            self.lib.dmb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing ----------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.dmb_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self._check(self.lib.dmb_sync(self._h))
+
+    def stats(self):
+        s = Stats()
+        self._check(self.lib.dmb_get_stats(self._h, ctypes.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+    def reset_stats(self):
+        self._check(self.lib.dmb_reset_stats(self._h))
+
+    def set_tile_variant(self, v):
+        self._check(self.lib.dmb_set_tile_variant(self._h, int(v)))
+
+    # -- state -------------------------------------------------------------------------
+    def init_product(self, state_ptr, n_bits, rank_bits, hi, lo, v, scale):
+        hi = np.ascontiguousarray(hi, dtype=np.int32)
+        lo = np.ascontiguousarray(lo, dtype=np.int32)
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(len(hi), 4)
+        self._check(self.lib.dmb_init_product(self._h, state_ptr, int(n_bits), int(rank_bits), len(hi),
+                                              _ptr(hi), _ptr(lo), _ptr(v), float(scale)))
+
+    def apply_passes(self, state_ptr, n_bits, passes):
+        if len(passes) == 0:
+            return
+        assert passes.dtype == PASS_DTYPE and passes.flags["C_CONTIGUOUS"]
+        self._check(self.lib.dmb_apply_passes(self._h, state_ptr, int(n_bits), _ptr(passes), len(passes)))
+
+    def marginal(self, state_ptr, n_bits, rank_bits, hi, lo, wt, out_ptr):
+        hi = np.ascontiguousarray(hi, dtype=np.int32)
+        lo = np.ascontiguousarray(lo, dtype=np.int32)
+        wt = np.ascontiguousarray(wt, dtype=np.float64).reshape(len(hi), 2, 4)
+        self._check(self.lib.dmb_marginal(self._h, state_ptr, int(n_bits), int(rank_bits), len(hi),
+                                          _ptr(hi), _ptr(lo), _ptr(wt), out_ptr))
+
+    def fwht(self, vec_ptr, n_qubits):
+        self._check(self.lib.dmb_fwht(self._h, vec_ptr, int(n_qubits)))
+
+    def contract_digit(self, in_ptr, out_ptr, H, L, nv):
+        nv = np.ascontiguousarray(nv, dtype=np.float64)
+        self._check(self.lib.dmb_contract_digit(self._h, in_ptr, out_ptr, int(H), int(L), _ptr(nv)))
+
+    def read_coeffs(self, state_ptr, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        out = np.empty(len(idx), dtype=np.float64)
+        self._check(self.lib.dmb_read_coeffs(self._h, state_ptr, _ptr(idx), len(idx), _ptr(out)))
+        return out
+
+    def to_matrix(self, state_ptr, n_qubits, work_ptr, out_ptr):
+        self._check(self.lib.dmb_to_matrix(self._h, state_ptr, int(n_qubits), work_ptr, out_ptr))
+
+    def dot(self, a_ptr, b_ptr, count):
+        out = ctypes.c_double()
+        self._check(self.lib.dmb_dot(self._h, a_ptr, b_ptr, int(count), ctypes.byref(out)))
+        return out.value
+
+    def chop(self, state_ptr, count, thr):
+        self._check(self.lib.dmb_chop(self._h, state_ptr, int(count), float(thr)))
+
+    def upload(self, state_ptr, host, offset=0):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        self._check(self.lib.dmb_upload(self._h, state_ptr, _ptr(host), int(offset), host.size))
+        self.sync()      # the host array may be a temporary
+
+    def download(self, state_ptr, host, offset=0):
+        assert host.dtype == np.float64 and host.flags["C_CONTIGUOUS"]
+        self._check(self.lib.dmb_download(self._h, state_ptr, _ptr(host), int(offset), host.size))

@@ -1,0 +1,362 @@
+// dm_device.h -- per-thread bodies of the dmb200 kernels.
+//
+// Every kernel in dmb200.cu is "phase structured": a phase is a function of the thread
+// index that touches shared/global memory, phases are separated by block barriers.  The
+// bodies live here as __host__ __device__ functions so that the index arithmetic (tile
+// addressing, shared-memory swizzle, per-op thread mapping, Pauli-pair arithmetic) is one
+// piece of code: dmb200.cu wraps it in __global__ kernels for sm_100a; the CPU unit tests
+// (tests/emu) run the same bodies thread-by-thread to check the arithmetic where no GPU is
+// available.  Nothing here is a fallback path of the product.
+#pragma once
+#include <stdint.h>
+#include "dmb200.h"
+
+#if defined(__CUDACC__)
+#define DMB_HD __host__ __device__ __forceinline__
+#else
+#define DMB_HD inline
+#endif
+
+#define DMB_TILE_THREADS 256
+
+struct alignas(16) dmb_d2 { double x, y; };
+
+// ---------------------------------------------------------------------------------------
+// Tile addressing
+// ---------------------------------------------------------------------------------------
+// A tile is addressed by a 2K-bit local index l: digit j of l (bits 2j,2j+1) is the value
+// of state digit tile_digit[j].  In shared memory element l lives at word dmb_swz(l).  The
+// swizzle keeps 16-byte pairs (l0) intact -- so tiles can be filled by 128-bit loads or
+// 16-byte cp.async -- and XORs the 16-byte chunk index inside each 128-byte row (bits 3:1)
+// with a linear function of the higher digits D2..D5:
+//     chunk[2:1] ^= D2 ^ D3 ^ D4 ^ D5          chunk[0] ^= parity(D3) ^ parity(D5)
+// With it every op is bank-conflict free for a suitable lane order (dmb_op.fd, chosen by
+// the host, see schedule.py):
+//   (A) op digits exclude digit 0: 64-bit accesses, lanes[1:0] = digit 0, lanes[3:2] = any
+//       other free digit -> the 16 lanes of a half-warp hit 16 distinct 8-byte slots;
+//   (B) op digits include digit 0: the thread's elements along digit 0 are two 16-byte
+//       chunks, accessed as 128-bit words; lanes[1:0] = digit 1 (or 2 if 1 is an op digit),
+//       lane[2] = low bit of digit 3 (or 5) -> the 8 lanes of a quarter-warp hit 8 distinct
+//       chunks.
+DMB_HD uint32_t dmb_swz(uint32_t l) {
+  const uint32_t d2 = (l >> 4) & 3u, d3 = (l >> 6) & 3u, d4 = (l >> 8) & 3u, d5 = (l >> 10) & 3u;
+  const uint32_t hi = d2 ^ d3 ^ d4 ^ d5;
+  const uint32_t odd = d3 ^ d5;
+  return l ^ (hi << 2) ^ (((odd ^ (odd >> 1)) & 1u) << 1);
+}
+
+// tile number -> offset of the tile's element 0: insert a zero digit at every tile digit.
+DMB_HD uint64_t dmb_tile_base(uint64_t tile, const int32_t* td, int K) {
+  uint64_t x = tile;
+  for (int j = 0; j < K; ++j) {
+    const int sh = 2 * td[j];
+    const uint64_t low = x & ((1ull << sh) - 1ull);
+    x = ((x >> sh) << (sh + 2)) | low;
+  }
+  return x;
+}
+
+// local index -> offset relative to the tile base.
+DMB_HD uint64_t dmb_tile_off(uint32_t l, const int32_t* td, int K) {
+  uint64_t off = 0;
+  for (int j = 0; j < K; ++j) off |= (uint64_t)((l >> (2 * j)) & 3u) << (2 * td[j]);
+  return off;
+}
+
+// Load phase: thread t moves the 16-byte pairs p = t, t+256, ... (tile_digit[0] == 0, so the
+// two elements of a pair are adjacent in global memory and share a 16-byte chunk of smem).
+template <int MAXPAIRS>
+DMB_HD void dmb_tile_load_thread(int t, const double* __restrict__ gtile, double* smem,
+                                 const int32_t* td, int K) {
+  const uint32_t npairs = 1u << (2 * K - 1);
+  dmb_d2 v[MAXPAIRS];
+#pragma unroll
+  for (int i = 0; i < MAXPAIRS; ++i) {
+    const uint32_t p = (uint32_t)t + (uint32_t)i * DMB_TILE_THREADS;
+    if (p < npairs) v[i] = *reinterpret_cast<const dmb_d2*>(gtile + dmb_tile_off(2u * p, td, K));
+  }
+#pragma unroll
+  for (int i = 0; i < MAXPAIRS; ++i) {
+    const uint32_t p = (uint32_t)t + (uint32_t)i * DMB_TILE_THREADS;
+    if (p < npairs) {
+      *reinterpret_cast<dmb_d2*>(smem + dmb_swz(2u * p)) = v[i];
+    }
+  }
+}
+
+template <int MAXPAIRS>
+DMB_HD void dmb_tile_store_thread(int t, double* __restrict__ gtile, const double* smem,
+                                  const int32_t* td, int K) {
+  const uint32_t npairs = 1u << (2 * K - 1);
+#pragma unroll
+  for (int i = 0; i < MAXPAIRS; ++i) {
+    const uint32_t p = (uint32_t)t + (uint32_t)i * DMB_TILE_THREADS;
+    if (p < npairs) {
+      const dmb_d2 w = *reinterpret_cast<const dmb_d2*>(smem + dmb_swz(2u * p));
+      *reinterpret_cast<dmb_d2*>(gtile + dmb_tile_off(2u * p, td, K)) = w;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Pauli-pair arithmetic on one 16-element block  v[i][j]  (i: digit a, j: digit b)
+// ---------------------------------------------------------------------------------------
+// rows 1..3 of a single-qubit map along the first index (x0 is the I component, unchanged)
+DMB_HD void dmb_mat3(const double* __restrict__ m, double& x0, double& x1, double& x2, double& x3) {
+  const double y1 = m[0] * x0 + m[1] * x1 + m[2] * x2 + m[3] * x3;
+  const double y2 = m[4] * x0 + m[5] * x1 + m[6] * x2 + m[7] * x3;
+  const double y3 = m[8] * x0 + m[9] * x1 + m[10] * x2 + m[11] * x3;
+  x1 = y1; x2 = y2; x3 = y3;
+}
+
+// CNOT with the transition-selective-pulse error model, control = first index, target =
+// second index.  Restates basicaertools.py:346-363 (the q_2 > q_1 branch; the other branch
+// is the same map with the axes exchanged).  I,X,Y,Z = 0,1,2,3.
+DMB_HD void dmb_cx_tsp(double (&v)[4][4], double c, double s, double c2, double s2, double cs) {
+  const double iy = v[0][2], zy = v[3][2], iz = v[0][3], zz = v[3][3];
+  const double dz = iz - zz, dy = iy - zy;
+  v[0][2] = s2 * iy + c2 * zy - cs * dz;
+  v[3][2] = c2 * iy + s2 * zy + cs * dz;
+  v[0][3] = s2 * iz + c2 * zz + cs * dy;
+  v[3][3] = c2 * iz + s2 * zz - cs * dy;
+  const double xi = v[1][0], xx = v[1][1], xy = v[1][2], xz = v[1][3];
+  const double yi = v[2][0], yx = v[2][1], yy = v[2][2], yz = v[2][3];
+  v[1][0] = c * xx - s * yi;
+  v[1][1] = c * xi - s * yx;
+  v[1][2] = -s * yy + c * yz;
+  v[1][3] = -c * yy - s * yz;
+  v[2][0] = s * xi + c * yx;
+  v[2][1] = s * xx + c * yi;
+  v[2][2] = s * xy - c * xz;
+  v[2][3] = c * xy + s * xz;
+}
+
+// Ideal CNOT: the same map with (c,s,c2,s2,cs) = (1,0,1,0,0) -- a signed permutation.
+DMB_HD void dmb_cx_ideal(double (&v)[4][4]) {
+  double t;
+  t = v[0][2]; v[0][2] = v[3][2]; v[3][2] = t;      // IY <-> ZY
+  t = v[0][3]; v[0][3] = v[3][3]; v[3][3] = t;      // IZ <-> ZZ
+  t = v[1][0]; v[1][0] = v[1][1]; v[1][1] = t;      // XI <-> XX
+  t = v[2][0]; v[2][0] = v[2][1]; v[2][1] = t;      // YI <-> YX
+  const double xy = v[1][2], xz = v[1][3], yy = v[2][2], yz = v[2][3];
+  v[1][2] = yz; v[1][3] = -yy; v[2][2] = -xz; v[2][3] = xy;
+}
+
+// Op phase: thread t owns the 16-block number t of the tile (4^(K-2) blocks).
+DMB_HD void dmb_tile_op_thread(int t, const dmb_op& op, double* smem, int K) {
+  const int nfree = K - 2;
+  if (t >= (1 << (2 * nfree))) return;
+  uint32_t bl = 0;
+  for (int m = 0; m < nfree; ++m) bl |= (uint32_t)((t >> (2 * m)) & 3) << (2 * op.fd[m]);
+  const uint32_t sb = dmb_swz(bl);
+  uint32_t sa[4], sj[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sa[i] = dmb_swz((uint32_t)i << (2 * op.a));
+    sj[i] = dmb_swz((uint32_t)i << (2 * op.b));
+  }
+  double v[4][4];
+  if (op.a == 0) {            // mode (B): pairs along i
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const dmb_d2 p0 = *reinterpret_cast<const dmb_d2*>(smem + (sb ^ sj[j]));
+      const dmb_d2 p1 = *reinterpret_cast<const dmb_d2*>(smem + (sb ^ sj[j] ^ 2u));
+      v[0][j] = p0.x; v[1][j] = p0.y; v[2][j] = p1.x; v[3][j] = p1.y;
+    }
+  } else if (op.b == 0) {     // mode (B): pairs along j
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const dmb_d2 p0 = *reinterpret_cast<const dmb_d2*>(smem + (sb ^ sa[i]));
+      const dmb_d2 p1 = *reinterpret_cast<const dmb_d2*>(smem + (sb ^ sa[i] ^ 2u));
+      v[i][0] = p0.x; v[i][1] = p0.y; v[i][2] = p1.x; v[i][3] = p1.y;
+    }
+  } else {                    // mode (A)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] = smem[sb ^ sa[i] ^ sj[j]];
+  }
+
+  if (op.flags & DMB_HAS_PA) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dmb_mat3(op.pa, v[0][j], v[1][j], v[2][j], v[3][j]);
+  }
+  if (op.flags & DMB_HAS_PB) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dmb_mat3(op.pb, v[i][0], v[i][1], v[i][2], v[i][3]);
+  }
+  switch (op.kind) {
+    case DMB_OP_CX:
+      dmb_cx_ideal(v);
+      break;
+    case DMB_OP_CX_TSP:
+      dmb_cx_tsp(v, op.coef[0], op.coef[1], op.coef[2], op.coef[3], op.coef[4]);
+      break;
+    case DMB_OP_DIAG2:
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i][j] *= op.coef[4 * i + j];
+      break;
+    case DMB_OP_SWAP:
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j) { const double tmp = v[i][j]; v[i][j] = v[j][i]; v[j][i] = tmp; }
+      break;
+    default:
+      break;
+  }
+  if (op.a == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dmb_d2 p0, p1;
+      p0.x = v[0][j]; p0.y = v[1][j]; p1.x = v[2][j]; p1.y = v[3][j];
+      *reinterpret_cast<dmb_d2*>(smem + (sb ^ sj[j])) = p0;
+      *reinterpret_cast<dmb_d2*>(smem + (sb ^ sj[j] ^ 2u)) = p1;
+    }
+  } else if (op.b == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      dmb_d2 p0, p1;
+      p0.x = v[i][0]; p0.y = v[i][1]; p1.x = v[i][2]; p1.y = v[i][3];
+      *reinterpret_cast<dmb_d2*>(smem + (sb ^ sa[i])) = p0;
+      *reinterpret_cast<dmb_d2*>(smem + (sb ^ sa[i] ^ 2u)) = p1;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) smem[sb ^ sa[i] ^ sj[j]] = v[i][j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Element-wise kernels (one logical thread per output element)
+// ---------------------------------------------------------------------------------------
+struct dmb_qubit_map {              // where each qubit's digit lives in the global index
+  int32_t n_qubits;
+  int32_t hi[DMB_MAX_QUBITS];
+  int32_t lo[DMB_MAX_QUBITS];
+};
+
+DMB_HD int dmb_digit_of(uint64_t g, int hi, int lo) {
+  return (int)(((g >> hi) & 1ull) << 1 | ((g >> lo) & 1ull));
+}
+
+struct dmb_init_params {
+  dmb_qubit_map map;
+  double v[DMB_MAX_QUBITS][4];
+  double scale;
+  uint64_t rank_bits;
+  int32_t n_bits;
+};
+
+DMB_HD double dmb_init_value(uint64_t idx, const dmb_init_params& p) {
+  const uint64_t g = (p.rank_bits << p.n_bits) | idx;
+  double x = p.scale;
+  for (int q = 0; q < p.map.n_qubits; ++q) x *= p.v[q][dmb_digit_of(g, p.map.hi[q], p.map.lo[q])];
+  return x;
+}
+
+// Marginal gather (see dmb_marginal in dmb200.h).  Qubits are split by the host into
+// "simple" ones (at most one non-zero weight per result bit value: the usual I / B pick)
+// and up to DMB_MAX_MULTI "multi" ones whose weights mix several digit values (pending
+// single-qubit maps on sharded qubits).
+#define DMB_MAX_MULTI 3
+struct dmb_marginal_params {
+  dmb_qubit_map map;
+  double wt[DMB_MAX_QUBITS][2][4];
+  int8_t simple_digit[DMB_MAX_QUBITS][2];   // digit picked for result bit 0 / 1, -1 = multi
+  int32_t n_multi;
+  int32_t multi[DMB_MAX_MULTI];
+  uint64_t rank_bits;
+  int32_t n_bits;
+};
+
+DMB_HD uint64_t dmb_place_digit(int d, int hi, int lo) {
+  return ((uint64_t)((d >> 1) & 1) << hi) | ((uint64_t)(d & 1) << lo);
+}
+
+DMB_HD double dmb_marginal_value(uint64_t c, const double* __restrict__ state,
+                                 const dmb_marginal_params& p) {
+  uint64_t g0 = 0;
+  double w0 = 1.0;
+  for (int k = 0; k < p.map.n_qubits; ++k) {
+    const int cb = (int)((c >> k) & 1ull);
+    const int d = p.simple_digit[k][cb];
+    if (d < 0) continue;
+    w0 *= p.wt[k][cb][d];
+    g0 |= dmb_place_digit(d, p.map.hi[k], p.map.lo[k]);
+  }
+  if (w0 == 0.0) return 0.0;
+  const uint64_t mask = (1ull << p.n_bits) - 1ull;
+  double total = 0.0;
+  const int combos = 1 << (2 * p.n_multi);
+  for (int combo = 0; combo < combos; ++combo) {
+    uint64_t g = g0;
+    double w = w0;
+    for (int m = 0; m < p.n_multi; ++m) {
+      const int k = p.multi[m];
+      const int cb = (int)((c >> k) & 1ull);
+      const int d = (combo >> (2 * m)) & 3;
+      w *= p.wt[k][cb][d];
+      g |= dmb_place_digit(d, p.map.hi[k], p.map.lo[k]);
+    }
+    if (w == 0.0) continue;
+    if ((g >> p.n_bits) != p.rank_bits) continue;
+    total += w * state[g & mask];
+  }
+  return total;
+}
+
+// One butterfly of the Walsh-Hadamard transform: pair number `t` of stage `stage`.
+DMB_HD void dmb_fwht_pair(uint64_t t, int stage, double* vec) {
+  const uint64_t low = t & ((1ull << stage) - 1ull);
+  const uint64_t i = ((t >> stage) << (stage + 1)) | low;
+  const uint64_t j = i | (1ull << stage);
+  const double a = vec[i], b = vec[j];
+  vec[i] = a + b;
+  vec[j] = a - b;
+}
+
+// 'N'-basis contraction step: in [H][4][L] -> out [H][2][L]; t enumerates (h, l).
+DMB_HD void dmb_contract_elem(uint64_t t, const double* __restrict__ in, double* __restrict__ out,
+                              uint64_t L, double n0, double n1, double n2) {
+  const uint64_t h = t / L, l = t - h * L;
+  const double* src = in + h * 4 * L + l;
+  out[h * 2 * L + l] = src[0];
+  out[h * 2 * L + L + l] = n0 * src[L] + n1 * src[2 * L] + n2 * src[3 * L];
+}
+
+// Pauli -> matrix basis, one digit: [I,X,Y,Z] -> [I+Z, X-iY, X+iY, I-Z]
+// (dm_simulator.py:1223-1245).  t enumerates the 4-vectors of digit position `pos`.
+// `first` != 0 reads the real state, otherwise the complex work buffer in place.
+DMB_HD void dmb_tomatrix_digit(uint64_t t, int pos, int first, const double* __restrict__ state,
+                               dmb_d2* work) {
+  const int sh = 2 * pos;
+  const uint64_t low = t & ((1ull << sh) - 1ull);
+  const uint64_t base = ((t >> sh) << (sh + 2)) | low;
+  const uint64_t st = 1ull << sh;
+  dmb_d2 a[4];
+  for (int d = 0; d < 4; ++d) {
+    if (first) { a[d].x = state[base + d * st]; a[d].y = 0.0; }
+    else a[d] = work[base + d * st];
+  }
+  dmb_d2 r0, r1, r2, r3;
+  r0.x = a[0].x + a[3].x; r0.y = a[0].y + a[3].y;
+  r1.x = a[1].x + a[2].y; r1.y = a[1].y - a[2].x;     // X - iY
+  r2.x = a[1].x - a[2].y; r2.y = a[1].y + a[2].x;     // X + iY
+  r3.x = a[0].x - a[3].x; r3.y = a[0].y - a[3].y;
+  work[base] = r0; work[base + st] = r1; work[base + 2 * st] = r2; work[base + 3 * st] = r3;
+}
+
+// Final scatter: out[row][col] = work[interleave(row, col)], digit mu = 2*rowbit + colbit
+// (dm_simulator.py:1229-1253).  t = row * 2^n + col.
+DMB_HD void dmb_tomatrix_scatter(uint64_t t, int n, const dmb_d2* __restrict__ work, dmb_d2* out) {
+  const uint64_t row = t >> n, col = t & ((1ull << n) - 1ull);
+  uint64_t idx = 0;
+  for (int b = 0; b < n; ++b)
+    idx |= (((row >> b) & 1ull) << (2 * b + 1)) | (((col >> b) & 1ull) << (2 * b));
+  out[t] = work[idx];
+}

@@ -1,0 +1,463 @@
+// dmb200.cu -- libdmb200.so: CUDA kernels (sm_100a) + the C ABI declared in include/dmb200.h.
+//
+// Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+//             -Iinclude qiskit-aakash_b200/csrc/dmb200.cu -o qiskit-aakash_b200/libdmb200.so
+//
+// Hot kernel: k_tile_pass -- one HBM round trip of the Pauli-coefficient vector per launch,
+// with up to DMB_MAX_OPS fused two-digit ops (pre-multiplied single-qubit maps + CNOT / TSP
+// CNOT / diagonal mask / digit swap) applied to each 4^K-coefficient tile while it sits in
+// shared memory.  HBM-bound by design: 16 algorithmic bytes per coefficient per launch.
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "dm_device.h"
+
+// ---------------------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(const char* what, const char* detail = nullptr) {
+  g_err = what;
+  if (detail) { g_err += ": "; g_err += detail; }
+  return 1;
+}
+
+#define CU_TRY(expr)                                                        \
+  do {                                                                      \
+    cudaError_t e_ = (expr);                                                \
+    if (e_ != cudaSuccess) return fail(#expr, cudaGetErrorString(e_));      \
+  } while (0)
+
+struct dmb_ctx {
+  int device;
+  cudaStream_t stream;
+  dmb_stats stats;
+  int tile_variant;
+  int sm_count;
+  double* d_scratch;        // small device scratch (gathers, reduction partials)
+  double* h_scratch;        // pinned host mirror
+  uint64_t* d_idx;
+  size_t scratch_elems;
+};
+
+static const size_t kScratchElems = 1 << 16;
+
+// ---------------------------------------------------------------------------------------
+// tile pass, variant 0: register-staged 128-bit loads/stores, one tile per CTA iteration
+// ---------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(DMB_TILE_THREADS, (K == 6 ? 3 : 1))
+k_tile_pass(double* __restrict__ state, const __grid_constant__ dmb_pass P, uint64_t n_tiles) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int MAXPAIRS = ((1 << (2 * K - 1)) + DMB_TILE_THREADS - 1) / DMB_TILE_THREADS;
+  const int t = threadIdx.x;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    double* gtile = state + dmb_tile_base(tile, P.tile_digit, K);
+    dmb_tile_load_thread<MAXPAIRS>(t, gtile, smem, P.tile_digit, K);
+    __syncthreads();
+    for (int i = 0; i < P.n_ops; ++i) {
+      dmb_tile_op_thread(t, P.ops[i], smem, K);
+      __syncthreads();
+    }
+    dmb_tile_store_thread<MAXPAIRS>(t, gtile, smem, P.tile_digit, K);
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// element-wise kernels
+// ---------------------------------------------------------------------------------------
+__global__ void k_init_product(double* __restrict__ state, uint64_t count, const __grid_constant__ dmb_init_params p) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+    state[i] = dmb_init_value(i, p);
+}
+
+__global__ void k_marginal(const double* __restrict__ state, double* __restrict__ out, uint64_t count,
+                           const __grid_constant__ dmb_marginal_params p) {
+  for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < count; c += (uint64_t)gridDim.x * blockDim.x)
+    out[c] = dmb_marginal_value(c, state, p);
+}
+
+__global__ void k_fwht_stage(double* vec, uint64_t pairs, int stage) {
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < pairs; t += (uint64_t)gridDim.x * blockDim.x)
+    dmb_fwht_pair(t, stage, vec);
+}
+
+// all stages of a <= 2^11-point transform (or the low 11 stages of a larger one) in shared memory
+__global__ void __launch_bounds__(1024) k_fwht_smem(double* vec, int n_stages) {
+  __shared__ double s[2048];
+  const uint64_t base = (uint64_t)blockIdx.x << n_stages;
+  const uint32_t len = 1u << n_stages;
+  for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) s[i] = vec[base + i];
+  __syncthreads();
+  for (int st = 0; st < n_stages; ++st) {
+    for (uint32_t t = threadIdx.x; t < len / 2; t += blockDim.x) dmb_fwht_pair(t, st, s);
+    __syncthreads();
+  }
+  for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) vec[base + i] = s[i];
+}
+
+__global__ void k_contract_digit(const double* __restrict__ in, double* __restrict__ out, uint64_t count,
+                                 uint64_t L, double n0, double n1, double n2) {
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < count; t += (uint64_t)gridDim.x * blockDim.x)
+    dmb_contract_elem(t, in, out, L, n0, n1, n2);
+}
+
+__global__ void k_gather(const double* __restrict__ state, const uint64_t* __restrict__ idx, size_t k,
+                         double* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < k; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = state[idx[i]];
+}
+
+__global__ void k_tomatrix_digit(const double* __restrict__ state, dmb_d2* work, uint64_t count, int pos, int first) {
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < count; t += (uint64_t)gridDim.x * blockDim.x)
+    dmb_tomatrix_digit(t, pos, first, state, work);
+}
+
+__global__ void k_tomatrix_scatter(const dmb_d2* __restrict__ work, dmb_d2* __restrict__ out, uint64_t count, int n) {
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < count; t += (uint64_t)gridDim.x * blockDim.x)
+    dmb_tomatrix_scatter(t, n, work, out);
+}
+
+__global__ void k_chop(double* state, uint64_t count, double thr) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double x = state[i];
+    if (fabs(x) < thr) state[i] = 0.0;
+  }
+}
+
+// deterministic two-stage dot product: fixed grid, fixed per-thread order, tree in the block
+__global__ void __launch_bounds__(256) k_dot_partial(const double* __restrict__ a, const double* __restrict__ b,
+                                                     uint64_t count, double* __restrict__ partial) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+    acc += a[i] * b[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+// ---------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------
+static inline unsigned grid_for(uint64_t count, int block, int sm_count) {
+  uint64_t g = (count + block - 1) / block;
+  const uint64_t cap = (uint64_t)sm_count * 32;
+  if (g > cap) g = cap;
+  if (g == 0) g = 1;
+  return (unsigned)g;
+}
+
+template <int K>
+static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass& P) {
+  const uint64_t n_tiles = 1ull << (n_bits - 2 * K);
+  const size_t smem = sizeof(double) << (2 * K);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU_TRY(cudaFuncSetAttribute(k_tile_pass<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const uint64_t grid = n_tiles < 0x7fffffffull ? n_tiles : 0x7fffffffull;
+  k_tile_pass<K><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, P, n_tiles);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int validate_pass(const dmb_pass& P, int n_bits) {
+  const int K = P.n_tile_digits;
+  if (K < 2 || K > DMB_MAX_TILE_DIGITS) return fail("dmb_apply_passes", "n_tile_digits out of range");
+  if (2 * K > n_bits) return fail("dmb_apply_passes", "tile larger than the state");
+  if (P.n_ops < 0 || P.n_ops > DMB_MAX_OPS) return fail("dmb_apply_passes", "n_ops out of range");
+  if (P.tile_digit[0] != 0) return fail("dmb_apply_passes", "tile_digit[0] must be 0");
+  for (int j = 0; j < K; ++j) {
+    if (j && P.tile_digit[j] <= P.tile_digit[j - 1]) return fail("dmb_apply_passes", "tile digits not ascending");
+    if (2 * P.tile_digit[j] + 1 >= n_bits) return fail("dmb_apply_passes", "tile digit outside the state");
+  }
+  for (int i = 0; i < P.n_ops; ++i) {
+    const dmb_op& op = P.ops[i];
+    if (op.kind < DMB_OP_MATS || op.kind > DMB_OP_SWAP) return fail("dmb_apply_passes", "unknown op kind");
+    if (op.a < 0 || op.a >= K || op.b < 0 || op.b >= K || op.a == op.b)
+      return fail("dmb_apply_passes", "op digits invalid");
+    unsigned seen = (1u << op.a) | (1u << op.b);
+    for (int m = 0; m < K - 2; ++m) {
+      if (op.fd[m] < 0 || op.fd[m] >= K || (seen >> op.fd[m]) & 1u)
+        return fail("dmb_apply_passes", "op free-digit list is not a permutation");
+      seen |= 1u << op.fd[m];
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int dmb_abi_version(void) { return DMB_ABI_VERSION; }
+size_t dmb_sizeof_op(void) { return sizeof(dmb_op); }
+size_t dmb_sizeof_pass(void) { return sizeof(dmb_pass); }
+const char* dmb_last_error(void) { return g_err.c_str(); }
+
+int dmb_create(int device, dmb_ctx** out) {
+  if (!out) return fail("dmb_create", "null out pointer");
+  int count = 0;
+  CU_TRY(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail("dmb_create", "no such CUDA device");
+  CU_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("dmb_create", "libdmb200 is built for sm_100a (B200) only");
+  dmb_ctx* ctx = new dmb_ctx();
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->device = device;
+  ctx->stream = 0;
+  ctx->tile_variant = 0;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->scratch_elems = kScratchElems;
+  CU_TRY(cudaMalloc(&ctx->d_scratch, kScratchElems * sizeof(double)));
+  CU_TRY(cudaMalloc(&ctx->d_idx, kScratchElems * sizeof(uint64_t)));
+  CU_TRY(cudaMallocHost(&ctx->h_scratch, kScratchElems * sizeof(double)));
+  *out = ctx;
+  return 0;
+}
+
+int dmb_destroy(dmb_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaFree(ctx->d_scratch);
+  cudaFree(ctx->d_idx);
+  cudaFreeHost(ctx->h_scratch);
+  delete ctx;
+  return 0;
+}
+
+int dmb_set_stream(dmb_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return fail("dmb_set_stream", "null context");
+  ctx->stream = (cudaStream_t)cuda_stream;
+  return 0;
+}
+
+int dmb_sync(dmb_ctx* ctx) {
+  if (!ctx) return fail("dmb_sync", "null context");
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out) {
+  if (!ctx || !out) return fail("dmb_get_stats", "null argument");
+  *out = ctx->stats;
+  return 0;
+}
+
+int dmb_reset_stats(dmb_ctx* ctx) {
+  if (!ctx) return fail("dmb_reset_stats", "null context");
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  return 0;
+}
+
+int dmb_set_tile_variant(dmb_ctx* ctx, int variant) {
+  if (!ctx) return fail("dmb_set_tile_variant", "null context");
+  if (variant != 0) return fail("dmb_set_tile_variant", "only variant 0 is built in this version");
+  ctx->tile_variant = variant;
+  return 0;
+}
+
+int dmb_init_product(dmb_ctx* ctx, double* state, int n_bits, uint64_t rank_bits, int n_qubits,
+                     const int32_t* hi, const int32_t* lo, const double* v, double scale) {
+  if (!ctx || !state || !hi || !lo || !v) return fail("dmb_init_product", "null argument");
+  if (n_qubits < 1 || n_qubits > DMB_MAX_QUBITS) return fail("dmb_init_product", "n_qubits out of range");
+  if (n_bits < 0 || n_bits > 62) return fail("dmb_init_product", "n_bits out of range");
+  CU_TRY(cudaSetDevice(ctx->device));
+  dmb_init_params p;
+  memset(&p, 0, sizeof(p));
+  p.map.n_qubits = n_qubits;
+  for (int q = 0; q < n_qubits; ++q) {
+    p.map.hi[q] = hi[q];
+    p.map.lo[q] = lo[q];
+    for (int d = 0; d < 4; ++d) p.v[q][d] = v[4 * q + d];
+  }
+  p.scale = scale;
+  p.rank_bits = rank_bits;
+  p.n_bits = n_bits;
+  const uint64_t count = 1ull << n_bits;
+  k_init_product<<<grid_for(count, 256, ctx->sm_count), 256, 0, ctx->stream>>>(state, count, p);
+  CU_TRY(cudaGetLastError());
+  ctx->stats.other_launches++;
+  return 0;
+}
+
+int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* passes, size_t n_passes) {
+  if (!ctx || !state || (!passes && n_passes)) return fail("dmb_apply_passes", "null argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  for (size_t i = 0; i < n_passes; ++i) {
+    const dmb_pass& P = passes[i];
+    if (validate_pass(P, n_bits)) return 1;
+    int rc = 0;
+    switch (P.n_tile_digits) {
+      case 2: rc = launch_tile_pass<2>(ctx, state, n_bits, P); break;
+      case 3: rc = launch_tile_pass<3>(ctx, state, n_bits, P); break;
+      case 4: rc = launch_tile_pass<4>(ctx, state, n_bits, P); break;
+      case 5: rc = launch_tile_pass<5>(ctx, state, n_bits, P); break;
+      case 6:
+        rc = launch_tile_pass<6>(ctx, state, n_bits, P);
+        break;
+      default: return fail("dmb_apply_passes", "unsupported tile size");
+    }
+    if (rc) return rc;
+    ctx->stats.tile_pass_launches++;
+    ctx->stats.fused_ops += (uint64_t)P.n_ops;
+    ctx->stats.state_bytes_moved += 16ull << n_bits;
+  }
+  return 0;
+}
+
+int dmb_marginal(dmb_ctx* ctx, const double* state, int n_bits, uint64_t rank_bits, int n_qubits,
+                 const int32_t* hi, const int32_t* lo, const double* wt, double* out) {
+  if (!ctx || !state || !hi || !lo || !wt || !out) return fail("dmb_marginal", "null argument");
+  if (n_qubits < 1 || n_qubits > DMB_MAX_QUBITS) return fail("dmb_marginal", "n_qubits out of range");
+  CU_TRY(cudaSetDevice(ctx->device));
+  dmb_marginal_params p;
+  memset(&p, 0, sizeof(p));
+  p.map.n_qubits = n_qubits;
+  p.rank_bits = rank_bits;
+  p.n_bits = n_bits;
+  for (int k = 0; k < n_qubits; ++k) {
+    p.map.hi[k] = hi[k];
+    p.map.lo[k] = lo[k];
+    bool multi = false;
+    for (int cb = 0; cb < 2; ++cb) {
+      int nz = 0, last = 0;
+      for (int d = 0; d < 4; ++d) {
+        const double w = wt[(k * 2 + cb) * 4 + d];
+        p.wt[k][cb][d] = w;
+        if (w != 0.0) { ++nz; last = d; }
+      }
+      p.simple_digit[k][cb] = (int8_t)last;
+      if (nz > 1) multi = true;
+    }
+    if (multi) {
+      if (p.n_multi >= DMB_MAX_MULTI) return fail("dmb_marginal", "too many multi-weight qubits");
+      p.simple_digit[k][0] = p.simple_digit[k][1] = -1;
+      p.multi[p.n_multi++] = k;
+    }
+  }
+  const uint64_t count = 1ull << n_qubits;
+  k_marginal<<<grid_for(count, 256, ctx->sm_count), 256, 0, ctx->stream>>>(state, out, count, p);
+  CU_TRY(cudaGetLastError());
+  ctx->stats.other_launches++;
+  return 0;
+}
+
+int dmb_fwht(dmb_ctx* ctx, double* vec, int n_qubits) {
+  if (!ctx || !vec) return fail("dmb_fwht", "null argument");
+  if (n_qubits < 0 || n_qubits > 40) return fail("dmb_fwht", "n_qubits out of range");
+  CU_TRY(cudaSetDevice(ctx->device));
+  const int low = n_qubits < 11 ? n_qubits : 11;
+  if (low > 0) {
+    k_fwht_smem<<<(unsigned)(1ull << (n_qubits - low)), 1024, 0, ctx->stream>>>(vec, low);
+    CU_TRY(cudaGetLastError());
+    ctx->stats.other_launches++;
+  }
+  const uint64_t pairs = (1ull << n_qubits) >> 1;
+  for (int st = low; st < n_qubits; ++st) {
+    k_fwht_stage<<<grid_for(pairs, 256, ctx->sm_count), 256, 0, ctx->stream>>>(vec, pairs, st);
+    CU_TRY(cudaGetLastError());
+    ctx->stats.other_launches++;
+  }
+  return 0;
+}
+
+int dmb_contract_digit(dmb_ctx* ctx, const double* in, double* out, uint64_t H, uint64_t L, const double nv[3]) {
+  if (!ctx || !in || !out || !nv) return fail("dmb_contract_digit", "null argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  const uint64_t count = H * L;
+  k_contract_digit<<<grid_for(count, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, out, count, L, nv[0], nv[1], nv[2]);
+  CU_TRY(cudaGetLastError());
+  ctx->stats.other_launches++;
+  return 0;
+}
+
+int dmb_read_coeffs(dmb_ctx* ctx, const double* state, const uint64_t* idx, size_t k, double* out_host) {
+  if (!ctx || !state || !idx || !out_host) return fail("dmb_read_coeffs", "null argument");
+  if (k > ctx->scratch_elems) return fail("dmb_read_coeffs", "too many coefficients in one call");
+  if (k == 0) return 0;
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaMemcpyAsync(ctx->d_idx, idx, k * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  k_gather<<<grid_for(k, 256, ctx->sm_count), 256, 0, ctx->stream>>>(state, ctx->d_idx, k, ctx->d_scratch);
+  CU_TRY(cudaGetLastError());
+  ctx->stats.other_launches++;
+  CU_TRY(cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(out_host, ctx->h_scratch, k * sizeof(double));
+  return 0;
+}
+
+int dmb_to_matrix(dmb_ctx* ctx, const double* state, int n_qubits, double* work, double* out) {
+  if (!ctx || !state || !work || !out) return fail("dmb_to_matrix", "null argument");
+  if (n_qubits < 1 || n_qubits > 15) return fail("dmb_to_matrix", "n_qubits out of range");
+  CU_TRY(cudaSetDevice(ctx->device));
+  const uint64_t vecs = 1ull << (2 * n_qubits - 2);
+  for (int pos = 0; pos < n_qubits; ++pos) {
+    k_tomatrix_digit<<<grid_for(vecs, 256, ctx->sm_count), 256, 0, ctx->stream>>>(state, (dmb_d2*)work, vecs, pos,
+                                                                               pos == 0 ? 1 : 0);
+    CU_TRY(cudaGetLastError());
+    ctx->stats.other_launches++;
+  }
+  const uint64_t count = 1ull << (2 * n_qubits);
+  k_tomatrix_scatter<<<grid_for(count, 256, ctx->sm_count), 256, 0, ctx->stream>>>((const dmb_d2*)work, (dmb_d2*)out,
+                                                                                 count, n_qubits);
+  CU_TRY(cudaGetLastError());
+  ctx->stats.other_launches++;
+  return 0;
+}
+
+int dmb_dot(dmb_ctx* ctx, const double* a, const double* b, uint64_t count, double* out_host) {
+  if (!ctx || !a || !b || !out_host) return fail("dmb_dot", "null argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  const unsigned blocks = 1024;
+  k_dot_partial<<<blocks, 256, 0, ctx->stream>>>(a, b, count, ctx->d_scratch);
+  CU_TRY(cudaGetLastError());
+  ctx->stats.other_launches++;
+  CU_TRY(cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, blocks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  double acc = 0.0;
+  for (unsigned i = 0; i < blocks; ++i) acc += ctx->h_scratch[i];
+  *out_host = acc;
+  return 0;
+}
+
+int dmb_chop(dmb_ctx* ctx, double* state, uint64_t count, double thr) {
+  if (!ctx || !state) return fail("dmb_chop", "null argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  k_chop<<<grid_for(count, 256, ctx->sm_count), 256, 0, ctx->stream>>>(state, count, thr);
+  CU_TRY(cudaGetLastError());
+  ctx->stats.other_launches++;
+  return 0;
+}
+
+int dmb_upload(dmb_ctx* ctx, double* state, const double* host, uint64_t offset, uint64_t count) {
+  if (!ctx || !state || !host) return fail("dmb_upload", "null argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaMemcpyAsync(state + offset, host, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int dmb_download(dmb_ctx* ctx, const double* state, double* host, uint64_t offset, uint64_t count) {
+  if (!ctx || !state || !host) return fail("dmb_download", "null argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaMemcpyAsync(host, state + offset, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,371 @@
+"""Device-resident Pauli-coefficient state and the lazy op queue in front of the CUDA kernels.
+
+``PauliEngine`` owns what the reference keeps in ``DmSimulatorPy._densitymatrix``
+(``dm_simulator.py:61-68``): a float64 vector of 4^n Pauli coefficients, here a PyTorch
+CUDA tensor (PyTorch is used for buffer ownership and streams only).  Its methods mirror
+the reference's state-mutating methods one to one but are *lazy*:
+
+* every single-qubit map -- u1/u3 (a6-a8), per-level memory noise (a11), projective
+  measurements (a19, a22), reset (a24) -- is multiplied on the host into a pending 4x4
+  matrix of its qubit (exact: single-qubit maps on different qubits commute, and all of
+  them are linear maps on one base-4 digit);
+* a two-qubit op (CNOT a9/a10, Bell mask a23) takes the pending matrices of its two qubits
+  with it and is appended to a queue;
+* anything that must *see* the state (readouts, final state) first flushes: the queue is
+  packed into tile passes by ``schedule.build_passes`` and executed by
+  ``dmb_apply_passes`` -- one HBM round trip per pass instead of the reference's ~6 sweeps
+  per U3, ~2 per CNOT and n per noise level.
+
+Layout: qubit q sits at digit position ``pos[q]`` (reference layout: n-1-q, qubit 0 most
+significant).  A 1-qubit register is padded with one phantom identity digit so that every
+state has at least two digit positions (the kernels work on digit pairs).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi, schedule
+from .exceptions import BasicAerError
+
+I4 = np.eye(4)
+
+
+# --------------------------------------------------------------------------------------
+# single-qubit maps on (I, X, Y, Z)
+# --------------------------------------------------------------------------------------
+
+_AXIS_PAIR = {"rz": (1, 2), "ry": (3, 1), "rx": (2, 3)}
+
+
+def rotation_matrix(axis, angle, err):
+    """``rot_gate_dm_matrix`` (``basicaertools.py:93-126``) as a 4x4 matrix:
+    c = r cos(angle+delta), s = r sin(angle+delta), (r, delta) = err."""
+    c = err[0] * np.cos(angle + err[1])
+    s = err[0] * np.sin(angle + err[1])
+    k0, k1 = _AXIS_PAIR[axis]
+    m = np.eye(4)
+    m[k0, k0], m[k0, k1] = c, -s
+    m[k1, k1], m[k1, k0] = c, s
+    return m
+
+
+def gate_matrix(name, params, rotation_error):
+    """u3(theta,phi,lam) = rz(lam), ry(theta), rz(phi) applied in that order; u1(lam) = rz(lam)
+    (``single_gate_dm_matrix``, ``basicaertools.py:69-90``)."""
+    p = list(map(float, params))
+    if name in ("U", "u3"):
+        seq = (("rz", p[2]), ("ry", p[0]), ("rz", p[1]))
+    elif name == "u1":
+        seq = (("rz", p[0]),)
+    else:
+        raise BasicAerError("Gate is not among the valid types: %s" % name)
+    m = np.eye(4)
+    for axis, ang in seq:
+        m = rotation_matrix(axis, ang, rotation_error[axis]) @ m
+    return m
+
+
+def memory_noise_matrix(f, p, g):
+    """``_add_decoherence_and_amp_decay`` (``dm_simulator.py:397-425``) on one qubit."""
+    off = np.sqrt(g) * f
+    m = np.diag([1.0, off, off, g])
+    m[3, 0] = (1 - g) * (2 * p - 1)
+    return m
+
+
+def measure_axis_matrix(basis, err):
+    """``_add_qasm_measure_X/Y/Z`` (``dm_simulator.py:574-664``)."""
+    m = np.zeros((4, 4))
+    m[0, 0] = 1.0
+    k = {"X": 1, "Y": 2, "Z": 3}[basis]
+    m[k, k] = err
+    return m
+
+
+def measure_n_matrix(nvec, err):
+    """``_add_qasm_measure_N`` (``dm_simulator.py:666-704``)."""
+    nvec = np.asarray(nvec, dtype=float)
+    m = np.zeros((4, 4))
+    m[0, 0] = 1.0
+    m[1:, 1:] = np.outer(nvec, nvec * err)
+    return m
+
+
+def reset_matrix():
+    """``_add_qasm_reset`` (``dm_simulator.py:810-823``): X = Y = 0, Z = I."""
+    m = np.zeros((4, 4))
+    m[0, 0] = 1.0
+    m[3, 0] = 1.0
+    return m
+
+
+def cx_coefficients(tsp):
+    """(c, s, c2, s2, cs) of ``cx_gate_dm_matrix`` (``basicaertools.py:329-336``)."""
+    cav, e1 = float(tsp[0]), float(tsp[1])
+    c2av = 4 * cav - 3
+    c = cav * np.cos(e1)
+    s = cav * np.sin(e1)
+    c2 = 0.5 * (1 + c2av * np.cos(2 * e1))
+    s2 = 0.5 * (1 - c2av * np.cos(2 * e1))
+    cs = c2av * np.sin(e1) * np.cos(e1)
+    return c, s, c2, s2, cs
+
+
+# --------------------------------------------------------------------------------------
+# buffers
+# --------------------------------------------------------------------------------------
+
+class TorchCudaAllocator:
+    """Device buffers are PyTorch CUDA tensors; kernels run on torch's current stream."""
+
+    def __init__(self, device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise capi.DmbError("no CUDA device: the dm_simulator B200 backend needs a GPU (no CPU fallback)")
+        self.torch = torch
+        self.device = torch.device("cuda", int(device))
+        self.index = int(device)
+
+    def empty(self, count):
+        return self.torch.empty(int(count), dtype=self.torch.float64, device=self.device)
+
+    def ptr(self, buf):
+        return buf.data_ptr()
+
+    def stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def pinned(self, count):
+        t = self.torch.empty(int(count), dtype=self.torch.float64, pin_memory=True)
+        return t, t.numpy()
+
+
+# --------------------------------------------------------------------------------------
+# engine
+# --------------------------------------------------------------------------------------
+
+class PauliEngine:
+    def __init__(self, n_qubits, lib=None, allocator=None, device=0, max_ops_per_pass=None):
+        if n_qubits < 1 or n_qubits > capi.MAX_QUBITS:
+            raise BasicAerError("number of qubits out of range: %d" % n_qubits)
+        self.n = int(n_qubits)
+        self.nd = max(self.n, 2)                 # digit positions incl. phantom padding
+        self.n_bits = 2 * self.nd
+        self.size = 4 ** self.nd
+        self.lib = lib if lib is not None else capi.load_library()
+        self.alloc = allocator if allocator is not None else TorchCudaAllocator(device)
+        self.ctx = capi.Context(self.lib, getattr(self.alloc, "index", 0))
+        self.ctx.set_stream(self.alloc.stream())
+        self.state = self.alloc.empty(self.size)
+        self.pos = [self.n - 1 - q for q in range(self.n)]     # qubit -> digit position
+        self.pending = [None] * self.n
+        self.queue = []
+        self.max_ops_per_pass = max_ops_per_pass or capi.MAX_OPS
+        self.passes_run = 0
+        self.h2d_bytes = 0
+
+    # -- helpers -----------------------------------------------------------------------
+    @property
+    def sptr(self):
+        return self.alloc.ptr(self.state)
+
+    def _hi_lo(self):
+        hi = [2 * self.pos[q] + 1 for q in range(self.n)]
+        lo = [2 * self.pos[q] for q in range(self.n)]
+        return hi, lo
+
+    # -- a4: initial states --------------------------------------------------------------
+    def init_product(self, vectors, scale):
+        """state = scale * kron_q vectors[q]  (``_initialize_densitymatrix``, ``:284-349``)."""
+        hi, lo = self._hi_lo()
+        v = [list(map(float, vec)) for vec in vectors]
+        if self.nd > self.n:                     # phantom digit: I component only
+            hi.append(2 * self.n + 1)
+            lo.append(2 * self.n)
+            v.append([1.0, 0.0, 0.0, 0.0])
+        self.ctx.init_product(self.sptr, self.n_bits, 0, hi, lo, v, scale)
+        self.pending = [None] * self.n
+        self.queue = []
+
+    def upload(self, vec):
+        vec = np.ascontiguousarray(vec, dtype=np.float64).reshape(-1)
+        if vec.size != 4 ** self.n:
+            raise BasicAerError("Wrong input stored density matrix")
+        if self.nd > self.n:
+            full = np.zeros(self.size)
+            full[:vec.size] = vec
+            vec = full
+        self.ctx.upload(self.sptr, vec)
+        self.h2d_bytes += vec.nbytes
+        self.pending = [None] * self.n
+        self.queue = []
+
+    # -- lazy op queue -------------------------------------------------------------------
+    def apply_1q(self, q, m):
+        """Left-multiply a single-qubit map onto qubit q's pending matrix."""
+        cur = self.pending[q]
+        self.pending[q] = np.array(m, dtype=float) if cur is None else np.asarray(m, dtype=float) @ cur
+
+    def apply_1q_all(self, m):
+        for q in range(self.n):
+            self.apply_1q(q, m)
+
+    def _take(self, q):
+        m = self.pending[q]
+        self.pending[q] = None
+        return m
+
+    def apply_cx(self, ctrl, tgt, tsp=(1.0, 0.0)):
+        """``_add_unitary_two`` / ``cx_gate_dm_matrix`` (``dm_simulator.py:386-395``)."""
+        if ctrl == tgt or not (0 <= ctrl < self.n) or not (0 <= tgt < self.n):
+            raise BasicAerError("Qubit Labels out of bound in CX Gate")
+        if float(tsp[0]) == 1.0 and float(tsp[1]) == 0.0:
+            kind, coef = capi.OP_CX, None
+        else:
+            kind, coef = capi.OP_CX_TSP, cx_coefficients(tsp)
+        self.queue.append(("2q", kind, ctrl, tgt, self._take(ctrl), self._take(tgt), coef))
+
+    def apply_diag2(self, qa, qb, weights):
+        """v[digit(qa)][digit(qb)] *= weights[i][j] (Bell mask, ``dm_simulator.py:749-756``)."""
+        self.queue.append(("2q", capi.OP_DIAG2, qa, qb, self._take(qa), self._take(qb),
+                           np.asarray(weights, dtype=float).reshape(16)))
+
+    def device_ops(self, final=True):
+        """Queue (+ pending matrices if ``final``) -> list of schedule.DevOp on digit positions."""
+        ops = []
+        for _, kind, qa, qb, pa, pb, coef in self.queue:
+            ops.append(schedule.DevOp(kind, self.pos[qa], self.pos[qb], pa, pb, coef))
+        if final:
+            left = sorted((self.pos[q], q) for q in range(self.n) if self.pending[q] is not None)
+            for i in range(0, len(left) - 1, 2):
+                (da, qa), (db, qb) = left[i], left[i + 1]
+                ops.append(schedule.DevOp(capi.OP_MATS, da, db, self.pending[qa], self.pending[qb]))
+            if len(left) % 2:
+                da, qa = left[-1]
+                ops.append(schedule.DevOp(capi.OP_MATS, da, None, self.pending[qa], None))
+        return ops
+
+    def plan(self):
+        """Schedule everything outstanding into passes (does not execute)."""
+        ops = self.device_ops(final=True)
+        if not ops:
+            return np.zeros(0, dtype=capi.PASS_DTYPE)
+        return schedule.build_passes(ops, self.nd, max_ops=self.max_ops_per_pass)
+
+    def flush(self):
+        passes = self.plan()
+        self.queue = []
+        self.pending = [None] * self.n
+        self.run_passes(passes)
+
+    def run_passes(self, passes):
+        if len(passes):
+            self.ctx.set_stream(self.alloc.stream())
+            self.ctx.apply_passes(self.sptr, self.n_bits, passes)
+            self.passes_run += len(passes)
+            self.h2d_bytes += passes.nbytes
+
+    # -- readouts (all flush first) --------------------------------------------------------
+    def marginal_probabilities(self, basis, err):
+        """2^n probabilities of ``_add_ensemble_measure`` for basis X/Y/Z (``:427-481``):
+        I/B-marginal gather with weights err^wt(c), then a Walsh-Hadamard transform.
+        Entry r has bit n-1-q = outcome of qubit q (= the reference's key order)."""
+        self.flush()
+        b = {"X": 1, "Y": 2, "Z": 3}[basis]
+        n = self.n
+        hi, lo, wt = [], [], np.zeros((n, 2, 4))
+        for k in range(n):                       # result bit k <-> qubit n-1-k
+            q = n - 1 - k
+            hi.append(2 * self.pos[q] + 1)
+            lo.append(2 * self.pos[q])
+            wt[k, 0, 0] = 1.0
+            wt[k, 1, b] = err
+        out = self.alloc.empty(2 ** n)
+        self.ctx.marginal(self.sptr, self.n_bits, 0, hi, lo, wt, self.alloc.ptr(out))
+        self.ctx.fwht(self.alloc.ptr(out), n)
+        host = np.empty(2 ** n)
+        self.ctx.download(self.alloc.ptr(out), host)
+        return host
+
+    def n_basis_probabilities(self, nvec, err):
+        """Basis 'N' of ``_add_ensemble_measure`` (``:457-462``): contract every digit
+        (I, X, Y, Z) -> (I, err * n.(X,Y,Z)), then the same Walsh-Hadamard transform."""
+        self.flush()
+        self._require_reference_layout()
+        n = self.n
+        nv = np.asarray(nvec, dtype=float) * err
+        src, src_ptr = self.state, self.sptr
+        for d in range(n):                       # digit d: [H = 4^(nd-1-d)][4][L = 2^d]
+            H, L = 4 ** (self.nd - 1 - d), 2 ** d
+            dst = self.alloc.empty(H * 2 * L)
+            self.ctx.contract_digit(src_ptr, self.alloc.ptr(dst), H, L, nv)
+            src, src_ptr = dst, self.alloc.ptr(dst)
+        # phantom digits (if any) are the leading axis with only index 0 populated: the first
+        # 2^n entries are the marginal
+        self.ctx.fwht(src_ptr, n)
+        host = np.empty(2 ** n)
+        self.ctx.download(src_ptr, host)
+        return host
+
+    def read_coefficients(self, digit_tuples):
+        """Coefficients a[p_0, ..., p_{n-1}] (tuple index = qubit) -> numpy array."""
+        self.flush()
+        idx = []
+        for tup in digit_tuples:
+            flat = 0
+            for q, p in enumerate(tup):
+                flat |= int(p) << (2 * self.pos[q])
+            idx.append(flat)
+        return self.ctx.read_coeffs(self.sptr, idx)
+
+    def _require_reference_layout(self):
+        if self.pos != [self.n - 1 - q for q in range(self.n)]:
+            raise BasicAerError("internal: state is not in the reference qubit order")
+
+    def download(self, out=None):
+        """Flat 4^n coefficient vector in the reference order (host numpy array)."""
+        self.flush()
+        self._require_reference_layout()
+        host = out if out is not None else np.empty(4 ** self.n)
+        self.ctx.download(self.sptr, host)
+        return host
+
+    def chop(self, thr):
+        self.flush()
+        self.ctx.chop(self.sptr, self.size, thr)
+
+    def to_matrix(self):
+        """``_compute_densitymatrix`` (``:1198-1255``) -> complex 2^n x 2^n numpy array."""
+        self.flush()
+        self._require_reference_layout()
+        n = self.n
+        if self.nd > n:
+            # 1-qubit register: convert on the first 4 coefficients (phantom digit is identity)
+            tmp = self.alloc.empty(4 ** n)
+            self.ctx.upload(self.alloc.ptr(tmp), self.ctx.read_coeffs(self.sptr, list(range(4 ** n))))
+            src_ptr = self.alloc.ptr(tmp)
+        else:
+            src_ptr = self.sptr
+        work = self.alloc.empty(2 * 4 ** n)
+        out = self.alloc.empty(2 * 4 ** n)
+        self.ctx.to_matrix(src_ptr, n, self.alloc.ptr(work), self.alloc.ptr(out))
+        host = np.empty(2 * 4 ** n)
+        self.ctx.download(self.alloc.ptr(out), host)
+        return host.view(np.complex128).reshape(2 ** n, 2 ** n)
+
+    def overlap_with(self, other_vec):
+        """dot(other, state) (``_state_overlap``, ``:1277-1282``, without the 2^n factor)."""
+        self.flush()
+        self._require_reference_layout()
+        other_vec = np.ascontiguousarray(other_vec, dtype=np.float64).reshape(-1)
+        if other_vec.size != 4 ** self.n:
+            raise BasicAerError("stored coefficients have the wrong length")
+        buf = self.alloc.empty(4 ** self.n)
+        self.ctx.upload(self.alloc.ptr(buf), other_vec)
+        return self.ctx.dot(self.alloc.ptr(buf), self.sptr, 4 ** self.n)
+
+    def sync(self):
+        self.ctx.sync()
+
+    def stats(self):
+        return self.ctx.stats()

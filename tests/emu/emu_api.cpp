@@ -1,0 +1,214 @@
+// TEST INFRASTRUCTURE ONLY -- CPU thread-by-thread emulation of the dmb200 kernels.
+//
+// Implements the C ABI of include/dmb200.h over HOST memory by running the very same
+// per-thread bodies (qiskit-aakash_b200/csrc/dm_device.h) that the CUDA kernels in
+// dmb200.cu wrap, one "thread" at a time, phase by phase.  It exists so that the index
+// arithmetic of the kernels (tile addressing, swizzle, lane mapping, Pauli-pair maths) and
+// the host-side scheduler can be unit-tested in the GPU-less build container.  It is built
+// into tests/emu/libdmb200_emu.so by tests/emu/build_emu.py and loaded only by the
+// `-m "not gpu"` tests through an explicit injection hook; the product never loads it.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "dm_device.h"
+
+static thread_local std::string g_err;
+static int fail(const char* what, const char* detail = nullptr) {
+  g_err = what;
+  if (detail) { g_err += ": "; g_err += detail; }
+  return 1;
+}
+
+struct dmb_ctx {
+  dmb_stats stats;
+};
+
+static int validate_pass(const dmb_pass& P, int n_bits) {
+  const int K = P.n_tile_digits;
+  if (K < 2 || K > DMB_MAX_TILE_DIGITS) return fail("dmb_apply_passes", "n_tile_digits out of range");
+  if (2 * K > n_bits) return fail("dmb_apply_passes", "tile larger than the state");
+  if (P.n_ops < 0 || P.n_ops > DMB_MAX_OPS) return fail("dmb_apply_passes", "n_ops out of range");
+  if (P.tile_digit[0] != 0) return fail("dmb_apply_passes", "tile_digit[0] must be 0");
+  for (int j = 0; j < K; ++j) {
+    if (j && P.tile_digit[j] <= P.tile_digit[j - 1]) return fail("dmb_apply_passes", "tile digits not ascending");
+    if (2 * P.tile_digit[j] + 1 >= n_bits) return fail("dmb_apply_passes", "tile digit outside the state");
+  }
+  for (int i = 0; i < P.n_ops; ++i) {
+    const dmb_op& op = P.ops[i];
+    if (op.kind < DMB_OP_MATS || op.kind > DMB_OP_SWAP) return fail("dmb_apply_passes", "unknown op kind");
+    if (op.a < 0 || op.a >= K || op.b < 0 || op.b >= K || op.a == op.b)
+      return fail("dmb_apply_passes", "op digits invalid");
+    unsigned seen = (1u << op.a) | (1u << op.b);
+    for (int m = 0; m < K - 2; ++m) {
+      if (op.fd[m] < 0 || op.fd[m] >= K || (seen >> op.fd[m]) & 1u)
+        return fail("dmb_apply_passes", "op free-digit list is not a permutation");
+      seen |= 1u << op.fd[m];
+    }
+  }
+  return 0;
+}
+
+template <int K>
+static void run_tile_pass(double* state, int n_bits, const dmb_pass& P) {
+  constexpr int MAXPAIRS = ((1 << (2 * K - 1)) + DMB_TILE_THREADS - 1) / DMB_TILE_THREADS;
+  const uint64_t n_tiles = 1ull << (n_bits - 2 * K);
+  alignas(16) static thread_local double smem[1 << 12];
+  for (uint64_t tile = 0; tile < n_tiles; ++tile) {
+    double* gtile = state + dmb_tile_base(tile, P.tile_digit, K);
+    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_tile_load_thread<MAXPAIRS>(t, gtile, smem, P.tile_digit, K);
+    for (int i = 0; i < P.n_ops; ++i)
+      for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_tile_op_thread(t, P.ops[i], smem, K);
+    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_tile_store_thread<MAXPAIRS>(t, gtile, smem, P.tile_digit, K);
+  }
+}
+
+extern "C" {
+
+int dmb_abi_version(void) { return DMB_ABI_VERSION; }
+size_t dmb_sizeof_op(void) { return sizeof(dmb_op); }
+size_t dmb_sizeof_pass(void) { return sizeof(dmb_pass); }
+const char* dmb_last_error(void) { return g_err.c_str(); }
+
+int dmb_create(int, dmb_ctx** out) {
+  if (!out) return fail("dmb_create", "null out pointer");
+  *out = new dmb_ctx();
+  memset(&(*out)->stats, 0, sizeof(dmb_stats));
+  return 0;
+}
+int dmb_destroy(dmb_ctx* ctx) { delete ctx; return 0; }
+int dmb_set_stream(dmb_ctx*, void*) { return 0; }
+int dmb_sync(dmb_ctx*) { return 0; }
+int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out) { *out = ctx->stats; return 0; }
+int dmb_reset_stats(dmb_ctx* ctx) { memset(&ctx->stats, 0, sizeof(dmb_stats)); return 0; }
+int dmb_set_tile_variant(dmb_ctx*, int variant) { return variant == 0 ? 0 : fail("dmb_set_tile_variant", "emu"); }
+
+int dmb_init_product(dmb_ctx* ctx, double* state, int n_bits, uint64_t rank_bits, int n_qubits,
+                     const int32_t* hi, const int32_t* lo, const double* v, double scale) {
+  if (n_qubits < 1 || n_qubits > DMB_MAX_QUBITS) return fail("dmb_init_product", "n_qubits out of range");
+  dmb_init_params p;
+  memset(&p, 0, sizeof(p));
+  p.map.n_qubits = n_qubits;
+  for (int q = 0; q < n_qubits; ++q) {
+    p.map.hi[q] = hi[q];
+    p.map.lo[q] = lo[q];
+    for (int d = 0; d < 4; ++d) p.v[q][d] = v[4 * q + d];
+  }
+  p.scale = scale;
+  p.rank_bits = rank_bits;
+  p.n_bits = n_bits;
+  for (uint64_t i = 0; i < (1ull << n_bits); ++i) state[i] = dmb_init_value(i, p);
+  ctx->stats.other_launches++;
+  return 0;
+}
+
+int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* passes, size_t n_passes) {
+  for (size_t i = 0; i < n_passes; ++i) {
+    const dmb_pass& P = passes[i];
+    if (validate_pass(P, n_bits)) return 1;
+    switch (P.n_tile_digits) {
+      case 2: run_tile_pass<2>(state, n_bits, P); break;
+      case 3: run_tile_pass<3>(state, n_bits, P); break;
+      case 4: run_tile_pass<4>(state, n_bits, P); break;
+      case 5: run_tile_pass<5>(state, n_bits, P); break;
+      case 6: run_tile_pass<6>(state, n_bits, P); break;
+      default: return fail("dmb_apply_passes", "unsupported tile size");
+    }
+    ctx->stats.tile_pass_launches++;
+    ctx->stats.fused_ops += (uint64_t)P.n_ops;
+    ctx->stats.state_bytes_moved += 16ull << n_bits;
+  }
+  return 0;
+}
+
+int dmb_marginal(dmb_ctx* ctx, const double* state, int n_bits, uint64_t rank_bits, int n_qubits,
+                 const int32_t* hi, const int32_t* lo, const double* wt, double* out) {
+  if (n_qubits < 1 || n_qubits > DMB_MAX_QUBITS) return fail("dmb_marginal", "n_qubits out of range");
+  dmb_marginal_params p;
+  memset(&p, 0, sizeof(p));
+  p.map.n_qubits = n_qubits;
+  p.rank_bits = rank_bits;
+  p.n_bits = n_bits;
+  for (int k = 0; k < n_qubits; ++k) {
+    p.map.hi[k] = hi[k];
+    p.map.lo[k] = lo[k];
+    bool multi = false;
+    for (int cb = 0; cb < 2; ++cb) {
+      int nz = 0, last = 0;
+      for (int d = 0; d < 4; ++d) {
+        const double w = wt[(k * 2 + cb) * 4 + d];
+        p.wt[k][cb][d] = w;
+        if (w != 0.0) { ++nz; last = d; }
+      }
+      p.simple_digit[k][cb] = (int8_t)last;
+      if (nz > 1) multi = true;
+    }
+    if (multi) {
+      if (p.n_multi >= DMB_MAX_MULTI) return fail("dmb_marginal", "too many multi-weight qubits");
+      p.simple_digit[k][0] = p.simple_digit[k][1] = -1;
+      p.multi[p.n_multi++] = k;
+    }
+  }
+  for (uint64_t c = 0; c < (1ull << n_qubits); ++c) out[c] = dmb_marginal_value(c, state, p);
+  ctx->stats.other_launches++;
+  return 0;
+}
+
+int dmb_fwht(dmb_ctx* ctx, double* vec, int n_qubits) {
+  const uint64_t pairs = (1ull << n_qubits) >> 1;
+  for (int st = 0; st < n_qubits; ++st)
+    for (uint64_t t = 0; t < pairs; ++t) dmb_fwht_pair(t, st, vec);
+  ctx->stats.other_launches++;
+  return 0;
+}
+
+int dmb_contract_digit(dmb_ctx* ctx, const double* in, double* out, uint64_t H, uint64_t L, const double nv[3]) {
+  for (uint64_t t = 0; t < H * L; ++t) dmb_contract_elem(t, in, out, L, nv[0], nv[1], nv[2]);
+  ctx->stats.other_launches++;
+  return 0;
+}
+
+int dmb_read_coeffs(dmb_ctx* ctx, const double* state, const uint64_t* idx, size_t k, double* out_host) {
+  for (size_t i = 0; i < k; ++i) out_host[i] = state[idx[i]];
+  ctx->stats.other_launches++;
+  return 0;
+}
+
+int dmb_to_matrix(dmb_ctx* ctx, const double* state, int n_qubits, double* work, double* out) {
+  const uint64_t vecs = 1ull << (2 * n_qubits - 2);
+  for (int pos = 0; pos < n_qubits; ++pos)
+    for (uint64_t t = 0; t < vecs; ++t) dmb_tomatrix_digit(t, pos, pos == 0, state, (dmb_d2*)work);
+  for (uint64_t t = 0; t < (1ull << (2 * n_qubits)); ++t)
+    dmb_tomatrix_scatter(t, n_qubits, (const dmb_d2*)work, (dmb_d2*)out);
+  ctx->stats.other_launches++;
+  return 0;
+}
+
+int dmb_dot(dmb_ctx* ctx, const double* a, const double* b, uint64_t count, double* out_host) {
+  double acc = 0.0;
+  for (uint64_t i = 0; i < count; ++i) acc += a[i] * b[i];
+  *out_host = acc;
+  ctx->stats.other_launches++;
+  return 0;
+}
+
+int dmb_chop(dmb_ctx* ctx, double* state, uint64_t count, double thr) {
+  for (uint64_t i = 0; i < count; ++i)
+    if (fabs(state[i]) < thr) state[i] = 0.0;
+  ctx->stats.other_launches++;
+  return 0;
+}
+
+int dmb_upload(dmb_ctx*, double* state, const double* host, uint64_t offset, uint64_t count) {
+  memcpy(state + offset, host, count * sizeof(double));
+  return 0;
+}
+
+int dmb_download(dmb_ctx*, const double* state, double* host, uint64_t offset, uint64_t count) {
+  memcpy(host, state + offset, count * sizeof(double));
+  return 0;
+}
+
+}  // extern "C"
