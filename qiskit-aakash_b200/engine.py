@@ -22,6 +22,8 @@ state has at least two digit positions (the kernels work on digit pairs).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import capi, schedule
@@ -145,7 +147,8 @@ class TorchCudaAllocator:
 # --------------------------------------------------------------------------------------
 
 class PauliEngine:
-    def __init__(self, n_qubits, lib=None, allocator=None, device=0, max_ops_per_pass=None):
+    def __init__(self, n_qubits, lib=None, allocator=None, device=0, max_ops_per_pass=None,
+                 reserve_low=None):
         if n_qubits < 1 or n_qubits > capi.MAX_QUBITS:
             raise BasicAerError("number of qubits out of range: %d" % n_qubits)
         self.n = int(n_qubits)
@@ -160,7 +163,9 @@ class PauliEngine:
         self.pos = [self.n - 1 - q for q in range(self.n)]     # qubit -> digit position
         self.pending = [None] * self.n
         self.queue = []
-        self.max_ops_per_pass = max_ops_per_pass or capi.MAX_OPS
+        # scheduling knobs (env overrides are for on-GPU experiments)
+        self.max_ops_per_pass = int(max_ops_per_pass or os.environ.get("DMB_MAX_OPS_PER_PASS", 8))
+        self.reserve_low = int(reserve_low if reserve_low is not None else os.environ.get("DMB_RESERVE_LOW", 2))
         self.passes_run = 0
         self.h2d_bytes = 0
 
@@ -250,7 +255,8 @@ class PauliEngine:
         ops = self.device_ops(final=True)
         if not ops:
             return np.zeros(0, dtype=capi.PASS_DTYPE)
-        return schedule.build_passes(ops, self.nd, max_ops=self.max_ops_per_pass)
+        return schedule.build_passes(ops, self.nd, max_ops=self.max_ops_per_pass,
+                                     reserve_low=self.reserve_low)
 
     def flush(self):
         passes = self.plan()

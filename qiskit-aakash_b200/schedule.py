@@ -66,8 +66,12 @@ def _rows13(m):
     return m[1:4, :].reshape(12)
 
 
-def build_passes(ops, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_OPS, window=256):
-    """ops: list of DevOp in program order -> numpy array of ``capi.PASS_DTYPE``."""
+def build_passes(ops, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_OPS, window=256,
+                 reserve_low=2):
+    """ops: list of DevOp in program order -> numpy array of ``capi.PASS_DTYPE``.
+
+    ``reserve_low`` digit positions 0..reserve_low-1 are part of every tile, which makes the
+    contiguous global-memory runs of a tile 4^reserve_low doubles long (2 -> 128 bytes)."""
     K = min(max_tile, n_digits)
     if K < 2:
         raise ValueError("state must have at least 2 digit positions")
@@ -75,7 +79,7 @@ def build_passes(ops, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_
     remaining = list(ops)
     plans = []
     while remaining:
-        tile = {0}
+        tile = set(range(max(1, min(reserve_low, K))))
         blocked = set()
         chosen, keep = [], []
         scanned = 0

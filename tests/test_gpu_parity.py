@@ -1,0 +1,189 @@
+"""Parity tests proper (``-m gpu``): the CUDA library on a B200, called through the C ABI,
+against (1) the golden fixtures generated from the unmodified reference, (2) the oracle on
+seeded circuits at sizes it finishes in seconds, (3) size-independent properties at the
+BASELINE sizes (n = 14: trace, normalisation, schedule independence, U.U^-1 round trip,
+GHZ known answer).  Tolerances are BASELINE.json's: max |delta| <= 1e-10 on Pauli
+coefficients and probabilities (float64), trace preserved to 1e-12."""
+import copy
+
+import numpy as np
+import pytest
+
+import cases
+from golden_check import TOL, TRACE_TOL, check_against_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def backend():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import __graft_entry__ as g
+    g.build()
+    from qiskit_aakash_b200 import DmSimulatorB200
+    return lambda: DmSimulatorB200()
+
+
+def _run(backend, n, instrs, options, name="c"):
+    from qiskit_aakash_b200 import assemble, circuits as C
+    circ = C.Circuit(n, name)
+    circ.instructions = instrs
+    res = backend().run(assemble(circ), backend_options=options).result()
+    assert res["success"]
+    return res["results"][0]
+
+
+def test_cuda_library_is_the_one_loaded(backend):
+    """The product path must be the in-tree CUDA library (no silent fallback)."""
+    from qiskit_aakash_b200 import capi, engine
+    e = engine.PauliEngine(3)
+    assert e.lib._name == capi.DEFAULT_LIB
+    e.init_product([[1, 0, 0, 1]] * 3, 0.125)
+    assert np.allclose(e.download()[[0, 3, 63]], 0.125)
+    assert e.stats()["other_launches"] >= 1
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_cuda_backend_matches_golden(name, golden, backend, case_dir):
+    case = cases.get(name)
+    cases.write_files(case, ".")
+    check_against_golden(golden, name, _run(backend, case["n"], case["instrs"], case["options"], name))
+
+
+def _compare_with_oracle(backend, n, instrs, options):
+    from oracle import dm_oracle
+    got = _run(backend, n, copy.deepcopy(instrs), copy.deepcopy(options))
+    ref = dm_oracle.run_oracle(n, copy.deepcopy(instrs), copy.deepcopy(options))
+    assert got["number_of_clock_cycles"] == ref["number_of_clock_cycles"]
+    assert set(got["data"]) == set(ref["data"])
+    worst = 0.0
+    for k, v in ref["data"].items():
+        a = np.array(list(v.values())) if isinstance(v, dict) else np.asarray(v)
+        w = got["data"][k]
+        b = np.array(list(w.values())) if isinstance(w, dict) else np.asarray(w)
+        worst = max(worst, float(np.max(np.abs(a - b))))
+    assert worst <= TOL, worst
+    assert abs(got["data"]["coeffmatrix"][0] * 2 ** n - 1) <= TRACE_TOL
+    return worst
+
+
+@pytest.mark.parametrize("n,seed", [(6, 1), (7, 2), (8, 3), (9, 4), (10, 5), (11, 6)])
+def test_random_circuits_vs_oracle(backend, n, seed):
+    circ = cases._rand_circuit(n, 60, 7000 + seed)
+    circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="XYZ"[seed % 3])
+    opts = dict(cases.FULL_NOISE, compute_densitymatrix=(n <= 8))
+    _compare_with_oracle(backend, n, circ.instructions, opts)
+
+
+def test_baseline_configs_at_oracle_sizes(backend):
+    from qiskit_aakash_b200 import circuits as C
+    _compare_with_oracle(backend, 10, C.qft(10).instructions, {"compute_densitymatrix": False})
+    _compare_with_oracle(backend, 11, C.random_layered(11, 6, 1100).instructions,
+                         dict(C.noisy_options(), compute_densitymatrix=False))
+    g = C.grover(5, "10110", 1)                       # 5 search + 3 ancilla qubits
+    _compare_with_oracle(backend, g.n_qubits, g.instructions, dict(C.grover_options(), compute_densitymatrix=False))
+
+
+def test_grover12_noisy_vs_oracle_prefix(backend):
+    """BASELINE configs[1] shape (n = 12, decoherence + amplitude damping): the first 40
+    instructions of Grover-12 against the oracle, then the full circuit's invariants."""
+    from qiskit_aakash_b200 import circuits as C
+    g = C.grover(7, "1011001", 1)
+    assert g.n_qubits == 12
+    prefix = g.instructions[:40]
+    _compare_with_oracle(backend, 12, prefix, dict(C.grover_options(), compute_densitymatrix=False))
+    res = _run(backend, 12, g.instructions, dict(C.grover_options(), compute_densitymatrix=False))
+    p = np.array(list(res["data"]["partial_probability"].values()))
+    assert abs(p.sum() - 1) <= 1e-10 and p.min() >= -1e-12
+    assert abs(res["data"]["coeffmatrix"][0] * 2 ** 12 - 1) <= TRACE_TOL
+
+
+# ---- every op kind on every digit pair, engine level, against NumPy on a random state ------
+
+@pytest.mark.parametrize("n", [2, 3, 5, 6, 8])
+def test_each_op_kind_on_every_digit_pair(backend, n):
+    from oracle import dm_oracle
+    from qiskit_aakash_b200 import engine
+    rng = np.random.default_rng(n)
+    vec = rng.normal(size=4 ** n)
+    vec[0] = 0.5 ** n
+    pairs = [(a, b) for a in range(n) for b in range(n) if a != b]
+    if len(pairs) > 14:
+        pairs = [pairs[i] for i in rng.choice(len(pairs), size=14, replace=False)]
+    for tsp in ([1.0, 0.0], [0.97, 0.05]):
+        e = engine.PauliEngine(n, max_ops_per_pass=1)
+        e.upload(vec)
+        o = dm_oracle.OracleSim({"tsp_model_error": tsp, "rotation_error": {"rz": [0.99, 0.01], "ry": [0.98, 0.02]},
+                                 "decay_factor": 0.9, "thermal_factor": 0.3, "decoherence_factor": 0.95})
+        o.n, o.dm = n, vec.copy()
+        for (a, b) in pairs:
+            ang = rng.uniform(0, 6, 3)
+            e.apply_1q(a, engine.gate_matrix("u3", ang, o.rotation_error))
+            o.single_gate("u3", ang, a)
+            e.apply_cx(a, b, tsp)
+            o.cx(a, b)
+            e.apply_1q_all(engine.memory_noise_matrix(o.f, o.p, o.g))
+            o.memory_noise()
+        got = e.download()
+        assert np.max(np.abs(got - o.dm)) <= 1e-12 * max(1.0, np.max(np.abs(vec)))
+
+
+# ---- size-independent properties at the BASELINE size (n = 14, 2 GiB state) ------------------
+
+def test_n14_ghz_known_answer(backend):
+    from qiskit_aakash_b200 import circuits as C
+    c = C.ghz(14)
+    c.measure(list(range(14)), list(range(14)), basis="Ensemble", add_param="Z")
+    res = _run(backend, 14, c.instructions, {"compute_densitymatrix": False})
+    p = res["data"]["ensemble_probability"]
+    assert abs(p["0" * 14] - 0.5) <= TOL and abs(p["1" * 14] - 0.5) <= TOL
+    assert abs(sum(p.values()) - 1) <= TOL
+    vec = res["data"]["coeffmatrix"]
+    assert abs(vec[0] * 2 ** 14 - 1) <= TRACE_TOL
+    assert abs(np.dot(vec, vec) * 2 ** 14 - 1) <= 1e-9          # purity of a pure state
+
+
+def test_n14_unitary_round_trip(backend):
+    """U then U^-1 (noise free) must return to |0..0>: coefficients 2^-n on the I/Z strings."""
+    from qiskit_aakash_b200 import circuits as C
+    fwd = C.random_layered(14, 6, 42, readout=False)
+    c = C.Circuit(14)
+    c.instructions = list(fwd.instructions)
+    for ins in reversed(fwd.instructions):
+        if ins.name == "cx":
+            c.cx(ins.qubits[0], ins.qubits[1])
+        else:
+            th, ph, lam = ins.params
+            c.barrier()                                   # keep U and U^-1 from being merged away
+            c.u3(-th, -lam, -ph, ins.qubits[0])
+    c.measure(list(range(14)), list(range(14)), basis="Ensemble", add_param="Z")
+    res = _run(backend, 14, c.instructions, {"compute_densitymatrix": False})
+    p = res["data"]["ensemble_probability"]
+    assert abs(p["0" * 14] - 1.0) <= 1e-9
+    vec = res["data"]["coeffmatrix"].reshape([4] * 14)
+    assert abs(vec[(3,) * 14] * 2 ** 14 - 1) <= 1e-9 and abs(vec[(1,) + (0,) * 13]) <= 1e-12
+
+
+def test_n14_noisy_invariants_and_schedule_independence(backend):
+    """Config 3 shape (n = 14, per-gate noise): trace, normalisation, and the same numbers
+    from the fused schedule and from the one-op-per-pass schedule."""
+    from qiskit_aakash_b200 import DmSimulatorB200, assemble, circuits as C, engine
+    circ = C.random_layered(14, 8, 1400)
+    opts = dict(C.noisy_options(), compute_densitymatrix=False, **C.grover_options())
+    outs = []
+    for max_ops, reserve in ((8, 2), (1, 1)):
+        be = DmSimulatorB200(_engine_factory=lambda n: engine.PauliEngine(n, max_ops_per_pass=max_ops, reserve_low=reserve))
+        c2 = C.Circuit(14); c2.instructions = copy.deepcopy(circ.instructions)
+        r = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
+        outs.append((r["data"]["coeffmatrix"].copy(), np.array(list(r["data"]["ensemble_probability"].values()))))
+        del r
+    (v1, p1), (v2, p2) = outs
+    assert abs(v1[0] * 2 ** 14 - 1) <= TRACE_TOL
+    assert abs(p1.sum() - 1) <= 1e-10 and p1.min() >= -1e-12
+    assert np.max(np.abs(v1 - v2)) <= 1e-12 and np.max(np.abs(p1 - p2)) <= 1e-12
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()
