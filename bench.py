@@ -63,11 +63,11 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -79,10 +79,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=5)
         med = statistics.median(self.samples) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),

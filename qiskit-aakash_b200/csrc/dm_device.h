@@ -232,6 +232,194 @@ DMB_HD void dmb_tile_op_thread(int t, const dmb_op& op, double* smem, int K) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Lean K = 6 path (the hot kernel, k_tile_pass6 in dmb200.cu)
+// ---------------------------------------------------------------------------------------
+// The generic bodies above recompute every address from the digit lists; ncu showed that
+// version issue-bound (69 % issue-slot utilisation, FP64 pipe 27 %, DRAM 40 %).  Everything
+// that does not depend on the thread is therefore precomputed on the host, once per pass,
+// into dmb_lean_pass (a kernel parameter, read through the uniform datapath):
+//   * load/store: element l = 2t + 512 i of a tile splits into a thread part (2t, bits 0-8)
+//     and a uniform part (i << 9, bits 9-11); both the global offset and the swizzle are
+//     linear in those disjoint bit fields, so address = thread_part (+|^) table[i];
+//   * op: byte offsets sa[i] / sj[j] of the digit values (already swizzled; the swizzle is
+//     XOR-linear), the shifts that scatter the thread's four index digits onto the free
+//     tile digits, the access mode, and "column 0 is zero" flags that drop 3 of 12 DFMAs
+//     per 4-vector when a map has no I-component admixture (no amplitude damping / reset).
+#define DMB_LEAN_K 6
+#define DMB_LEAN_TILE (1u << (2 * DMB_LEAN_K))          // 4096 elements
+#define DMB_LEAN_TILE_BYTES (DMB_LEAN_TILE * 8u)        // 32 KiB
+#define DMB_LEAN_PAIRS 8                                 // 16-byte pairs per thread per tile
+enum { DMB_MODE_A = 0, DMB_MODE_PAIR_A = 1, DMB_MODE_PAIR_B = 2 };
+enum { DMB_PA_COL0 = 4, DMB_PB_COL0 = 8 };               // extra flag bits (library-internal)
+
+struct dmb_lean_op {
+  uint32_t sa[4];      // swizzled BYTE offset of digit-a value i
+  uint32_t sj[4];      // swizzled BYTE offset of digit-b value j
+  uint32_t sh[4];      // left shift (bits) placing thread digit m at its tile digit
+  int32_t kind, flags, mode, pad_;
+  double pa[12], pb[12], coef[16];
+};
+
+struct dmb_lean_pass {
+  uint64_t n_tiles;
+  int32_t n_ops;
+  int32_t td[DMB_LEAN_K];
+  int32_t pad_;
+  uint64_t pair_goff[DMB_LEAN_PAIRS];   // element offset of the uniform part (i << 9)
+  uint32_t pair_soff[DMB_LEAN_PAIRS];   // swizzled byte offset of the uniform part
+  dmb_lean_op ops[DMB_MAX_OPS];
+};
+
+// host-side conversion (runs once per pass, before the launch)
+inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L) {
+  L.n_tiles = 1ull << (n_bits - 2 * DMB_LEAN_K);
+  L.n_ops = P.n_ops;
+  L.pad_ = 0;
+  for (int j = 0; j < DMB_LEAN_K; ++j) L.td[j] = P.tile_digit[j];
+  for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
+    const uint32_t l = (uint32_t)i << 9;
+    L.pair_goff[i] = dmb_tile_off(l, P.tile_digit, DMB_LEAN_K);
+    L.pair_soff[i] = dmb_swz(l) << 3;
+  }
+  for (int k = 0; k < P.n_ops; ++k) {
+    const dmb_op& o = P.ops[k];
+    dmb_lean_op& q = L.ops[k];
+    for (int i = 0; i < 4; ++i) {
+      q.sa[i] = dmb_swz((uint32_t)i << (2 * o.a)) << 3;
+      q.sj[i] = dmb_swz((uint32_t)i << (2 * o.b)) << 3;
+      q.sh[i] = (uint32_t)(2 * o.fd[i]);
+    }
+    q.kind = o.kind;
+    q.flags = o.flags & (DMB_HAS_PA | DMB_HAS_PB);
+    q.mode = o.a == 0 ? DMB_MODE_PAIR_A : (o.b == 0 ? DMB_MODE_PAIR_B : DMB_MODE_A);
+    q.pad_ = 0;
+    for (int i = 0; i < 12; ++i) { q.pa[i] = o.pa[i]; q.pb[i] = o.pb[i]; }
+    for (int i = 0; i < 16; ++i) q.coef[i] = o.coef[i];
+    if ((o.flags & DMB_HAS_PA) && (o.pa[0] != 0.0 || o.pa[4] != 0.0 || o.pa[8] != 0.0)) q.flags |= DMB_PA_COL0;
+    if ((o.flags & DMB_HAS_PB) && (o.pb[0] != 0.0 || o.pb[4] != 0.0 || o.pb[8] != 0.0)) q.flags |= DMB_PB_COL0;
+  }
+}
+
+// rows 1..3 of a map whose column 0 is zero (X,Y,Z mix among themselves only)
+DMB_HD void dmb_mat3_nocol0(const double* __restrict__ m, double& x1, double& x2, double& x3) {
+  const double y1 = m[1] * x1 + m[2] * x2 + m[3] * x3;
+  const double y2 = m[5] * x1 + m[6] * x2 + m[7] * x3;
+  const double y3 = m[9] * x1 + m[10] * x2 + m[11] * x3;
+  x1 = y1; x2 = y2; x3 = y3;
+}
+
+struct dmb_lean_thread {        // per-thread constants, computed once per launch
+  uint32_t tq[4];               // the thread's four base-4 index digits
+  uint64_t goff;                // global element offset of pair 0 (l = 2t)
+  uint32_t soff;                // swizzled byte offset of pair 0
+};
+
+DMB_HD void dmb_lean_thread_init(int t, const dmb_lean_pass& L, dmb_lean_thread& T) {
+  T.tq[0] = (uint32_t)t & 3u; T.tq[1] = ((uint32_t)t >> 2) & 3u;
+  T.tq[2] = ((uint32_t)t >> 4) & 3u; T.tq[3] = ((uint32_t)t >> 6) & 3u;
+  T.goff = dmb_tile_off(2u * (uint32_t)t, L.td, DMB_LEAN_K);
+  T.soff = dmb_swz(2u * (uint32_t)t) << 3;
+}
+
+// arithmetic of one op on the thread's 16-block (shared by all access modes)
+DMB_HD void dmb_lean_math(const dmb_lean_op& op, double (&v)[4][4]) {
+  if (op.flags & DMB_HAS_PA) {
+    if (op.flags & DMB_PA_COL0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmb_mat3(op.pa, v[0][j], v[1][j], v[2][j], v[3][j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmb_mat3_nocol0(op.pa, v[1][j], v[2][j], v[3][j]);
+    }
+  }
+  if (op.flags & DMB_HAS_PB) {
+    if (op.flags & DMB_PB_COL0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dmb_mat3(op.pb, v[i][0], v[i][1], v[i][2], v[i][3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dmb_mat3_nocol0(op.pb, v[i][1], v[i][2], v[i][3]);
+    }
+  }
+  switch (op.kind) {
+    case DMB_OP_CX: dmb_cx_ideal(v); break;
+    case DMB_OP_CX_TSP: dmb_cx_tsp(v, op.coef[0], op.coef[1], op.coef[2], op.coef[3], op.coef[4]); break;
+    case DMB_OP_DIAG2:
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i][j] *= op.coef[4 * i + j];
+      break;
+    case DMB_OP_SWAP:
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j) { const double tmp = v[i][j]; v[i][j] = v[j][i]; v[j][i] = tmp; }
+      break;
+    default: break;
+  }
+}
+
+DMB_HD void dmb_lean_op_thread(const dmb_lean_thread& T, const dmb_lean_op& op, unsigned char* stage) {
+  const uint32_t bl = (T.tq[0] << op.sh[0]) | (T.tq[1] << op.sh[1]) | (T.tq[2] << op.sh[2]) | (T.tq[3] << op.sh[3]);
+  const uint32_t sb = dmb_swz(bl) << 3;
+  const int mode = op.mode;
+  double v[4][4];
+  if (mode == DMB_MODE_A) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] = *reinterpret_cast<const double*>(stage + (sb ^ op.sa[i] ^ op.sj[j]));
+  } else {
+    // pairs along digit 0: it is digit a (PAIR_A: rows i come in pairs) or digit b (PAIR_B)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t o = sb ^ (mode == DMB_MODE_PAIR_A ? op.sj[k] : op.sa[k]);
+      const dmb_d2 p0 = *reinterpret_cast<const dmb_d2*>(stage + o);
+      const dmb_d2 p1 = *reinterpret_cast<const dmb_d2*>(stage + (o ^ 16u));
+      if (mode == DMB_MODE_PAIR_A) { v[0][k] = p0.x; v[1][k] = p0.y; v[2][k] = p1.x; v[3][k] = p1.y; }
+      else { v[k][0] = p0.x; v[k][1] = p0.y; v[k][2] = p1.x; v[k][3] = p1.y; }
+    }
+  }
+  dmb_lean_math(op, v);
+  if (mode == DMB_MODE_A) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<double*>(stage + (sb ^ op.sa[i] ^ op.sj[j])) = v[i][j];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t o = sb ^ (mode == DMB_MODE_PAIR_A ? op.sj[k] : op.sa[k]);
+      dmb_d2 p0, p1;
+      if (mode == DMB_MODE_PAIR_A) { p0.x = v[0][k]; p0.y = v[1][k]; p1.x = v[2][k]; p1.y = v[3][k]; }
+      else { p0.x = v[k][0]; p0.y = v[k][1]; p1.x = v[k][2]; p1.y = v[k][3]; }
+      *reinterpret_cast<dmb_d2*>(stage + o) = p0;
+      *reinterpret_cast<dmb_d2*>(stage + (o ^ 16u)) = p1;
+    }
+  }
+}
+
+// synchronous stand-ins for the cp.async load / the store of one tile (used by the CPU tests;
+// the CUDA kernel issues the same addresses through cp.async.cg and LDS.128 + STG.128)
+DMB_HD void dmb_lean_load_thread(const dmb_lean_thread& T, const dmb_lean_pass& L, const double* gtile,
+                                 unsigned char* stage) {
+#pragma unroll
+  for (int i = 0; i < DMB_LEAN_PAIRS; ++i)
+    *reinterpret_cast<dmb_d2*>(stage + (T.soff ^ L.pair_soff[i])) =
+        *reinterpret_cast<const dmb_d2*>(gtile + (T.goff | L.pair_goff[i]));
+}
+
+DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass& L, double* gtile,
+                                  const unsigned char* stage) {
+  dmb_d2 w[DMB_LEAN_PAIRS];
+#pragma unroll
+  for (int i = 0; i < DMB_LEAN_PAIRS; ++i) w[i] = *reinterpret_cast<const dmb_d2*>(stage + (T.soff ^ L.pair_soff[i]));
+#pragma unroll
+  for (int i = 0; i < DMB_LEAN_PAIRS; ++i) *reinterpret_cast<dmb_d2*>(gtile + (T.goff | L.pair_goff[i])) = w[i];
+}
+
+// ---------------------------------------------------------------------------------------
 // Element-wise kernels (one logical thread per output element)
 // ---------------------------------------------------------------------------------------
 struct dmb_qubit_map {              // where each qubit's digit lives in the global index

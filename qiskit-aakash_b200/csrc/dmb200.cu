@@ -48,7 +48,9 @@ struct dmb_ctx {
 static const size_t kScratchElems = 1 << 16;
 
 // ---------------------------------------------------------------------------------------
-// tile pass, variant 0: register-staged 128-bit loads/stores, one tile per CTA iteration
+// tile pass, generic K (2..6): register-staged 128-bit loads/stores, one tile per CTA
+// iteration.  Used for states smaller than 4^6 coefficients (K < 6) and kept selectable
+// for K = 6 (dmb_set_tile_variant(ctx, 1)) as the A/B baseline of the lean kernel below.
 // ---------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(DMB_TILE_THREADS, (K == 6 ? 3 : 1))
@@ -66,6 +68,59 @@ k_tile_pass(double* __restrict__ state, const __grid_constant__ dmb_pass P, uint
     }
     dmb_tile_store_thread<MAXPAIRS>(t, gtile, smem, P.tile_digit, K);
     __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// tile pass, K = 6: the hot kernel.  Persistent CTAs (3 per SM), two 32 KiB stages each:
+// the 16-byte pairs of tile i+1 stream into the other stage with cp.async.cg (LDGSTS, no
+// register staging, L1 bypass) while the op run is applied to tile i in place and tile i is
+// written back with LDS.128 + STG.128 -- loads, arithmetic and stores of consecutive tiles
+// overlap inside one CTA instead of relying on CTAs drifting out of phase.
+// (The TMA bulk engine cannot be used for the staging: the bank-conflict-free layout XORs
+// 16-byte chunks inside each 128-byte row, which no bulk/tensor copy can express.)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(DMB_TILE_THREADS, 3)
+k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L) {
+  extern __shared__ __align__(128) unsigned char lean_smem[];
+  dmb_lean_thread T;
+  dmb_lean_thread_init(threadIdx.x, L, T);
+  uint64_t tile = blockIdx.x;
+  if (tile >= L.n_tiles) return;
+  {
+    const double* g = state + dmb_tile_base(tile, L.td, DMB_LEAN_K) + T.goff;
+#pragma unroll
+    for (int i = 0; i < DMB_LEAN_PAIRS; ++i) cp_async16(lean_smem + (T.soff ^ L.pair_soff[i]), g + L.pair_goff[i]);
+    cp_async_commit();
+  }
+  uint32_t stage_off = 0;
+  for (; tile < L.n_tiles; tile += gridDim.x) {
+    const uint64_t next = tile + gridDim.x;
+    if (next < L.n_tiles) {
+      const double* g = state + dmb_tile_base(next, L.td, DMB_LEAN_K) + T.goff;
+      unsigned char* dst = lean_smem + (stage_off ^ DMB_LEAN_TILE_BYTES);
+#pragma unroll
+      for (int i = 0; i < DMB_LEAN_PAIRS; ++i) cp_async16(dst + (T.soff ^ L.pair_soff[i]), g + L.pair_goff[i]);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    unsigned char* stage = lean_smem + stage_off;
+    for (int i = 0; i < L.n_ops; ++i) {
+      dmb_lean_op_thread(T, L.ops[i], stage);
+      __syncthreads();
+    }
+    dmb_lean_store_thread(T, L, state + dmb_tile_base(tile, L.td, DMB_LEAN_K), stage);
+    __syncthreads();
+    stage_off ^= DMB_LEAN_TILE_BYTES;
   }
 }
 
@@ -173,6 +228,22 @@ static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_p
   return 0;
 }
 
+static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass& P) {
+  static dmb_lean_pass L;                 // 6.5 KB: keep it off the stack; single-threaded per ctx
+  dmb_make_lean_pass(P, n_bits, L);
+  const size_t smem = 2 * DMB_LEAN_TILE_BYTES;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU_TRY(cudaFuncSetAttribute(k_tile_pass6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  uint64_t grid = (uint64_t)ctx->sm_count * 3;
+  if (grid > L.n_tiles) grid = L.n_tiles;
+  k_tile_pass6<<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, L);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
 static int validate_pass(const dmb_pass& P, int n_bits) {
   const int K = P.n_tile_digits;
   if (K < 2 || K > DMB_MAX_TILE_DIGITS) return fail("dmb_apply_passes", "n_tile_digits out of range");
@@ -267,7 +338,7 @@ int dmb_reset_stats(dmb_ctx* ctx) {
 
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant) {
   if (!ctx) return fail("dmb_set_tile_variant", "null context");
-  if (variant != 0) return fail("dmb_set_tile_variant", "only variant 0 is built in this version");
+  if (variant != 0 && variant != 1) return fail("dmb_set_tile_variant", "variant must be 0 or 1");
   ctx->tile_variant = variant;
   return 0;
 }
@@ -309,7 +380,8 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
       case 4: rc = launch_tile_pass<4>(ctx, state, n_bits, P); break;
       case 5: rc = launch_tile_pass<5>(ctx, state, n_bits, P); break;
       case 6:
-        rc = launch_tile_pass<6>(ctx, state, n_bits, P);
+        rc = ctx->tile_variant == 1 ? launch_tile_pass<6>(ctx, state, n_bits, P)
+                                    : launch_tile_pass6(ctx, state, n_bits, P);
         break;
       default: return fail("dmb_apply_passes", "unsupported tile size");
     }

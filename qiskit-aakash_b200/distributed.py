@@ -1,0 +1,398 @@
+"""Multi-GPU layer: the Pauli-coefficient vector sharded over G = 2, 4 or 8 B200s of one box.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink 5 / NVSwitch).  Rank r owns the
+contiguous slice ``[r * 4^n / G, (r+1) * 4^n / G)`` of the reference's vector, i.e. the top
+``g = log2 G`` bits of the 2n-bit flat index are the rank: for G = 4
+qubit 0's whole digit, for G = 2 the high bit of that digit, for G = 8 that digit plus the
+high bit of qubit 1's digit.
+
+* Qubits sit in *slots* (digit positions).  The top ``m = ceil(g/2)`` slots are (partly)
+  global; all others are ordinary local digits and the single-GPU tile kernel runs on them
+  unchanged -- ops on local qubits are embarrassingly parallel, no collective.
+* Single-qubit maps never force communication: they stay in the host-side pending matrix
+  of their qubit (``PauliEngine`` docstring), also for global qubits, including the
+  per-level memory noise with its I->Z mixing (SURVEY.md section 7 "hard parts").
+* Before a two-qubit op touches a global qubit, the m global slots are swapped with the m
+  top local slots: a permutation of index bits that leaves the low B bits alone, executed
+  out of place as an exchange of 2^B-element blocks between ranks (NCCL grouped
+  send/recv = all-to-all); ``ExchangePlan`` enumerates the block moves.  Which qubits are
+  sent out is chosen Belady-style (farthest next use) and they are first moved into the top
+  local slots with SWAP ops fused into the preceding tile passes.
+* Readout: every rank gathers its part of the I/B marginal (``dmb_marginal`` drops terms
+  whose global bits are not this rank's and folds pending maps of global qubits in as
+  weights), one all-reduce of 2^n doubles, then the Walsh-Hadamard transform.
+
+Not sharded yet ("next"): N-basis ensemble, Expect, Bell and
+Pauli->matrix on a sharded state.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import capi, schedule
+from .engine import PauliEngine, TorchCudaAllocator, cx_coefficients
+from .exceptions import BasicAerError
+
+
+def log2_exact(x):
+    g = int(x).bit_length() - 1
+    if x < 1 or (1 << g) != x:
+        raise BasicAerError("world size must be a power of two, got %r" % (x,))
+    return g
+
+
+class ExchangePlan:
+    """Block moves of the global<->top-local slot swap for one rank.
+
+    Index bits above B = 2*(n_loc - m) form two groups of 2m bits (upper: the m global
+    slots, lower: the m top local slots); the swap exchanges the groups.  A block is the
+    2^B elements sharing those 4m bits; (rank, block) pairs are the 4m-bit numbers
+    H = rank << (4m-g) | block."""
+
+    def __init__(self, n_qubits, world, rank):
+        self.g = log2_exact(world)
+        self.m = (self.g + 1) // 2
+        self.n_loc = n_qubits - self.m
+        self.n_bits_local = 2 * n_qubits - self.g
+        self.block_bits = 4 * self.m - self.g
+        self.B = self.n_bits_local - self.block_bits
+        if self.n_loc < 2 * self.m or self.n_loc < 2 or self.B < 2:
+            raise BasicAerError("too few qubits (%d) to shard over %d ranks" % (n_qubits, world))
+        self.block_elems = 1 << self.B
+        self.rank = rank
+        self.world = world
+        self.moves = []          # (src_block, dst_rank, dst_block)
+        for s in range(1 << self.block_bits):
+            dr, db = self.image(rank, s)
+            self.moves.append((s, dr, db))
+
+    def image(self, rank, block):
+        two_m = 2 * self.m
+        H = (rank << self.block_bits) | block
+        hi, lo = H >> two_m, H & ((1 << two_m) - 1)
+        H2 = (lo << two_m) | hi
+        return H2 >> self.block_bits, H2 & ((1 << self.block_bits) - 1)
+
+    def bytes_sent(self):
+        return sum(8 * self.block_elems for (_, dr, _) in self.moves if dr != self.rank)
+
+
+class TorchCommunicator:
+    """torch.distributed plumbing (NCCL on GPUs; gloo in the CPU unit tests)."""
+
+    def __init__(self, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def exchange(self, plan, src, dst):
+        """dst[dst_block] on dst_rank <- src[src_block] for every move (out of place)."""
+        dist, be = self.dist, plan.block_elems
+        sends, recvs = [], []
+        for (s, dr, db) in plan.moves:
+            if dr == self.rank:
+                dst[db * be:(db + 1) * be].copy_(src[s * be:(s + 1) * be])
+            else:
+                sends.append((dr, s))
+        # the swap is an involution: block d of this rank is filled from image(rank, d)
+        for d in range(1 << plan.block_bits):
+            sr, sb = plan.image(self.rank, d)
+            if sr != self.rank:
+                recvs.append((sr, sb, d))
+        ops = []
+        for (dr, s) in sorted(sends):
+            ops.append(dist.P2POp(dist.isend, src[s * be:(s + 1) * be], dr, group=self.group, tag=s))
+        for (sr, sb, d) in sorted(recvs):
+            ops.append(dist.P2POp(dist.irecv, dst[d * be:(d + 1) * be], sr, group=self.group, tag=sb))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def all_reduce_sum(self, tensor):
+        self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+    def all_gather_host(self, arr):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, arr, group=self.group)
+        return out
+
+
+class ShardedPauliEngine(PauliEngine):
+    """``PauliEngine`` over a sharded state.  Every rank runs the same host logic on the same
+    instruction stream, so schedules and collectives line up without negotiation."""
+
+    def __init__(self, n_qubits, comm, lib=None, allocator=None, device=0, max_ops_per_pass=None,
+                 reserve_low=None):
+        self.comm = comm
+        self.rank, self.world = comm.rank, comm.world
+        self.plan_x = ExchangePlan(n_qubits, self.world, self.rank)
+        self.g, self.m, self.n_loc = self.plan_x.g, self.plan_x.m, self.plan_x.n_loc
+        self.n = int(n_qubits)
+        self.nd = self.n_loc                     # digit positions the tile kernel may touch
+        self.n_bits = self.plan_x.n_bits_local
+        self.size = 1 << self.n_bits
+        self.lib = lib if lib is not None else capi.load_library()
+        self.alloc = allocator if allocator is not None else TorchCudaAllocator(device)
+        self.ctx = capi.Context(self.lib, getattr(self.alloc, "index", 0))
+        self.ctx.set_stream(self.alloc.stream())
+        self.state = self.alloc.empty(self.size)
+        self.scratch = self.alloc.empty(self.size)
+        self.pos = [self.n - 1 - q for q in range(self.n)]      # qubit -> slot
+        self.pending = [None] * self.n
+        self.queue = []
+        self.max_ops_per_pass = int(max_ops_per_pass or os.environ.get("DMB_MAX_OPS_PER_PASS", 8))
+        self.reserve_low = int(reserve_low if reserve_low is not None else os.environ.get("DMB_RESERVE_LOW", 2))
+        self.passes_run = 0
+        self.h2d_bytes = 0
+        self.exchanges = 0
+        self.nvlink_bytes_sent = 0
+
+    # -- layout -------------------------------------------------------------------------------
+    def is_local(self, q):
+        return self.pos[q] < self.n_loc
+
+    def _hi_lo(self):
+        return [2 * self.pos[q] + 1 for q in range(self.n)], [2 * self.pos[q] for q in range(self.n)]
+
+    def init_product(self, vectors, scale):
+        self.pos = [self.n - 1 - q for q in range(self.n)]
+        hi, lo = self._hi_lo()
+        self.ctx.init_product(self.sptr, self.n_bits, self.rank, hi, lo,
+                              [list(map(float, v)) for v in vectors], scale)
+        self.pending = [None] * self.n
+        self.queue = []
+
+    def upload(self, vec):
+        raise BasicAerError("stored_density_matrix is not supported on a sharded state yet")
+
+    # -- scheduling with exchanges ------------------------------------------------------------
+    def compile(self, final=True):
+        """Queue (+ pending maps of LOCAL qubits if ``final``) -> list of steps
+        ``("passes", PASS array)`` / ``("exchange",)``; updates ``self.pos`` to the layout
+        after the last step and clears the queue.  Pending maps of qubits that end up global
+        stay pending (readouts fold them in)."""
+        steps = []
+        queue = list(self.queue)
+        pos = list(self.pos)
+        n_loc, m = self.n_loc, self.m
+        while True:
+            # ops runnable in the current layout: all qubits local, none blocked by a skipped op
+            blocked, run, keep = set(), [], []
+            for item in queue:
+                _, kind, qa, qb, pa, pb, coef = item
+                if qa in blocked or qb in blocked or pos[qa] >= n_loc or pos[qb] >= n_loc:
+                    blocked.update((qa, qb))
+                    keep.append(item)
+                else:
+                    run.append(item)
+            devops = [schedule.DevOp(kind, pos[qa], pos[qb], pa, pb, coef) for (_, kind, qa, qb, pa, pb, coef) in run]
+            queue = keep
+            if queue:
+                # evict the local qubits whose next use is farthest away (never-used first)
+                next_use = {}
+                for idx, (_, _, qa, qb, _, _, _) in enumerate(queue):
+                    next_use.setdefault(qa, idx)
+                    next_use.setdefault(qb, idx)
+                local = [q for q in range(self.n) if pos[q] < n_loc]
+                local.sort(key=lambda q: (-next_use.get(q, len(queue) + 1), pos[q]))
+                victims = local[:m]
+                slot_owner = {pos[q]: q for q in range(self.n)}
+                for i, v in enumerate(victims):
+                    target = n_loc - m + i
+                    if pos[v] != target:
+                        other = slot_owner[target]
+                        devops.append(schedule.DevOp(capi.OP_SWAP, pos[v], target))
+                        slot_owner[pos[v]], slot_owner[target] = other, v
+                        pos[other], pos[v] = pos[v], target
+            elif final:
+                left = sorted((pos[q], q) for q in range(self.n) if self.pending[q] is not None and pos[q] < n_loc)
+                for i in range(0, len(left) - 1, 2):
+                    (da, qa), (db, qb) = left[i], left[i + 1]
+                    devops.append(schedule.DevOp(capi.OP_MATS, da, db, self.pending[qa], self.pending[qb]))
+                if len(left) % 2:
+                    da, qa = left[-1]
+                    devops.append(schedule.DevOp(capi.OP_MATS, da, None, self.pending[qa], None))
+                for _, q in left:
+                    self.pending[q] = None
+            if devops:
+                steps.append(("passes", schedule.build_passes(devops, self.nd, max_ops=self.max_ops_per_pass,
+                                                             reserve_low=self.reserve_low)))
+            if not queue:
+                break
+            steps.append(("exchange",))
+            for q in range(self.n):              # global slot s <-> local slot s - m
+                if pos[q] >= n_loc:
+                    pos[q] -= m
+                elif pos[q] >= n_loc - m:
+                    pos[q] += m
+        self.queue = []
+        self.pos = pos
+        return steps
+
+    def run_steps(self, steps):
+        for step in steps:
+            if step[0] == "passes":
+                self.run_passes(step[1])
+            else:
+                self.exchange()
+
+    def exchange(self):
+        self.comm.exchange(self.plan_x, self.state, self.scratch)
+        self.state, self.scratch = self.scratch, self.state
+        self.exchanges += 1
+        self.nvlink_bytes_sent += self.plan_x.bytes_sent()
+
+    def flush(self):
+        saved = list(self.pos)
+        steps = self.compile(final=True)
+        final_pos = self.pos
+        self.pos = saved                         # run_steps does not depend on pos; keep it coherent on error
+        self.run_steps(steps)
+        self.pos = final_pos
+
+    def plan(self):
+        raise BasicAerError("use compile() on a sharded engine")
+
+    # -- readouts -----------------------------------------------------------------------------
+    def marginal_probabilities(self, basis, err):
+        self.flush()
+        b = {"X": 1, "Y": 2, "Z": 3}[basis]
+        n = self.n
+        hi, lo, wt = [], [], np.zeros((n, 2, 4))
+        for k in range(n):
+            q = n - 1 - k
+            hi.append(2 * self.pos[q] + 1)
+            lo.append(2 * self.pos[q])
+            P = self.pending[q] if self.pending[q] is not None else np.eye(4)
+            wt[k, 0, :] = P[0, :]
+            wt[k, 1, :] = err * P[b, :]
+        out = self.alloc.empty(2 ** n)
+        self.ctx.marginal(self.sptr, self.n_bits, self.rank, hi, lo, wt, self.alloc.ptr(out))
+        self.ctx.sync()
+        self.comm.all_reduce_sum(out)
+        self.ctx.fwht(self.alloc.ptr(out), n)
+        host = np.empty(2 ** n)
+        self.ctx.download(self.alloc.ptr(out), host)
+        return host
+
+    def n_basis_probabilities(self, nvec, err):
+        raise BasicAerError("N-basis ensemble measurement is not supported on a sharded state yet")
+
+    def read_coefficients(self, digit_tuples):
+        raise BasicAerError("coefficient reads (Expect / Bell) are not supported on a sharded state yet")
+
+    def to_matrix(self):
+        raise BasicAerError("compute_densitymatrix is not supported on a sharded state; pass "
+                            "compute_densitymatrix=False")
+
+    def _localise_all_pending(self):
+        """Apply pending maps of global qubits too (costs exchanges): needed before the state
+        itself (not just a marginal) is read."""
+        self.flush()
+        guard = 0
+        while any(self.pending[q] is not None for q in range(self.n)):
+            self.exchange()
+            for q in range(self.n):
+                if self.pos[q] >= self.n_loc:
+                    self.pos[q] -= self.m
+                elif self.pos[q] >= self.n_loc - self.m:
+                    self.pos[q] += self.m
+            self.flush()
+            guard += 1
+            if guard > 4:
+                raise BasicAerError("internal: pending maps could not be localised")
+
+    def chop(self, thr):
+        self._localise_all_pending()
+        self.ctx.chop(self.sptr, self.size, thr)
+
+    def download(self, out=None):
+        """Gather the shards and undo the slot permutation on the host (small n only: this is
+        result formatting for the 'coeffmatrix' entry, not part of the hot path)."""
+        self._localise_all_pending()
+        shard = np.empty(self.size)
+        self.ctx.download(self.sptr, shard)
+        shards = self.comm.all_gather_host(shard)
+        full = np.concatenate(shards).reshape([4] * self.n)     # axis j <-> slot n-1-j
+        # slot p holds qubit q with pos[q] == p; reference order wants qubit q on axis q
+        axes = [self.n - 1 - self.pos[q] for q in range(self.n)]
+        vec = np.ascontiguousarray(np.transpose(full, axes)).reshape(-1)
+        if out is not None:
+            out[:] = vec
+            return out
+        return vec
+
+    def overlap_with(self, other_vec):
+        raise BasicAerError("compare is not supported on a sharded state yet")
+
+
+class ShardedCircuitRunner:
+    """bench.py helper: compile the circuit once, then time init -> steps -> marginal."""
+
+    def __init__(self, n, circ, opts, device=0, comm=None, engine=None):
+        import copy
+        from . import engine as eng, hostpass
+        from .dm_simulator import DmSimulatorB200
+        self.n = n
+        self.comm = comm or TorchCommunicator()
+        self.engine = engine or ShardedPauliEngine(n, self.comm, device=device)
+        be = DmSimulatorB200(device=device)
+        be._set_options(None, copy.deepcopy(opts))
+        be._initialize_errors()
+        ops = hostpass.merge_single_qubit_gates(circ.instructions, n, True)
+        levels, self.n_levels = hostpass.partition_levels(ops, n)
+        e = self.engine
+        for level in levels[:self.n_levels]:
+            for op in level:
+                if op.name in ("u1", "u3"):
+                    e.apply_1q(op.qubits[0], eng.gate_matrix(op.name, op.params, be._error_params["one_qubit_gates"]))
+                elif op.name == "cx":
+                    e.apply_cx(op.qubits[0], op.qubits[1], be._error_params["two_qubit_gates"])
+        self.steps = e.compile(final=True)
+        self.final_pos = list(e.pos)
+        self.final_pending = list(e.pending)
+        self.err = be._error_params["measurement"]
+        self._ev = []
+
+    def step(self):
+        import torch
+        e = self.engine
+        e.init_product([[1, 0, 0, 1]] * self.n, 0.5 ** self.n)
+        cuda = torch.cuda.is_available()
+        for st in self.steps:
+            if st[0] == "passes" and cuda:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                e.run_passes(st[1])
+                b.record()
+                self._ev.append((a, b))
+            else:
+                e.run_steps([st])
+        e.pos = list(self.final_pos)
+        e.pending = list(self.final_pending)
+        self.probs = e.marginal_probabilities("Z", self.err)
+
+    def reset_counters(self):
+        self.engine.ctx.sync()
+        self.engine.ctx.reset_stats()
+        self.engine.exchanges = 0
+        self.engine.nvlink_bytes_sent = 0
+        self._ev = []
+
+    def counters(self):
+        return self.engine.stats()
+
+    def pass_ms_total(self):
+        import torch
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in self._ev)
+
+    def e2e(self, args):
+        return None

@@ -168,6 +168,8 @@ class PauliEngine:
         self.reserve_low = int(reserve_low if reserve_low is not None else os.environ.get("DMB_RESERVE_LOW", 2))
         self.passes_run = 0
         self.h2d_bytes = 0
+        if os.environ.get("DMB_TILE_VARIANT"):
+            self.ctx.set_tile_variant(int(os.environ["DMB_TILE_VARIANT"]))
 
     # -- helpers -----------------------------------------------------------------------
     @property

@@ -65,6 +65,24 @@ static void run_tile_pass(double* state, int n_bits, const dmb_pass& P) {
   }
 }
 
+// lean K = 6 path: same per-thread bodies as k_tile_pass6, tiles processed one after another
+static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P) {
+  static dmb_lean_pass L;
+  dmb_make_lean_pass(P, n_bits, L);
+  alignas(128) static unsigned char stage[DMB_LEAN_TILE_BYTES];
+  static dmb_lean_thread T[DMB_TILE_THREADS];
+  for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_thread_init(t, L, T[t]);
+  for (uint64_t tile = 0; tile < L.n_tiles; ++tile) {
+    double* gtile = state + dmb_tile_base(tile, L.td, DMB_LEAN_K);
+    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, gtile, stage);
+    for (int i = 0; i < L.n_ops; ++i)
+      for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_thread(T[t], L.ops[i], stage);
+    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_store_thread(T[t], L, gtile, stage);
+  }
+}
+
+static int g_variant = 0;
+
 extern "C" {
 
 int dmb_abi_version(void) { return DMB_ABI_VERSION; }
@@ -83,7 +101,11 @@ int dmb_set_stream(dmb_ctx*, void*) { return 0; }
 int dmb_sync(dmb_ctx*) { return 0; }
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out) { *out = ctx->stats; return 0; }
 int dmb_reset_stats(dmb_ctx* ctx) { memset(&ctx->stats, 0, sizeof(dmb_stats)); return 0; }
-int dmb_set_tile_variant(dmb_ctx*, int variant) { return variant == 0 ? 0 : fail("dmb_set_tile_variant", "emu"); }
+int dmb_set_tile_variant(dmb_ctx*, int variant) {
+  if (variant != 0 && variant != 1) return fail("dmb_set_tile_variant", "variant must be 0 or 1");
+  g_variant = variant;
+  return 0;
+}
 
 int dmb_init_product(dmb_ctx* ctx, double* state, int n_bits, uint64_t rank_bits, int n_qubits,
                      const int32_t* hi, const int32_t* lo, const double* v, double scale) {
@@ -113,7 +135,10 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
       case 3: run_tile_pass<3>(state, n_bits, P); break;
       case 4: run_tile_pass<4>(state, n_bits, P); break;
       case 5: run_tile_pass<5>(state, n_bits, P); break;
-      case 6: run_tile_pass<6>(state, n_bits, P); break;
+      case 6:
+        if (g_variant == 1) run_tile_pass<6>(state, n_bits, P);
+        else run_tile_pass6(state, n_bits, P);
+        break;
       default: return fail("dmb_apply_passes", "unsupported tile size");
     }
     ctx->stats.tile_pass_launches++;

@@ -48,10 +48,12 @@ def main():
         return engine.gate_matrix("u3", rng.uniform(0, 6, 3), {"rz": [0.999, 0], "ry": [0.999, 0]})
 
     tiles = {"low6": [0, 1, 2, 3, 4, 5], "r2_high": [0, 1, 10, 11, 12, 13], "r2_mid": [0, 1, 5, 6, 7, 8],
-             "r3_high": [0, 1, 2, 11, 12, 13], "r1_high": [0, 9, 10, 11, 12, 13], "r1_mid": [0, 4, 5, 6, 7, 8]}
+             "r1_mid": [0, 4, 5, 6, 7, 8]}
     tsp = engine.cx_coefficients([0.999, 0.0])
-    for tname, tile in tiles.items():
-        for n_ops in (0, 1, 2, 4, 6, 8, 12, 16):
+    variants = [int(x) for x in os.environ.get("PROBE_VARIANTS", "0,1").split(",")]
+    for variant, (tname, tile) in [(v, it) for v in variants for it in tiles.items()]:
+        e.ctx.set_tile_variant(variant)
+        for n_ops in (0, 1, 2, 3, 4, 6, 8, 16):
             for kind in ("cx_tsp_mats", "cx_ideal_nomats"):
                 if n_ops == 0 and kind != "cx_tsp_mats":
                     continue
@@ -64,7 +66,7 @@ def main():
                         ops.append(schedule.DevOp(capi.OP_CX, int(a), int(b), None, None, None))
                 passes = schedule.encode_passes([(tile, ops)])
                 ms = timed(lambda: e.ctx.apply_passes(e.sptr, e.n_bits, passes))
-                print(json.dumps({"probe": "tile_pass", "tile": tname, "digits": tile, "n_ops": n_ops, "kind": kind,
+                print(json.dumps({"probe": "tile_pass", "variant": variant, "tile": tname, "digits": tile, "n_ops": n_ops, "kind": kind,
                                   "ms": round(ms, 4), "GBps": round(bytes_pass / ms / 1e6, 1)}))
                 sys.stdout.flush()
 
