@@ -99,9 +99,9 @@ int dmb_set_stream(dmb_ctx* ctx, void* cuda_stream);
 int dmb_sync(dmb_ctx* ctx);                                   /* synchronous */
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out);
 int dmb_reset_stats(dmb_ctx* ctx);
-/* Tile-kernel variant for 4^6-coefficient tiles: 0 = persistent cp.async double-buffered
- * kernel with host-precomputed address tables (default); 1 = the generic register-staged
- * kernel (one tile per CTA), kept for A/B measurements. */
+/* Tile-kernel variant for 4^6-coefficient tiles: 0 = persistent cp.async kernel, 2 stages x
+ * 3 CTAs/SM (default); 2 = same with 3 stages x 2 CTAs/SM; 3 = 2 stages x 2 CTAs/SM;
+ * 1 = the generic register-staged kernel (one tile per CTA), kept for A/B measurements. */
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant);
 
 /* ---- state initialisation (replaces DmSimulatorPy._initialize_densitymatrix,

@@ -131,6 +131,19 @@ DMB_HD void dmb_cx_tsp(double (&v)[4][4], double c, double s, double c2, double 
   v[2][3] = c * xy + s * xz;
 }
 
+// TSP CNOT with zero mean angle error (s = cs = 0): half the arithmetic.
+DMB_HD void dmb_cx_tsp0(double (&v)[4][4], double c, double c2, double s2) {
+  const double iy = v[0][2], zy = v[3][2], iz = v[0][3], zz = v[3][3];
+  v[0][2] = s2 * iy + c2 * zy;
+  v[3][2] = c2 * iy + s2 * zy;
+  v[0][3] = s2 * iz + c2 * zz;
+  v[3][3] = c2 * iz + s2 * zz;
+  const double xi = v[1][0], xx = v[1][1], xy = v[1][2], xz = v[1][3];
+  const double yi = v[2][0], yx = v[2][1], yy = v[2][2], yz = v[2][3];
+  v[1][0] = c * xx; v[1][1] = c * xi; v[1][2] = c * yz; v[1][3] = -(c * yy);
+  v[2][0] = c * yx; v[2][1] = c * yi; v[2][2] = -(c * xz); v[2][3] = c * xy;
+}
+
 // Ideal CNOT: the same map with (c,s,c2,s2,cs) = (1,0,1,0,0) -- a signed permutation.
 DMB_HD void dmb_cx_ideal(double (&v)[4][4]) {
   double t;
@@ -250,9 +263,9 @@ DMB_HD void dmb_tile_op_thread(int t, const dmb_op& op, double* smem, int K) {
 #define DMB_LEAN_TILE_BYTES (DMB_LEAN_TILE * 8u)        // 32 KiB
 #define DMB_LEAN_PAIRS 8                                 // 16-byte pairs per thread per tile
 enum { DMB_MODE_A = 0, DMB_MODE_PAIR_A = 1, DMB_MODE_PAIR_B = 2 };
-enum { DMB_PA_COL0 = 4, DMB_PB_COL0 = 8 };               // extra flag bits (library-internal)
+enum { DMB_PA_COL0 = 4, DMB_PB_COL0 = 8, DMB_TSP_ZERO_MEAN = 16 };   // extra flag bits (library-internal)
 
-struct dmb_lean_op {
+struct alignas(16) dmb_lean_op {
   uint32_t sa[4];      // swizzled BYTE offset of digit-a value i
   uint32_t sj[4];      // swizzled BYTE offset of digit-b value j
   uint32_t sh[4];      // left shift (bits) placing thread digit m at its tile digit
@@ -260,7 +273,7 @@ struct dmb_lean_op {
   double pa[12], pb[12], coef[16];
 };
 
-struct dmb_lean_pass {
+struct alignas(16) dmb_lean_pass {
   uint64_t n_tiles;
   int32_t n_ops;
   int32_t td[DMB_LEAN_K];
@@ -297,6 +310,7 @@ inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L) 
     for (int i = 0; i < 16; ++i) q.coef[i] = o.coef[i];
     if ((o.flags & DMB_HAS_PA) && (o.pa[0] != 0.0 || o.pa[4] != 0.0 || o.pa[8] != 0.0)) q.flags |= DMB_PA_COL0;
     if ((o.flags & DMB_HAS_PB) && (o.pb[0] != 0.0 || o.pb[4] != 0.0 || o.pb[8] != 0.0)) q.flags |= DMB_PB_COL0;
+    if (o.kind == DMB_OP_CX_TSP && o.coef[1] == 0.0 && o.coef[4] == 0.0) q.flags |= DMB_TSP_ZERO_MEAN;
   }
 }
 
@@ -360,7 +374,19 @@ DMB_HD void dmb_lean_math(const dmb_lean_op& op, double (&v)[4][4]) {
   }
 }
 
-DMB_HD void dmb_lean_op_thread(const dmb_lean_thread& T, const dmb_lean_op& op, unsigned char* stage) {
+// Memory accessor for a stage: the CUDA kernel passes a 32-bit shared-window address and
+// inline ld.shared/st.shared (one LDS/STS per access, no 64-bit generic address arithmetic);
+// the CPU tests pass a plain pointer.  Mem::ld64/ld128/st64/st128 take a BYTE offset.
+struct dmb_host_mem {
+  unsigned char* base;
+  double ld64(uint32_t off) const { return *reinterpret_cast<const double*>(base + off); }
+  dmb_d2 ld128(uint32_t off) const { return *reinterpret_cast<const dmb_d2*>(base + off); }
+  void st64(uint32_t off, double v) const { *reinterpret_cast<double*>(base + off) = v; }
+  void st128(uint32_t off, dmb_d2 v) const { *reinterpret_cast<dmb_d2*>(base + off) = v; }
+};
+
+template <class Mem>
+DMB_HD void dmb_lean_op_thread(const dmb_lean_thread& T, const dmb_lean_op& op, const Mem& mem) {
   const uint32_t bl = (T.tq[0] << op.sh[0]) | (T.tq[1] << op.sh[1]) | (T.tq[2] << op.sh[2]) | (T.tq[3] << op.sh[3]);
   const uint32_t sb = dmb_swz(bl) << 3;
   const int mode = op.mode;
@@ -369,16 +395,22 @@ DMB_HD void dmb_lean_op_thread(const dmb_lean_thread& T, const dmb_lean_op& op, 
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[i][j] = *reinterpret_cast<const double*>(stage + (sb ^ op.sa[i] ^ op.sj[j]));
-  } else {
-    // pairs along digit 0: it is digit a (PAIR_A: rows i come in pairs) or digit b (PAIR_B)
+      for (int j = 0; j < 4; ++j) v[i][j] = mem.ld64(sb ^ op.sa[i] ^ op.sj[j]);
+  } else if (mode == DMB_MODE_PAIR_A) {      // digit 0 is digit a: rows i come in 16-byte pairs
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t o = sb ^ (mode == DMB_MODE_PAIR_A ? op.sj[k] : op.sa[k]);
-      const dmb_d2 p0 = *reinterpret_cast<const dmb_d2*>(stage + o);
-      const dmb_d2 p1 = *reinterpret_cast<const dmb_d2*>(stage + (o ^ 16u));
-      if (mode == DMB_MODE_PAIR_A) { v[0][k] = p0.x; v[1][k] = p0.y; v[2][k] = p1.x; v[3][k] = p1.y; }
-      else { v[k][0] = p0.x; v[k][1] = p0.y; v[k][2] = p1.x; v[k][3] = p1.y; }
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t o = sb ^ op.sj[j];
+      const dmb_d2 p0 = mem.ld128(o);
+      const dmb_d2 p1 = mem.ld128(o ^ 16u);
+      v[0][j] = p0.x; v[1][j] = p0.y; v[2][j] = p1.x; v[3][j] = p1.y;
+    }
+  } else {                                   // digit 0 is digit b: columns j come in pairs
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t o = sb ^ op.sa[i];
+      const dmb_d2 p0 = mem.ld128(o);
+      const dmb_d2 p1 = mem.ld128(o ^ 16u);
+      v[i][0] = p0.x; v[i][1] = p0.y; v[i][2] = p1.x; v[i][3] = p1.y;
     }
   }
   dmb_lean_math(op, v);
@@ -386,35 +418,44 @@ DMB_HD void dmb_lean_op_thread(const dmb_lean_thread& T, const dmb_lean_op& op, 
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) *reinterpret_cast<double*>(stage + (sb ^ op.sa[i] ^ op.sj[j])) = v[i][j];
+      for (int j = 0; j < 4; ++j) mem.st64(sb ^ op.sa[i] ^ op.sj[j], v[i][j]);
+  } else if (mode == DMB_MODE_PAIR_A) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t o = sb ^ op.sj[j];
+      dmb_d2 p0, p1;
+      p0.x = v[0][j]; p0.y = v[1][j]; p1.x = v[2][j]; p1.y = v[3][j];
+      mem.st128(o, p0);
+      mem.st128(o ^ 16u, p1);
+    }
   } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t o = sb ^ (mode == DMB_MODE_PAIR_A ? op.sj[k] : op.sa[k]);
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t o = sb ^ op.sa[i];
       dmb_d2 p0, p1;
-      if (mode == DMB_MODE_PAIR_A) { p0.x = v[0][k]; p0.y = v[1][k]; p1.x = v[2][k]; p1.y = v[3][k]; }
-      else { p0.x = v[k][0]; p0.y = v[k][1]; p1.x = v[k][2]; p1.y = v[k][3]; }
-      *reinterpret_cast<dmb_d2*>(stage + o) = p0;
-      *reinterpret_cast<dmb_d2*>(stage + (o ^ 16u)) = p1;
+      p0.x = v[i][0]; p0.y = v[i][1]; p1.x = v[i][2]; p1.y = v[i][3];
+      mem.st128(o, p0);
+      mem.st128(o ^ 16u, p1);
     }
   }
 }
 
-// synchronous stand-ins for the cp.async load / the store of one tile (used by the CPU tests;
-// the CUDA kernel issues the same addresses through cp.async.cg and LDS.128 + STG.128)
+// load / store of one tile (the CUDA kernel replaces the load by cp.async.cg of the same
+// addresses; the store is used as is)
+template <class Mem>
 DMB_HD void dmb_lean_load_thread(const dmb_lean_thread& T, const dmb_lean_pass& L, const double* gtile,
-                                 unsigned char* stage) {
+                                 const Mem& mem) {
 #pragma unroll
   for (int i = 0; i < DMB_LEAN_PAIRS; ++i)
-    *reinterpret_cast<dmb_d2*>(stage + (T.soff ^ L.pair_soff[i])) =
-        *reinterpret_cast<const dmb_d2*>(gtile + (T.goff | L.pair_goff[i]));
+    mem.st128(T.soff ^ L.pair_soff[i], *reinterpret_cast<const dmb_d2*>(gtile + (T.goff | L.pair_goff[i])));
 }
 
+template <class Mem>
 DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass& L, double* gtile,
-                                  const unsigned char* stage) {
+                                  const Mem& mem) {
   dmb_d2 w[DMB_LEAN_PAIRS];
 #pragma unroll
-  for (int i = 0; i < DMB_LEAN_PAIRS; ++i) w[i] = *reinterpret_cast<const dmb_d2*>(stage + (T.soff ^ L.pair_soff[i]));
+  for (int i = 0; i < DMB_LEAN_PAIRS; ++i) w[i] = mem.ld128(T.soff ^ L.pair_soff[i]);
 #pragma unroll
   for (int i = 0; i < DMB_LEAN_PAIRS; ++i) *reinterpret_cast<dmb_d2*>(gtile + (T.goff | L.pair_goff[i])) = w[i];
 }

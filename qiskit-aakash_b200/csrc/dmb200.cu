@@ -88,39 +88,79 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(DMB_TILE_THREADS, 3)
+// shared-window accessor: 32-bit addresses, one LDS/STS per access
+struct dmb_smem_mem {
+  uint32_t base;
+  __device__ __forceinline__ double ld64(uint32_t off) const {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + off) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ dmb_d2 ld128(uint32_t off) const {
+    dmb_d2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(base + off) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void st64(uint32_t off, double v) const {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + off), "d"(v) : "memory");
+  }
+  __device__ __forceinline__ void st128(uint32_t off, dmb_d2 v) const {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(base + off), "d"(v.x), "d"(v.y) : "memory");
+  }
+};
+
+__device__ __forceinline__ void cp_async16s(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+// STAGES-deep ring of 32 KiB stages per CTA: tiles k+1 .. k+STAGES-1 are in flight while the
+// op run executes on tile k.  (STAGES, CTAs per SM) = (2, 3) or (3, 2) fit the 227 KB of
+// shared memory; chosen at run time (dmb_set_tile_variant / DMB_LEAN_STAGES).
+template <int STAGES, int CTAS>
+__global__ void __launch_bounds__(DMB_TILE_THREADS, CTAS)
 k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L) {
   extern __shared__ __align__(128) unsigned char lean_smem[];
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
   dmb_lean_thread T;
   dmb_lean_thread_init(threadIdx.x, L, T);
-  uint64_t tile = blockIdx.x;
-  if (tile >= L.n_tiles) return;
-  {
-    const double* g = state + dmb_tile_base(tile, L.td, DMB_LEAN_K) + T.goff;
+  const uint64_t first = blockIdx.x;
+  if (first >= L.n_tiles) return;
+  const uint64_t stride = gridDim.x;
+  // prologue: tiles 0 .. STAGES-2 of this CTA
 #pragma unroll
-    for (int i = 0; i < DMB_LEAN_PAIRS; ++i) cp_async16(lean_smem + (T.soff ^ L.pair_soff[i]), g + L.pair_goff[i]);
+  for (int s = 0; s < STAGES - 1; ++s) {
+    const uint64_t tl = first + (uint64_t)s * stride;
+    if (tl < L.n_tiles) {
+      const double* g = state + dmb_tile_base(tl, L.td, DMB_LEAN_K) + T.goff;
+      const uint32_t dst = smem0 + (uint32_t)s * DMB_LEAN_TILE_BYTES;
+#pragma unroll
+      for (int i = 0; i < DMB_LEAN_PAIRS; ++i) cp_async16s(dst + (T.soff ^ L.pair_soff[i]), g + L.pair_goff[i]);
+    }
     cp_async_commit();
   }
-  uint32_t stage_off = 0;
-  for (; tile < L.n_tiles; tile += gridDim.x) {
-    const uint64_t next = tile + gridDim.x;
-    if (next < L.n_tiles) {
-      const double* g = state + dmb_tile_base(next, L.td, DMB_LEAN_K) + T.goff;
-      unsigned char* dst = lean_smem + (stage_off ^ DMB_LEAN_TILE_BYTES);
+  uint32_t cur = 0;                       // stage of the tile being processed
+  uint32_t fill = STAGES - 1;             // stage the next prefetch goes to
+  for (uint64_t tile = first; tile < L.n_tiles; tile += stride) {
+    const uint64_t ahead = tile + (uint64_t)(STAGES - 1) * stride;
+    if (ahead < L.n_tiles) {
+      const double* g = state + dmb_tile_base(ahead, L.td, DMB_LEAN_K) + T.goff;
+      const uint32_t dst = smem0 + fill * DMB_LEAN_TILE_BYTES;
 #pragma unroll
-      for (int i = 0; i < DMB_LEAN_PAIRS; ++i) cp_async16(dst + (T.soff ^ L.pair_soff[i]), g + L.pair_goff[i]);
+      for (int i = 0; i < DMB_LEAN_PAIRS; ++i) cp_async16s(dst + (T.soff ^ L.pair_soff[i]), g + L.pair_goff[i]);
     }
     cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<STAGES - 1>();
     __syncthreads();
-    unsigned char* stage = lean_smem + stage_off;
+    dmb_smem_mem mem;
+    mem.base = smem0 + cur * DMB_LEAN_TILE_BYTES;
     for (int i = 0; i < L.n_ops; ++i) {
-      dmb_lean_op_thread(T, L.ops[i], stage);
+      dmb_lean_op_thread(T, L.ops[i], mem);
       __syncthreads();
     }
-    dmb_lean_store_thread(T, L, state + dmb_tile_base(tile, L.td, DMB_LEAN_K), stage);
+    dmb_lean_store_thread(T, L, state + dmb_tile_base(tile, L.td, DMB_LEAN_K), mem);
     __syncthreads();
-    stage_off ^= DMB_LEAN_TILE_BYTES;
+    cur = (cur + 1 == STAGES) ? 0 : cur + 1;
+    fill = (fill + 1 == STAGES) ? 0 : fill + 1;
   }
 }
 
@@ -228,20 +268,29 @@ static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_p
   return 0;
 }
 
+template <int STAGES, int CTAS>
+static int launch_lean(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
+  const size_t smem = (size_t)STAGES * DMB_LEAN_TILE_BYTES;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU_TRY(cudaFuncSetAttribute(k_tile_pass6<STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
+  if (grid > L.n_tiles) grid = L.n_tiles;
+  k_tile_pass6<STAGES, CTAS><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, L);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
 static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass& P) {
   static dmb_lean_pass L;                 // 6.5 KB: keep it off the stack; single-threaded per ctx
   dmb_make_lean_pass(P, n_bits, L);
-  const size_t smem = 2 * DMB_LEAN_TILE_BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CU_TRY(cudaFuncSetAttribute(k_tile_pass6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+  switch (ctx->tile_variant) {
+    case 2: return launch_lean<3, 2>(ctx, state, L);
+    case 3: return launch_lean<2, 2>(ctx, state, L);
+    default: return launch_lean<2, 3>(ctx, state, L);
   }
-  uint64_t grid = (uint64_t)ctx->sm_count * 3;
-  if (grid > L.n_tiles) grid = L.n_tiles;
-  k_tile_pass6<<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, L);
-  CU_TRY(cudaGetLastError());
-  return 0;
 }
 
 static int validate_pass(const dmb_pass& P, int n_bits) {
@@ -338,7 +387,7 @@ int dmb_reset_stats(dmb_ctx* ctx) {
 
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant) {
   if (!ctx) return fail("dmb_set_tile_variant", "null context");
-  if (variant != 0 && variant != 1) return fail("dmb_set_tile_variant", "variant must be 0 or 1");
+  if (variant < 0 || variant > 3) return fail("dmb_set_tile_variant", "variant must be 0..3");
   ctx->tile_variant = variant;
   return 0;
 }

@@ -151,6 +151,7 @@ class ShardedPauliEngine(PauliEngine):
         self.reserve_low = int(reserve_low if reserve_low is not None else os.environ.get("DMB_RESERVE_LOW", 2))
         self.passes_run = 0
         self.h2d_bytes = 0
+        self.drain_threshold = 0         # exchanges are collectives: compile whole queues
         self.exchanges = 0
         self.nvlink_bytes_sent = 0
 

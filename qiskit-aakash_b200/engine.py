@@ -168,6 +168,9 @@ class PauliEngine:
         self.reserve_low = int(reserve_low if reserve_low is not None else os.environ.get("DMB_RESERVE_LOW", 2))
         self.passes_run = 0
         self.h2d_bytes = 0
+        # launch queued two-qubit ops as soon as this many have accumulated, so that the GPU
+        # works while the host is still lowering later levels (0 = only at readouts)
+        self.drain_threshold = int(os.environ.get("DMB_DRAIN_THRESHOLD", 96))
         if os.environ.get("DMB_TILE_VARIANT"):
             self.ctx.set_tile_variant(int(os.environ["DMB_TILE_VARIANT"]))
 
@@ -231,6 +234,16 @@ class PauliEngine:
         else:
             kind, coef = capi.OP_CX_TSP, cx_coefficients(tsp)
         self.queue.append(("2q", kind, ctrl, tgt, self._take(ctrl), self._take(tgt), coef))
+        if self.drain_threshold and len(self.queue) >= self.drain_threshold:
+            self.drain()
+
+    def drain(self):
+        """Schedule and launch the queued two-qubit ops now (pending matrices stay pending)."""
+        ops = self.device_ops(final=False)
+        self.queue = []
+        if ops:
+            self.run_passes(schedule.build_passes(ops, self.nd, max_ops=self.max_ops_per_pass,
+                                                  reserve_low=self.reserve_low))
 
     def apply_diag2(self, qa, qb, weights):
         """v[digit(qa)][digit(qb)] *= weights[i][j] (Bell mask, ``dm_simulator.py:749-756``)."""

@@ -72,12 +72,14 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P) {
   alignas(128) static unsigned char stage[DMB_LEAN_TILE_BYTES];
   static dmb_lean_thread T[DMB_TILE_THREADS];
   for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_thread_init(t, L, T[t]);
+  dmb_host_mem mem;
+  mem.base = stage;
   for (uint64_t tile = 0; tile < L.n_tiles; ++tile) {
     double* gtile = state + dmb_tile_base(tile, L.td, DMB_LEAN_K);
-    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, gtile, stage);
+    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, gtile, mem);
     for (int i = 0; i < L.n_ops; ++i)
-      for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_thread(T[t], L.ops[i], stage);
-    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_store_thread(T[t], L, gtile, stage);
+      for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_thread(T[t], L.ops[i], mem);
+    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_store_thread(T[t], L, gtile, mem);
   }
 }
 
@@ -102,7 +104,7 @@ int dmb_sync(dmb_ctx*) { return 0; }
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out) { *out = ctx->stats; return 0; }
 int dmb_reset_stats(dmb_ctx* ctx) { memset(&ctx->stats, 0, sizeof(dmb_stats)); return 0; }
 int dmb_set_tile_variant(dmb_ctx*, int variant) {
-  if (variant != 0 && variant != 1) return fail("dmb_set_tile_variant", "variant must be 0 or 1");
+  if (variant < 0 || variant > 3) return fail("dmb_set_tile_variant", "variant must be 0..3");
   g_variant = variant;
   return 0;
 }

@@ -50,10 +50,10 @@ def main():
     tiles = {"low6": [0, 1, 2, 3, 4, 5], "r2_high": [0, 1, 10, 11, 12, 13], "r2_mid": [0, 1, 5, 6, 7, 8],
              "r1_mid": [0, 4, 5, 6, 7, 8]}
     tsp = engine.cx_coefficients([0.999, 0.0])
-    variants = [int(x) for x in os.environ.get("PROBE_VARIANTS", "0,1").split(",")]
+    variants = [int(x) for x in os.environ.get("PROBE_VARIANTS", "0,2,3,1").split(",")]
     for variant, (tname, tile) in [(v, it) for v in variants for it in tiles.items()]:
         e.ctx.set_tile_variant(variant)
-        for n_ops in (0, 1, 2, 3, 4, 6, 8, 16):
+        for n_ops in (0, 2, 3, 4, 5, 6, 8):
             for kind in ("cx_tsp_mats", "cx_ideal_nomats"):
                 if n_ops == 0 and kind != "cx_tsp_mats":
                     continue
