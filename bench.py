@@ -247,7 +247,9 @@ def run_ours(args):
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(state_bytes + 8 * 2 ** n),
                "prob_sum": float(sum(probs.values()))}
     else:
-        e2e = runner.e2e(args)
+        nv = {"exchanges_per_step": runner.engine.exchanges / args.steps,
+              "nvlink_bytes_sent_per_gpu_per_step": runner.engine.nvlink_bytes_sent / args.steps}
+        e2e = runner.e2e(args, lambda: circuits.random_layered(n, depth, seed), opts, n_gates, device=local_rank)
 
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
@@ -270,6 +272,8 @@ def run_ours(args):
                 "circuit_ms": ms_step, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(counters["tile_pass_launches"] + counters["other_launches"]),
                 "clocks": clocks}
+        if world > 1:
+            line["nvlink"] = nv
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -284,6 +288,7 @@ class SingleGpuRunner:
         self.torch = torch
         self.n = n
         self.engine = eng.PauliEngine(n, device=device)
+        self.engine.drain_threshold = 0          # compile the whole circuit into one resident plan
         be = DmSimulatorB200(device=device)
         be._set_options(None, copy.deepcopy(opts))
         be._initialize_errors()

@@ -234,7 +234,7 @@ def test_scheduler_fuses_brick_layers():
     e = engine.PauliEngine.__new__(engine.PauliEngine)     # planning only: no buffers
     e.n, e.nd = 14, 14
     e.pos = [13 - q for q in range(14)]
-    e.pending, e.queue, e.max_ops_per_pass, e.reserve_low = [None] * 14, [], 16, 2
+    e.pending, e.queue, e.max_ops_per_pass, e.reserve_low, e.drain_threshold = [None] * 14, [], 16, 2, 0
     for ins in circ.instructions:
         if ins.name == "u3":
             e.apply_1q(ins.qubits[0], engine.gate_matrix("u3", ins.params, {"rz": [1, 0], "ry": [1, 0]}))
