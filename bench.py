@@ -240,12 +240,13 @@ def run_ours(args):
             assert res["success"]
             probs = res["results"][0]["data"]["ensemble_probability"]
             h2d = backend.last_engine_stats["h2d_bytes"]
+            breakdown = {k: round(1e3 * v, 2) for k, v in backend.last_engine_stats.items() if k.startswith("t_")}
             del res
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / reps
         e2e = {"value": n_gates * 16.0 * 4 ** n / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(state_bytes + 8 * 2 ** n),
-               "prob_sum": float(sum(probs.values()))}
+               "prob_sum": float(sum(probs.values())), "breakdown_ms": breakdown}
     else:
         nv = {"exchanges_per_step": runner.engine.exchanges / args.steps,
               "nvlink_bytes_sent_per_gpu_per_step": runner.engine.nvlink_bytes_sent / args.steps}

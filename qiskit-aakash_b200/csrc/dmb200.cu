@@ -154,7 +154,7 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
     dmb_smem_mem mem;
     mem.base = smem0 + cur * DMB_LEAN_TILE_BYTES;
     for (int i = 0; i < L.n_ops; ++i) {
-      dmb_lean_op_thread(T, L.ops[i], mem);
+      dmb_lean_op_dispatch(T, L.ops[i], mem);
       __syncthreads();
     }
     dmb_lean_store_thread(T, L, state + dmb_tile_base(tile, L.td, DMB_LEAN_K), mem);

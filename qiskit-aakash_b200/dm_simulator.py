@@ -428,16 +428,24 @@ class DmSimulatorB200:
             if not noise_is_identity:                                   # :1173-1177
                 engine.apply_1q_all(noise)
 
+        t_levels = time.time()
+        t_dl0 = t_dl1 = t_levels
         if self.SHOW_FINAL_STATE:
             matrix = engine.to_matrix() if self._get_den_mat else None   # before the chop (:1261-1263)
             engine.chop(self._chop_threshold)
+            engine.sync()
+            t_dl0 = time.time()
             data["coeffmatrix"] = self._download(engine)
+            t_dl1 = time.time()
             if self._get_den_mat:
                 data["densitymatrix"] = matrix
             if self._fidelity is not None:
                 data["fidelity"] = self._fidelity
         engine.sync()
-        self.last_engine_stats = dict(engine.stats(), passes=engine.passes_run, h2d_bytes=engine.h2d_bytes)
+        self.last_engine_stats = dict(engine.stats(), passes=engine.passes_run, h2d_bytes=engine.h2d_bytes,
+                                      t_host_pre=end_processing - start_processing,
+                                      t_levels=t_levels - start_runtime, t_final_compute=t_dl0 - t_levels,
+                                      t_download=t_dl1 - t_dl0)
         end_runtime = time.time()
         header = getattr(experiment, "header", None)
         return {"name": getattr(header, "name", None),

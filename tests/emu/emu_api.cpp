@@ -78,7 +78,7 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P) {
     double* gtile = state + dmb_tile_base(tile, L.td, DMB_LEAN_K);
     for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, gtile, mem);
     for (int i = 0; i < L.n_ops; ++i)
-      for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_thread(T[t], L.ops[i], mem);
+      for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_dispatch(T[t], L.ops[i], mem);
     for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_store_thread(T[t], L, gtile, mem);
   }
 }
