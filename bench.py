@@ -304,6 +304,7 @@ class SingleGpuRunner:
                 elif op.name == "cx":
                     e.apply_cx(op.qubits[0], op.qubits[1], be._error_params["two_qubit_gates"])
         self.passes = e.plan()
+        self.final_pos = list(e.pos)
         e.queue, e.pending = [], [None] * n
         self.err = be._error_params["measurement"]
         self._pass_ms = 0.0
@@ -317,6 +318,7 @@ class SingleGpuRunner:
         e.run_passes(self.passes)
         b.record()
         self._ev.append((a, b))
+        e.pos = list(self.final_pos)
         self.probs = e.marginal_probabilities("Z", self.err)
 
     def reset_counters(self):

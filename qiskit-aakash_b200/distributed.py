@@ -152,6 +152,7 @@ class ShardedPauliEngine(PauliEngine):
         self.passes_run = 0
         self.h2d_bytes = 0
         self.drain_threshold = 0         # exchanges are collectives: compile whole queues
+        self.relabel = False
         self.exchanges = 0
         self.nvlink_bytes_sent = 0
 

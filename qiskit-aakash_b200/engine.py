@@ -164,13 +164,15 @@ class PauliEngine:
         self.pending = [None] * self.n
         self.queue = []
         # scheduling knobs (env overrides are for on-GPU experiments)
-        self.max_ops_per_pass = int(max_ops_per_pass or os.environ.get("DMB_MAX_OPS_PER_PASS", 8))
+        self.max_ops_per_pass = int(max_ops_per_pass or os.environ.get("DMB_MAX_OPS_PER_PASS", 10))
         self.reserve_low = int(reserve_low if reserve_low is not None else os.environ.get("DMB_RESERVE_LOW", 2))
         self.passes_run = 0
         self.h2d_bytes = 0
         # launch queued two-qubit ops as soon as this many have accumulated, so that the GPU
         # works while the host is still lowering later levels (0 = only at readouts)
         self.drain_threshold = int(os.environ.get("DMB_DRAIN_THRESHOLD", 96))
+        # dynamic relabelling of the two low digit positions (schedule.build_passes_relabel)
+        self.relabel = bool(int(os.environ.get("DMB_RELABEL", "1")))
         if os.environ.get("DMB_TILE_VARIANT"):
             self.ctx.set_tile_variant(int(os.environ["DMB_TILE_VARIANT"]))
 
@@ -187,6 +189,7 @@ class PauliEngine:
     # -- a4: initial states --------------------------------------------------------------
     def init_product(self, vectors, scale):
         """state = scale * kron_q vectors[q]  (``_initialize_densitymatrix``, ``:284-349``)."""
+        self.pos = [self.n - 1 - q for q in range(self.n)]
         hi, lo = self._hi_lo()
         v = [list(map(float, vec)) for vec in vectors]
         if self.nd > self.n:                     # phantom digit: I component only
@@ -206,6 +209,7 @@ class PauliEngine:
             full[:vec.size] = vec
             vec = full
         self.ctx.upload(self.sptr, vec)
+        self.pos = [self.n - 1 - q for q in range(self.n)]
         self.h2d_bytes += vec.nbytes
         self.pending = [None] * self.n
         self.queue = []
@@ -237,13 +241,32 @@ class PauliEngine:
         if self.drain_threshold and len(self.queue) >= self.drain_threshold:
             self.drain()
 
+    def _schedule(self, final):
+        """Outstanding work -> PASS array.  With relabelling the ops are scheduled on qubit ids
+        and ``self.pos`` is advanced to the layout after the last pass."""
+        if getattr(self, "relabel", False):
+            qops = [schedule.DevOp(kind, qa, qb, pa, pb, coef) for (_, kind, qa, qb, pa, pb, coef) in self.queue]
+            if final:
+                left = [q for q in range(self.n) if self.pending[q] is not None]
+                left.sort(key=lambda q: self.pos[q])
+                for i in range(0, len(left) - 1, 2):
+                    qops.append(schedule.DevOp(capi.OP_MATS, left[i], left[i + 1],
+                                               self.pending[left[i]], self.pending[left[i + 1]]))
+                if len(left) % 2:
+                    qops.append(schedule.DevOp(capi.OP_MATS, left[-1], None, self.pending[left[-1]], None))
+            if not qops:
+                return np.zeros(0, dtype=capi.PASS_DTYPE)
+            return schedule.build_passes_relabel(qops, self.pos, self.nd, max_ops=self.max_ops_per_pass)
+        ops = self.device_ops(final=final)
+        if not ops:
+            return np.zeros(0, dtype=capi.PASS_DTYPE)
+        return schedule.build_passes(ops, self.nd, max_ops=self.max_ops_per_pass, reserve_low=self.reserve_low)
+
     def drain(self):
         """Schedule and launch the queued two-qubit ops now (pending matrices stay pending)."""
-        ops = self.device_ops(final=False)
+        passes = self._schedule(final=False)
         self.queue = []
-        if ops:
-            self.run_passes(schedule.build_passes(ops, self.nd, max_ops=self.max_ops_per_pass,
-                                                  reserve_low=self.reserve_low))
+        self.run_passes(passes)
 
     def apply_diag2(self, qa, qb, weights):
         """v[digit(qa)][digit(qb)] *= weights[i][j] (Bell mask, ``dm_simulator.py:749-756``)."""
@@ -266,12 +289,8 @@ class PauliEngine:
         return ops
 
     def plan(self):
-        """Schedule everything outstanding into passes (does not execute)."""
-        ops = self.device_ops(final=True)
-        if not ops:
-            return np.zeros(0, dtype=capi.PASS_DTYPE)
-        return schedule.build_passes(ops, self.nd, max_ops=self.max_ops_per_pass,
-                                     reserve_low=self.reserve_low)
+        """Schedule everything outstanding into passes (does not execute; advances ``pos``)."""
+        return self._schedule(final=True)
 
     def flush(self):
         passes = self.plan()
@@ -340,8 +359,23 @@ class PauliEngine:
         return self.ctx.read_coeffs(self.sptr, idx)
 
     def _require_reference_layout(self):
-        if self.pos != [self.n - 1 - q for q in range(self.n)]:
-            raise BasicAerError("internal: state is not in the reference qubit order")
+        """Bring every qubit q back to digit position n-1-q (SWAP ops in ordinary tile passes)."""
+        n = self.n
+        pos = list(self.pos)
+        if pos == [n - 1 - q for q in range(n)]:
+            return
+        owner = {pos[q]: q for q in range(n)}
+        ops = []
+        for q in range(n):
+            t = n - 1 - q
+            if pos[q] != t:
+                other = owner[t]
+                ops.append(schedule.DevOp(capi.OP_SWAP, pos[q], t))
+                owner[pos[q]], pos[other] = other, pos[q]
+                owner[t], pos[q] = q, t
+        self.run_passes(schedule.build_passes(ops, self.nd, max_ops=self.max_ops_per_pass,
+                                              reserve_low=self.reserve_low))
+        self.pos = pos
 
     def download(self, out=None):
         """Flat 4^n coefficient vector in the reference order (host numpy array)."""

@@ -115,6 +115,106 @@ def build_passes(ops, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_
     return encode_passes(plans)
 
 
+def _greedy_select(remaining, start_set, cap, max_ops, window, n_qubits):
+    """One pass of list scheduling over QUBIT ids: returns (chosen indices, tile qubit set)."""
+    tile = set(start_set)
+    blocked = set()
+    chosen = []
+    for idx, op in enumerate(remaining):
+        if idx >= window or len(chosen) >= max_ops or len(blocked) >= n_qubits:
+            break
+        dg = op.digits()
+        if any(d in blocked for d in dg):
+            blocked.update(dg)
+            continue
+        need = tile.union(dg)
+        if len(need) <= cap:
+            tile = need
+            chosen.append(idx)
+        else:
+            blocked.update(dg)
+    return chosen, tile
+
+
+def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_OPS, window=256):
+    """Like ``build_passes`` but with dynamic relabelling of the two low digit positions.
+
+    ``qops`` are DevOps whose ``da``/``db`` are QUBIT ids; ``pos[q]`` is the digit position of
+    qubit q (mutated to the layout after the last pass).  Digit positions 0 and 1 are part of
+    every tile (they give the 128-byte contiguous runs in HBM), so whatever qubits live there
+    ride along in every pass for free.  After choosing the ops of pass k the scheduler looks at
+    what pass k+1 would like to work on and, if that set shares qubits with pass k's tile,
+    moves up to two of them into positions 0/1 with SWAP ops appended to pass k (both digits
+    are in pass k's tile, so the swap is one more fused op, not another HBM round trip).  For
+    nearest-neighbour circuits this turns the useful tile from 4 fresh qubits into a sliding
+    window of 6."""
+    n_qubits = len(pos)
+    K = min(max_tile, n_digits)
+    if K < 2:
+        raise ValueError("state must have at least 2 digit positions")
+    max_ops = min(max_ops, capi.MAX_OPS)
+    real_ops_cap = max(1, max_ops - 2) if K >= 4 else max_ops     # leave room for two swaps
+    owner = {pos[q]: q for q in range(n_qubits)}                  # digit position -> qubit (phantoms absent)
+    remaining = list(qops)
+    plans = []
+
+    def lows():
+        return [owner[d] for d in (0, 1) if d in owner and d < n_digits]
+
+    while remaining:
+        chosen, tile_q = _greedy_select(remaining, lows(), K, real_ops_cap, window, n_qubits)
+        if not chosen:
+            raise RuntimeError("scheduler made no progress")
+        chosen_set = set(chosen)
+        ops_now = [remaining[i] for i in chosen]
+        remaining = [op for i, op in enumerate(remaining) if i not in chosen_set]
+        # tile digit positions: the chosen qubits' positions + positions 0,1 (+ filler)
+        tile_d = {pos[q] for q in tile_q} | {0, 1} if n_digits >= 2 else {pos[q] for q in tile_q}
+        d = 0
+        while len(tile_d) < K:
+            if d not in tile_d:
+                tile_d.add(d)
+            d += 1
+        devops = []
+        for op in ops_now:
+            devops.append(DevOp(op.kind, pos[op.da], None if op.db is None else pos[op.db], op.pa, op.pb, op.coef))
+        # look ahead: which two qubits of this tile should sit in positions 0/1 for the next
+        # pass?  Try every pair (plus "leave as is") and keep the one whose greedy next pass
+        # executes the most ops; ties prefer fewer swaps.
+        if remaining and K >= 4:
+            in_tile = sorted(owner[dd] for dd in tile_d if dd in owner)
+            cur = lows()
+            active = set()
+            for op in remaining[:window]:
+                active.update(op.digits())
+            cands = [q for q in in_tile if q in active]
+            best = (len(_greedy_select(remaining, cur, K, real_ops_cap, window, n_qubits)[0]), 0, tuple(cur))
+            for i in range(len(cands)):
+                for j in range(i + 1, len(cands)):
+                    pair = (cands[i], cands[j])
+                    swaps = sum(1 for q in pair if q not in cur)
+                    cnt = len(_greedy_select(remaining, pair, K, real_ops_cap, window, n_qubits)[0])
+                    if (cnt, -swaps) > (best[0], -best[1]):
+                        best = (cnt, swaps, pair)
+            targets = list(best[2])
+            keep = [q for q in cur if q in targets]
+            new = [q for q in targets if q not in cur]
+            free_low = [dd for dd in (0, 1) if owner.get(dd) not in keep]
+            for q, dd in zip(new, free_low):
+                other = owner.get(dd)
+                src = pos[q]
+                devops.append(DevOp(capi.OP_SWAP, dd, src))
+                owner[dd] = q
+                pos[q] = dd
+                if other is not None:
+                    owner[src] = other
+                    pos[other] = src
+                else:
+                    owner.pop(src, None)
+        plans.append((sorted(tile_d), devops))
+    return encode_passes(plans)
+
+
 def encode_passes(plans):
     """[(sorted tile digits, [DevOp...])] -> PASS_DTYPE array."""
     out = np.zeros(len(plans), dtype=capi.PASS_DTYPE)

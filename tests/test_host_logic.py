@@ -226,6 +226,49 @@ def test_scheduler_preserves_program_order_per_digit(n_digits, max_ops):
     assert sorted(seen) == list(range(len(ops)))
 
 
+@pytest.mark.parametrize("n_qubits,max_ops", [(2, 16), (3, 4), (5, 6), (7, 10), (14, 10), (14, 4)])
+def test_relabel_scheduler_is_a_valid_reordering(n_qubits, max_ops):
+    """Replay the relabelled schedule symbolically: every op lands on the digit positions its
+    qubits occupy at that moment (SWAPs move qubits), per-qubit program order is kept, and the
+    returned layout matches the replay."""
+    rng = np.random.default_rng(n_qubits * 10 + max_ops)
+    qops = []
+    for k in range(150):
+        if n_qubits == 1 or rng.random() < 0.15:
+            qops.append(schedule.DevOp(capi.OP_MATS, int(rng.integers(n_qubits)), None, np.eye(4), None, [float(k)]))
+        else:
+            a, b = rng.choice(n_qubits, size=2, replace=False)
+            qops.append(schedule.DevOp(capi.OP_CX, int(a), int(b), np.eye(4), None, [float(k)]))
+    nd = max(n_qubits, 2)
+    pos = [n_qubits - 1 - q for q in range(n_qubits)]
+    sim = {p: q for q, p in enumerate(pos)}                  # digit position -> qubit
+    passes = schedule.build_passes_relabel(qops, pos, nd, max_ops=max_ops)
+    last, seen = {}, []
+    for p in passes:
+        K = int(p["n_tile_digits"])
+        tile = [int(x) for x in p["tile_digit"][:K]]
+        assert tile[0] == 0 and tile == sorted(set(tile)) and K == min(6, nd) and p["n_ops"] <= 16
+        if nd >= 2:
+            assert tile[1] == 1
+        for o in p["ops"][:p["n_ops"]]:
+            da, db = tile[o["a"]], tile[o["b"]]
+            if o["kind"] == capi.OP_SWAP:
+                sim[da], sim[db] = sim.get(db), sim.get(da)
+                continue
+            tag = int(o["coef"][0])
+            src = qops[tag]
+            assert sim[da] == src.da
+            if src.db is not None:
+                assert sim[db] == src.db
+            for q in src.digits():
+                assert last.get(q, -1) < tag
+                last[q] = tag
+            seen.append(tag)
+    assert sorted(seen) == list(range(len(qops)))
+    for q in range(n_qubits):
+        assert sim[pos[q]] == q
+
+
 def test_scheduler_fuses_brick_layers():
     """Config 3 shape: the fused schedule needs far fewer HBM round trips than gates."""
     from emu_backend import NumpyAllocator, emu_lib
@@ -234,7 +277,7 @@ def test_scheduler_fuses_brick_layers():
     e = engine.PauliEngine.__new__(engine.PauliEngine)     # planning only: no buffers
     e.n, e.nd = 14, 14
     e.pos = [13 - q for q in range(14)]
-    e.pending, e.queue, e.max_ops_per_pass, e.reserve_low, e.drain_threshold = [None] * 14, [], 16, 2, 0
+    e.pending, e.queue, e.max_ops_per_pass, e.reserve_low, e.drain_threshold, e.relabel = [None] * 14, [], 16, 2, 0, False
     for ins in circ.instructions:
         if ins.name == "u3":
             e.apply_1q(ins.qubits[0], engine.gate_matrix("u3", ins.params, {"rz": [1, 0], "ry": [1, 0]}))

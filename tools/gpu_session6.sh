@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== pytest gpu" ; timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" ; tail -3 gpurun_out/pytest_gpu.log
+echo "== bench relabel"; timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench6.json 2> gpurun_out/bench6.err; echo "rc=$?"; cat gpurun_out/bench6.json; tail -3 gpurun_out/bench6.err
+for mo in 6 8 12 16; do DMB_MAX_OPS_PER_PASS=$mo timeout 600 python bench.py --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('relabel maxops',$mo, d['ms_per_step'], d['config']['passes_per_step'], d['roofline']['avg_launch_ms'], d['roofline']['frac'], d['roofline']['fused_ops_per_launch'], d['e2e']['ms_per_step'], d['e2e']['breakdown_ms'])"; done
+echo "== no relabel"; DMB_RELABEL=0 DMB_MAX_OPS_PER_PASS=8 timeout 600 python bench.py --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('norelabel', d['ms_per_step'], d['config']['passes_per_step'], d['roofline']['avg_launch_ms'], d['roofline']['frac'], d['e2e']['ms_per_step'])"
