@@ -166,6 +166,8 @@ def run_ours(args):
     from qiskit_aakash_b200 import BasicAer, DmSimulatorB200, assemble, circuits, engine, hostpass
 
     n, depth, seed = workload(args.gpus)
+    if args.n:
+        n, depth, seed = args.n, (args.depth or depth), 100 * args.n
     circ = circuits.random_layered(n, depth, seed)
     opts = circuits.noisy_options()
     n_gates = sum(1 for i in circ.instructions if i.name in ("u3", "cx"))
@@ -250,7 +252,8 @@ def run_ours(args):
     else:
         nv = {"exchanges_per_step": runner.engine.exchanges / args.steps,
               "nvlink_bytes_sent_per_gpu_per_step": runner.engine.nvlink_bytes_sent / args.steps}
-        e2e = runner.e2e(args, lambda: circuits.random_layered(n, depth, seed), opts, n_gates, device=local_rank)
+        e2e = None if args.no_e2e else runner.e2e(args, lambda: circuits.random_layered(n, depth, seed), opts,
+                                                 n_gates, device=local_rank)
 
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
@@ -341,6 +344,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--n", type=int, default=0, help="override the qubit count (experiments, e.g. --n 18 --depth 20)")
+    ap.add_argument("--depth", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
