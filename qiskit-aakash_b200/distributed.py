@@ -153,6 +153,7 @@ class ShardedPauliEngine(PauliEngine):
         self.h2d_bytes = 0
         self.drain_threshold = 0         # exchanges are collectives: compile whole queues
         self.relabel = False
+        self.relabel_local = bool(int(os.environ.get("DMB_RELABEL", "1")))
         self.exchanges = 0
         self.nvlink_bytes_sent = 0
 
@@ -194,7 +195,26 @@ class ShardedPauliEngine(PauliEngine):
                     keep.append(item)
                 else:
                     run.append(item)
-            devops = [schedule.DevOp(kind, pos[qa], pos[qb], pa, pb, coef) for (_, kind, qa, qb, pa, pb, coef) in run]
+            use_relabel = self.relabel_local and self.nd >= 4
+            chunks = []                      # PASS arrays of this exchange-free stretch
+            if use_relabel:
+                qops = [schedule.DevOp(kind, qa, qb, pa, pb, coef) for (_, kind, qa, qb, pa, pb, coef) in run]
+                if not keep and final:
+                    left = [q for q in range(self.n) if self.pending[q] is not None and pos[q] < n_loc]
+                    left.sort(key=lambda q: pos[q])
+                    for i in range(0, len(left) - 1, 2):
+                        qops.append(schedule.DevOp(capi.OP_MATS, left[i], left[i + 1],
+                                                   self.pending[left[i]], self.pending[left[i + 1]]))
+                    if len(left) % 2:
+                        qops.append(schedule.DevOp(capi.OP_MATS, left[-1], None, self.pending[left[-1]], None))
+                    for q in left:
+                        self.pending[q] = None
+                if qops:
+                    chunks.append(schedule.build_passes_relabel(qops, pos, self.nd, max_ops=self.max_ops_per_pass))
+                devops = []
+            else:
+                devops = [schedule.DevOp(kind, pos[qa], pos[qb], pa, pb, coef)
+                          for (_, kind, qa, qb, pa, pb, coef) in run]
             queue = keep
             if queue:
                 # evict the local qubits whose next use is farthest away (never-used first)
@@ -213,7 +233,7 @@ class ShardedPauliEngine(PauliEngine):
                         devops.append(schedule.DevOp(capi.OP_SWAP, pos[v], target))
                         slot_owner[pos[v]], slot_owner[target] = other, v
                         pos[other], pos[v] = pos[v], target
-            elif final:
+            elif final and not use_relabel:
                 left = sorted((pos[q], q) for q in range(self.n) if self.pending[q] is not None and pos[q] < n_loc)
                 for i in range(0, len(left) - 1, 2):
                     (da, qa), (db, qb) = left[i], left[i + 1]
@@ -224,8 +244,10 @@ class ShardedPauliEngine(PauliEngine):
                 for _, q in left:
                     self.pending[q] = None
             if devops:
-                steps.append(("passes", schedule.build_passes(devops, self.nd, max_ops=self.max_ops_per_pass,
-                                                             reserve_low=self.reserve_low)))
+                chunks.append(schedule.build_passes(devops, self.nd, max_ops=self.max_ops_per_pass,
+                                                    reserve_low=self.reserve_low))
+            if chunks:
+                steps.append(("passes", np.concatenate(chunks) if len(chunks) > 1 else chunks[0]))
             if not queue:
                 break
             steps.append(("exchange",))
