@@ -166,8 +166,8 @@ def run_ours(args):
     from qiskit_aakash_b200 import BasicAer, DmSimulatorB200, assemble, circuits, engine, hostpass
 
     n, depth, seed = workload(args.gpus)
-    if args.n:
-        n, depth, seed = args.n, (args.depth or depth), 100 * args.n
+    if args.qubits:
+        n, depth, seed = args.qubits, (args.layers or depth), 100 * args.qubits
     circ = circuits.random_layered(n, depth, seed)
     opts = circuits.noisy_options()
     n_gates = sum(1 for i in circ.instructions if i.name in ("u3", "cx"))
@@ -344,8 +344,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--n", type=int, default=0, help="override the qubit count (experiments, e.g. --n 18 --depth 20)")
-    ap.add_argument("--depth", type=int, default=0)
+    ap.add_argument("--qubits", type=int, default=0, help="override the qubit count (experiments: --qubits 18 --layers 20)")
+    ap.add_argument("--layers", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
