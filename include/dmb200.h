@@ -84,6 +84,7 @@ typedef struct dmb_stats {
   uint64_t other_launches;       /* every other kernel of this library                     */
   uint64_t fused_ops;            /* dmb_op entries executed                                */
   uint64_t state_bytes_moved;    /* algorithmic HBM bytes of tile passes: 16 B x elements  */
+  uint64_t r3_phases;            /* register phases executed by the 3-digits-per-thread kernel */
 } dmb_stats;
 
 /* ---- context ------------------------------------------------------------------------ */
@@ -99,9 +100,12 @@ int dmb_set_stream(dmb_ctx* ctx, void* cuda_stream);
 int dmb_sync(dmb_ctx* ctx);                                   /* synchronous */
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out);
 int dmb_reset_stats(dmb_ctx* ctx);
-/* Tile-kernel variant for 4^6-coefficient tiles: 0 = persistent cp.async kernel, 2 stages x
- * 3 CTAs/SM (default); 2 = same with 3 stages x 2 CTAs/SM; 3 = 2 stages x 2 CTAs/SM;
- * 1 = the generic register-staged kernel (one tile per CTA), kept for A/B measurements. */
+/* Tile-kernel variant for 4^6-coefficient tiles:
+ *   0 = two digits per thread, persistent cp.async kernel, 2 stages x 3 CTAs/SM
+ *   2 / 3 = same with 3 stages x 2 CTAs/SM / 2 stages x 2 CTAs/SM
+ *   4 / 5 = three digits per thread (ops grouped into register phases), 2 stages x 3 CTAs/SM /
+ *           1 stage x 4 CTAs/SM
+ *   1 = the generic register-staged kernel (one tile per CTA), kept as A/B baseline. */
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant);
 
 /* ---- state initialisation (replaces DmSimulatorPy._initialize_densitymatrix,

@@ -165,6 +165,57 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
 }
 
 // ---------------------------------------------------------------------------------------
+// tile pass, K = 6, three digits per thread (R3): 64 threads per tile, each phase keeps a
+// digit triple's 64 coefficients in registers and runs all ops inside the triple back to
+// back -- roughly half the shared-memory traffic per fused op of k_tile_pass6.
+// ---------------------------------------------------------------------------------------
+template <int STAGES, int CTAS>
+__global__ void __launch_bounds__(DMB_R3_THREADS, CTAS)
+k_tile_pass_r3(double* __restrict__ state, const __grid_constant__ dmb_r3_pass R) {
+  extern __shared__ __align__(128) unsigned char lean_smem[];
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
+  dmb_r3_thread T;
+  dmb_r3_thread_init(threadIdx.x, R, T);
+  const uint64_t first = blockIdx.x;
+  if (first >= R.n_tiles) return;
+  const uint64_t stride = gridDim.x;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    const uint64_t tl = first + (uint64_t)s * stride;
+    if (tl < R.n_tiles) {
+      const double* g = state + dmb_tile_base(tl, R.td, DMB_LEAN_K) + T.goff;
+      const uint32_t dst = smem0 + (uint32_t)s * DMB_LEAN_TILE_BYTES;
+#pragma unroll 8
+      for (int i = 0; i < DMB_R3_PAIRS; ++i) cp_async16s(dst + (T.soff ^ R.pair_soff[i]), g + R.pair_goff[i]);
+    }
+    cp_async_commit();
+  }
+  uint32_t cur = 0, fill = STAGES - 1;
+  for (uint64_t tile = first; tile < R.n_tiles; tile += stride) {
+    const uint64_t ahead = tile + (uint64_t)(STAGES - 1) * stride;
+    if (ahead < R.n_tiles) {
+      const double* g = state + dmb_tile_base(ahead, R.td, DMB_LEAN_K) + T.goff;
+      const uint32_t dst = smem0 + fill * DMB_LEAN_TILE_BYTES;
+#pragma unroll 8
+      for (int i = 0; i < DMB_R3_PAIRS; ++i) cp_async16s(dst + (T.soff ^ R.pair_soff[i]), g + R.pair_goff[i]);
+    }
+    cp_async_commit();
+    cp_async_wait<STAGES - 1>();
+    __syncthreads();
+    dmb_smem_mem mem;
+    mem.base = smem0 + cur * DMB_LEAN_TILE_BYTES;
+    for (int p = 0; p < R.n_phases; ++p) {
+      dmb_r3_phase_thread(T, R, R.phases[p], mem);
+      __syncthreads();
+    }
+    dmb_r3_store_thread(T, R, state + dmb_tile_base(tile, R.td, DMB_LEAN_K), mem);
+    __syncthreads();
+    cur = (cur + 1 == STAGES) ? 0 : cur + 1;
+    fill = (fill + 1 == STAGES) ? 0 : fill + 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // element-wise kernels
 // ---------------------------------------------------------------------------------------
 __global__ void k_init_product(double* __restrict__ state, uint64_t count, const __grid_constant__ dmb_init_params p) {
@@ -283,7 +334,29 @@ static int launch_lean(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
   return 0;
 }
 
+template <int STAGES, int CTAS>
+static int launch_r3(dmb_ctx* ctx, double* state, const dmb_r3_pass& R) {
+  const size_t smem = (size_t)STAGES * DMB_LEAN_TILE_BYTES;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU_TRY(cudaFuncSetAttribute(k_tile_pass_r3<STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
+  if (grid > R.n_tiles) grid = R.n_tiles;
+  k_tile_pass_r3<STAGES, CTAS><<<(unsigned)grid, DMB_R3_THREADS, smem, ctx->stream>>>(state, R);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
 static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass& P) {
+  if (ctx->tile_variant >= 4) {
+    static dmb_r3_pass R;
+    if (dmb_make_r3_pass(P, n_bits, R)) {
+      ctx->stats.r3_phases += (uint64_t)R.n_phases;
+      return ctx->tile_variant == 5 ? launch_r3<1, 4>(ctx, state, R) : launch_r3<2, 3>(ctx, state, R);
+    }
+  }
   static dmb_lean_pass L;                 // 6.5 KB: keep it off the stack; single-threaded per ctx
   dmb_make_lean_pass(P, n_bits, L);
   switch (ctx->tile_variant) {
@@ -387,7 +460,7 @@ int dmb_reset_stats(dmb_ctx* ctx) {
 
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant) {
   if (!ctx) return fail("dmb_set_tile_variant", "null context");
-  if (variant < 0 || variant > 3) return fail("dmb_set_tile_variant", "variant must be 0..3");
+  if (variant < 0 || variant > 5) return fail("dmb_set_tile_variant", "variant must be 0..5");
   ctx->tile_variant = variant;
   return 0;
 }

@@ -83,6 +83,29 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P) {
   }
 }
 
+// R3 path (three digits per thread), same bodies as k_tile_pass_r3
+static long g_r3_passes = 0, g_r3_phases = 0, g_r3_ops = 0;
+extern "C" void dmb_emu_r3_counters(long* out) { out[0] = g_r3_passes; out[1] = g_r3_phases; out[2] = g_r3_ops; }
+
+static bool run_tile_pass_r3(double* state, int n_bits, const dmb_pass& P) {
+  static dmb_r3_pass R;
+  if (!dmb_make_r3_pass(P, n_bits, R)) return false;
+  g_r3_passes++; g_r3_phases += R.n_phases; g_r3_ops += P.n_ops;
+  alignas(128) static unsigned char stage[DMB_LEAN_TILE_BYTES];
+  static dmb_r3_thread T[DMB_R3_THREADS];
+  for (int t = 0; t < DMB_R3_THREADS; ++t) dmb_r3_thread_init(t, R, T[t]);
+  dmb_host_mem mem;
+  mem.base = stage;
+  for (uint64_t tile = 0; tile < R.n_tiles; ++tile) {
+    double* gtile = state + dmb_tile_base(tile, R.td, DMB_LEAN_K);
+    for (int t = 0; t < DMB_R3_THREADS; ++t) dmb_r3_load_thread(T[t], R, gtile, mem);
+    for (int p = 0; p < R.n_phases; ++p)
+      for (int t = 0; t < DMB_R3_THREADS; ++t) dmb_r3_phase_thread(T[t], R, R.phases[p], mem);
+    for (int t = 0; t < DMB_R3_THREADS; ++t) dmb_r3_store_thread(T[t], R, gtile, mem);
+  }
+  return true;
+}
+
 static int g_variant = 0;
 
 extern "C" {
@@ -104,7 +127,7 @@ int dmb_sync(dmb_ctx*) { return 0; }
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out) { *out = ctx->stats; return 0; }
 int dmb_reset_stats(dmb_ctx* ctx) { memset(&ctx->stats, 0, sizeof(dmb_stats)); return 0; }
 int dmb_set_tile_variant(dmb_ctx*, int variant) {
-  if (variant < 0 || variant > 3) return fail("dmb_set_tile_variant", "variant must be 0..3");
+  if (variant < 0 || variant > 5) return fail("dmb_set_tile_variant", "variant must be 0..5");
   g_variant = variant;
   return 0;
 }
@@ -139,6 +162,7 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
       case 5: run_tile_pass<5>(state, n_bits, P); break;
       case 6:
         if (g_variant == 1) run_tile_pass<6>(state, n_bits, P);
+        else if (g_variant >= 4 && run_tile_pass_r3(state, n_bits, P)) {}
         else run_tile_pass6(state, n_bits, P);
         break;
       default: return fail("dmb_apply_passes", "unsupported tile size");
