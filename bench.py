@@ -42,6 +42,15 @@ def workload(n_gpus):
     return {1: (14, 200, 1400), 2: (15, 100, 1500), 4: (15, 100, 1500), 8: (16, 60, 1600)}[n_gpus]
 
 
+def workload_config(n, depth, n_gates=None, extra=None):
+    cfg = {"workload": "random layered U3+CX n=%d depth %d, rotation/tsp error r=0.999, depolarization 0.99, "
+                       "ensemble-Z readout (BASELINE configs[2] shape)" % (n, depth)}
+    if n_gates is not None:
+        cfg["gates"] = n_gates
+    cfg.update(extra or {})
+    return cfg
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -135,7 +144,7 @@ def run_reference_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "random layered U3+CX n=%d depth %d noisy (CPU: bounded sample)" % (n, depth)},
+            "config": workload_config(n, depth, extra={"cpu_sample": sample}),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -267,12 +276,11 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "random layered U3+CX n=%d depth %d, rotation/tsp error r=0.999, "
-                                       "depolarization 0.99, ensemble-Z readout (BASELINE configs[2] shape)" % (n, depth),
-                           "gates": n_gates, "levels": runner.n_levels, "state_bytes": state_bytes,
+                "config": workload_config(n, depth, n_gates, {
+                           "levels": runner.n_levels, "state_bytes": state_bytes,
                            "passes_per_step": counters["tile_pass_launches"] / args.steps,
                            "l2": "state (%.1f GiB/GPU) >> 126 MB L2, no flush needed" % (state_bytes / world / 2 ** 30),
-                           "parallelism": "1 GPU" if world == 1 else "%d GPUs, high-order Pauli digits sharded" % world},
+                           "parallelism": "1 GPU" if world == 1 else "%d GPUs, high-order Pauli digits sharded" % world}),
                 "circuit_ms": ms_step, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(counters["tile_pass_launches"] + counters["other_launches"]),
                 "clocks": clocks}

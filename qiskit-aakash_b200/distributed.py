@@ -22,8 +22,8 @@ high bit of qubit 1's digit.
   whose global bits are not this rank's and folds pending maps of global qubits in as
   weights), one all-reduce of 2^n doubles, then the Walsh-Hadamard transform.
 
-Not sharded yet ("next"): N-basis ensemble, Expect, Bell and
-Pauli->matrix on a sharded state.
+Expect and Bell readouts work on a sharded state (owner rank reads, all-reduce).  Not sharded
+yet ("next"): N-basis ensemble, Pauli->matrix, compare/store.
 """
 from __future__ import annotations
 
@@ -32,7 +32,7 @@ import os
 import numpy as np
 
 from . import capi, schedule
-from .engine import PauliEngine, TorchCudaAllocator, cx_coefficients
+from .engine import PauliEngine, TorchCudaAllocator, cx_coefficients, shared_context
 from .exceptions import BasicAerError
 
 
@@ -140,8 +140,9 @@ class ShardedPauliEngine(PauliEngine):
         self.size = 1 << self.n_bits
         self.lib = lib if lib is not None else capi.load_library()
         self.alloc = allocator if allocator is not None else TorchCudaAllocator(device)
-        self.ctx = capi.Context(self.lib, getattr(self.alloc, "index", 0))
+        self.ctx = shared_context(self.lib, getattr(self.alloc, "index", 0))
         self.ctx.set_stream(self.alloc.stream())
+        self.ctx.reset_stats()
         self.state = self.alloc.empty(self.size)
         self.scratch = self.alloc.empty(self.size)
         self.pos = [self.n - 1 - q for q in range(self.n)]      # qubit -> slot
@@ -310,7 +311,25 @@ class ShardedPauliEngine(PauliEngine):
         raise BasicAerError("N-basis ensemble measurement is not supported on a sharded state yet")
 
     def read_coefficients(self, digit_tuples):
-        raise BasicAerError("coefficient reads (Expect / Bell) are not supported on a sharded state yet")
+        """Coefficients a[p_0..p_{n-1}] of a sharded state: the owning rank reads, one all-reduce
+        (Expect / Bell readouts, ``dm_simulator.py:569-570, 744-760``)."""
+        self._localise_all_pending()
+        mask = (1 << self.n_bits) - 1
+        local_idx, mine = [], []
+        for tup in digit_tuples:
+            g = 0
+            for q, p in enumerate(tup):
+                g |= int(p) << (2 * self.pos[q])
+            mine.append((g >> self.n_bits) == self.rank)
+            local_idx.append(g & mask)
+        vals = self.ctx.read_coeffs(self.sptr, local_idx)
+        vals = np.where(np.array(mine), vals, 0.0)
+        t = self.alloc.empty(len(vals))
+        self.ctx.upload(self.alloc.ptr(t), vals)
+        self.comm.all_reduce_sum(t)
+        out = np.empty(len(vals))
+        self.ctx.download(self.alloc.ptr(t), out)
+        return out
 
     def to_matrix(self):
         raise BasicAerError("compute_densitymatrix is not supported on a sharded state; pass "

@@ -146,9 +146,22 @@ class TorchCudaAllocator:
 # engine
 # --------------------------------------------------------------------------------------
 
+_CONTEXTS = {}
+
+
+def shared_context(lib, device_index):
+    """One ``dmb_ctx`` per (library, device), reused by successive engines: creating one costs
+    two cudaMallocs and a pinned allocation, which dominates the run time of small circuits."""
+    key = (id(lib), int(device_index))
+    ctx = _CONTEXTS.get(key)
+    if ctx is None:
+        ctx = _CONTEXTS[key] = capi.Context(lib, device_index)
+    return ctx
+
+
 class PauliEngine:
     def __init__(self, n_qubits, lib=None, allocator=None, device=0, max_ops_per_pass=None,
-                 reserve_low=None):
+                 reserve_low=None, relabel=None):
         if n_qubits < 1 or n_qubits > capi.MAX_QUBITS:
             raise BasicAerError("number of qubits out of range: %d" % n_qubits)
         self.n = int(n_qubits)
@@ -157,8 +170,9 @@ class PauliEngine:
         self.size = 4 ** self.nd
         self.lib = lib if lib is not None else capi.load_library()
         self.alloc = allocator if allocator is not None else TorchCudaAllocator(device)
-        self.ctx = capi.Context(self.lib, getattr(self.alloc, "index", 0))
+        self.ctx = shared_context(self.lib, getattr(self.alloc, "index", 0))
         self.ctx.set_stream(self.alloc.stream())
+        self.ctx.reset_stats()
         self.state = self.alloc.empty(self.size)
         self.pos = [self.n - 1 - q for q in range(self.n)]     # qubit -> digit position
         self.pending = [None] * self.n
@@ -170,9 +184,9 @@ class PauliEngine:
         self.h2d_bytes = 0
         # launch queued two-qubit ops as soon as this many have accumulated, so that the GPU
         # works while the host is still lowering later levels (0 = only at readouts)
-        self.drain_threshold = int(os.environ.get("DMB_DRAIN_THRESHOLD", 96))
+        self.drain_threshold = int(os.environ.get("DMB_DRAIN_THRESHOLD", 256))
         # dynamic relabelling of the two low digit positions (schedule.build_passes_relabel)
-        self.relabel = bool(int(os.environ.get("DMB_RELABEL", "1")))
+        self.relabel = bool(int(os.environ.get("DMB_RELABEL", "1"))) if relabel is None else bool(relabel)
         if os.environ.get("DMB_TILE_VARIANT"):
             self.ctx.set_tile_variant(int(os.environ["DMB_TILE_VARIANT"]))
 

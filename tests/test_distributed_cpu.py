@@ -72,6 +72,12 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
 
     comm = distributed.TorchCommunicator()
     circ = cases._rand_circuit(n, 45, seed) if mode != "layered" else C.random_layered(n, 5, seed, readout=False)
+    if mode == "expect":
+        circ.measure(0, 0, basis="Expect", add_param=("XZIY" * n)[:n])
+        circ.u3(0.1, 0.2, 0.3, 0); circ.cx(0, n - 1)
+    elif mode == "bell":
+        circ.measure(0, 0, basis="Bell", add_param="0%d" % (n - 1))
+        circ.u3(0.1, 0.2, 0.3, 1); circ.cx(1, 0)
     circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="XYZ"[seed % 3])
     opts = dict(cases.FULL_NOISE, compute_densitymatrix=False)
     engines = []
@@ -90,6 +96,12 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
     p_ref = np.array(list(ref["data"]["ensemble_probability"].values()))
     d_p = float(np.max(np.abs(p_got - p_ref)))
     d_c = float(np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])))
+    assert set(res["data"]) == set(ref["data"]), (set(res["data"]), set(ref["data"]))
+    for key, val in ref["data"].items():
+        if key.startswith(("Pauli_string", "reduced_bell")):
+            d_c = max(d_c, float(np.max(np.abs(np.asarray(val) - np.asarray(res["data"][key])))))
+        elif key.startswith("bell_prob"):
+            d_p = max(d_p, max(abs(val[k] - res["data"][key][k]) for k in val))
     with open(os.path.join(out_dir, "r%d.txt" % rank), "w") as f:
         f.write("%r %r %d %d\n" % (d_p, d_c, engines[0].exchanges, res["number_of_clock_cycles"] - ref["number_of_clock_cycles"]))
     dist.barrier()
@@ -97,7 +109,8 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
 
 
 @pytest.mark.parametrize("world,n,seed,mode", [(2, 5, 1, "rand"), (2, 6, 2, "layered"), (4, 6, 3, "rand"),
-                                               (4, 7, 4, "layered"), (8, 7, 5, "rand"), (8, 7, 6, "layered")])
+                                               (4, 7, 4, "layered"), (8, 7, 5, "rand"), (8, 7, 6, "layered"),
+                                               (2, 5, 7, "expect"), (4, 6, 8, "bell"), (8, 7, 9, "expect")])
 def test_sharded_backend_matches_oracle(world, n, seed, mode, tmp_path):
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(HERE, "emu"))

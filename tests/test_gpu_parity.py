@@ -172,8 +172,9 @@ def test_n14_noisy_invariants_and_schedule_independence(backend):
     circ = C.random_layered(14, 8, 1400)
     opts = dict(C.noisy_options(), compute_densitymatrix=False, **C.grover_options())
     outs = []
-    for max_ops, reserve in ((8, 2), (1, 1)):
-        be = DmSimulatorB200(_engine_factory=lambda n: engine.PauliEngine(n, max_ops_per_pass=max_ops, reserve_low=reserve))
+    for max_ops, reserve, relabel in ((10, 2, True), (1, 1, False)):
+        be = DmSimulatorB200(_engine_factory=lambda n: engine.PauliEngine(n, max_ops_per_pass=max_ops, reserve_low=reserve,
+                                                                          relabel=relabel))
         c2 = C.Circuit(14); c2.instructions = copy.deepcopy(circ.instructions)
         r = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
         outs.append((r["data"]["coeffmatrix"].copy(), np.array(list(r["data"]["ensemble_probability"].values()))))
