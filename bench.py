@@ -220,7 +220,9 @@ def run_ours(args):
     # dominant kernel: tile pass; average launch duration measured live (events around the
     # back-to-back pass launches of every step, accumulated by the runner)
     peak, peak_src = measured_peak()
-    pass_ms = runner.pass_ms_total() / max(1, counters["tile_pass_launches"])
+    timed_launches = runner.timed_pass_launches() if hasattr(runner, "timed_pass_launches") \
+        else counters["tile_pass_launches"]
+    pass_ms = runner.pass_ms_total() / max(1, timed_launches)
     per_launch_bytes = 16.0 * 4 ** n / world
     achieved = per_launch_bytes / (pass_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_tile_pass<6>", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -125,6 +125,21 @@ int dmb_init_product(dmb_ctx* ctx, double* state, int n_bits, uint64_t rank_bits
 int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits,
                      const dmb_pass* passes, size_t n_passes);
 
+/* ---- multi-GPU: fused exchange + tile pass over NVLink peer memory -----------------------
+ * In the pass that follows a global<->local slot swap (qiskit-aakash_b200/distributed.py) the
+ * tile kernel PULLS its input straight from the ranks that hold it in the old layout: element
+ * idx of the new local layout is read from  (const double*)src_tab[idx >> block_shift] + idx
+ * (peer-mapped addresses, 2^tab_bits entries, block_shift + tab_bits == n_bits), the fused ops
+ * are applied, and the tile is written to dst_state[idx].  One kernel = all-to-all + ops; a pass
+ * with n_ops == 0 is a pure exchange.  All ranks must have finished writing their old buffers
+ * (host barrier) before the call, and must not overwrite them until every rank has finished.
+ * dmb_ipc_export / dmb_ipc_open turn a device pointer of one process into a mapped pointer of
+ * another (cudaIpcGetMemHandle / cudaIpcOpenMemHandle; mappings live until process exit). */
+int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb_pass* pass,
+                          const uint64_t* src_tab, int tab_bits, int block_shift);
+int dmb_ipc_export(dmb_ctx* ctx, const void* dev_ptr, unsigned char* handle64, uint64_t* offset);
+int dmb_ipc_open(dmb_ctx* ctx, const unsigned char* handle64, uint64_t offset, void** out_ptr);
+
 /* ---- readout ------------------------------------------------------------------------
  * I/B-marginal of _add_ensemble_measure (:427-481) for basis X/Y/Z: for c in [0,2^n_qubits)
  *   out[c] = sum over the listed digit values of  w * state[...],

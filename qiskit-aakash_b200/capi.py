@@ -55,6 +55,9 @@ _SIGNATURES = {
     "dmb_set_tile_variant": (_i, [_vp, _i]),
     "dmb_init_product": (_i, [_vp, _vp, _i, _u64, _i, _vp, _vp, _vp, _d]),
     "dmb_apply_passes": (_i, [_vp, _vp, _i, _vp, _sz]),
+    "dmb_apply_pass_remote": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i]),
+    "dmb_ipc_export": (_i, [_vp, _vp, _vp, _vp]),
+    "dmb_ipc_open": (_i, [_vp, _vp, _u64, _vp]),
     "dmb_marginal": (_i, [_vp, _vp, _i, _u64, _i, _vp, _vp, _vp, _vp]),
     "dmb_fwht": (_i, [_vp, _vp, _i]),
     "dmb_contract_digit": (_i, [_vp, _vp, _vp, _u64, _u64, _vp]),
@@ -144,6 +147,27 @@ class Context:
             return
         assert passes.dtype == PASS_DTYPE and passes.flags["C_CONTIGUOUS"]
         self._check(self.lib.dmb_apply_passes(self._h, state_ptr, int(n_bits), _ptr(passes), len(passes)))
+
+    def apply_pass_remote(self, dst_ptr, n_bits, one_pass, src_tab, block_shift):
+        """One tile pass whose input is pulled from peer buffers (fused exchange)."""
+        assert one_pass.dtype == PASS_DTYPE and len(one_pass) == 1
+        tab = np.ascontiguousarray(src_tab, dtype=np.uint64)
+        tab_bits = int(len(tab)).bit_length() - 1
+        assert (1 << tab_bits) == len(tab)
+        self._check(self.lib.dmb_apply_pass_remote(self._h, dst_ptr, int(n_bits), _ptr(one_pass), _ptr(tab),
+                                                   tab_bits, int(block_shift)))
+
+    def ipc_export(self, dev_ptr):
+        handle = (ctypes.c_ubyte * 64)()
+        off = ctypes.c_uint64()
+        self._check(self.lib.dmb_ipc_export(self._h, ctypes.c_void_p(dev_ptr), handle, ctypes.byref(off)))
+        return bytes(handle), int(off.value)
+
+    def ipc_open(self, handle, offset):
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        out = ctypes.c_void_p()
+        self._check(self.lib.dmb_ipc_open(self._h, buf, int(offset), ctypes.byref(out)))
+        return int(out.value)
 
     def marginal(self, state_ptr, n_bits, rank_bits, hi, lo, wt, out_ptr):
         hi = np.ascontiguousarray(hi, dtype=np.int32)

@@ -63,17 +63,35 @@ DMB_HD uint64_t dmb_tile_off(uint32_t l, const int32_t* td, int K) {
   return off;
 }
 
+// Fused exchange ("pull"): in the pass that follows a global<->local slot swap, element idx of
+// the NEW local layout is read straight from the rank that holds it in the OLD layout --
+// tab[idx >> shift] is that rank's (peer-mapped) buffer address, pre-offset so that the
+// element sits at tab[..] + idx -- and the result is written to the local destination buffer.
+// One kernel does the all-to-all and the first fused ops; enabled == 0 means in place.
+#define DMB_REMOTE_MAX 32
+struct dmb_remote_src {
+  uint64_t tab[DMB_REMOTE_MAX];
+  int32_t shift;
+  int32_t enabled;
+};
+
+DMB_HD const double* dmb_src_ptr(const dmb_remote_src& S, const double* local, uint64_t idx) {
+  if (!S.enabled) return local + idx;
+  return reinterpret_cast<const double*>(S.tab[idx >> S.shift]) + idx;
+}
+
 // Load phase: thread t moves the 16-byte pairs p = t, t+256, ... (tile_digit[0] == 0, so the
 // two elements of a pair are adjacent in global memory and share a 16-byte chunk of smem).
 template <int MAXPAIRS>
-DMB_HD void dmb_tile_load_thread(int t, const double* __restrict__ gtile, double* smem,
-                                 const int32_t* td, int K) {
+DMB_HD void dmb_tile_load_thread(int t, const double* __restrict__ state, uint64_t tile_base, double* smem,
+                                 const int32_t* td, int K, const dmb_remote_src& S) {
   const uint32_t npairs = 1u << (2 * K - 1);
   dmb_d2 v[MAXPAIRS];
 #pragma unroll
   for (int i = 0; i < MAXPAIRS; ++i) {
     const uint32_t p = (uint32_t)t + (uint32_t)i * DMB_TILE_THREADS;
-    if (p < npairs) v[i] = *reinterpret_cast<const dmb_d2*>(gtile + dmb_tile_off(2u * p, td, K));
+    if (p < npairs)
+      v[i] = *reinterpret_cast<const dmb_d2*>(dmb_src_ptr(S, state, tile_base + dmb_tile_off(2u * p, td, K)));
   }
 #pragma unroll
   for (int i = 0; i < MAXPAIRS; ++i) {
@@ -557,11 +575,12 @@ DMB_HD void dmb_lean_op_dispatch(const dmb_lean_thread& T, const dmb_lean_op& op
 // load / store of one tile (the CUDA kernel replaces the load by cp.async.cg of the same
 // addresses; the store is used as is)
 template <class Mem>
-DMB_HD void dmb_lean_load_thread(const dmb_lean_thread& T, const dmb_lean_pass& L, const double* gtile,
-                                 const Mem& mem) {
+DMB_HD void dmb_lean_load_thread(const dmb_lean_thread& T, const dmb_lean_pass& L, const double* state,
+                                 uint64_t tile_base, const dmb_remote_src& S, const Mem& mem) {
 #pragma unroll
   for (int i = 0; i < DMB_LEAN_PAIRS; ++i)
-    mem.st128(T.soff ^ L.pair_soff[i], *reinterpret_cast<const dmb_d2*>(gtile + (T.goff | L.pair_goff[i])));
+    mem.st128(T.soff ^ L.pair_soff[i],
+              *reinterpret_cast<const dmb_d2*>(dmb_src_ptr(S, state, tile_base + (T.goff | L.pair_goff[i]))));
 }
 
 template <class Mem>

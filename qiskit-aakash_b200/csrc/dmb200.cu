@@ -8,9 +8,10 @@
 // CNOT / diagonal mask / digit swap) applied to each 4^K-coefficient tile while it sits in
 // shared memory.  HBM-bound by design: 16 algorithmic bytes per coefficient per launch.
 #include <cuda_runtime.h>
-#include <cuda.h>
+#include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -54,13 +55,15 @@ static const size_t kScratchElems = 1 << 16;
 // ---------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(DMB_TILE_THREADS, (K == 6 ? 3 : 1))
-k_tile_pass(double* __restrict__ state, const __grid_constant__ dmb_pass P, uint64_t n_tiles) {
+k_tile_pass(double* __restrict__ state, const __grid_constant__ dmb_pass P, uint64_t n_tiles,
+            const __grid_constant__ dmb_remote_src S) {
   extern __shared__ __align__(16) double smem[];
   constexpr int MAXPAIRS = ((1 << (2 * K - 1)) + DMB_TILE_THREADS - 1) / DMB_TILE_THREADS;
   const int t = threadIdx.x;
   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    double* gtile = state + dmb_tile_base(tile, P.tile_digit, K);
-    dmb_tile_load_thread<MAXPAIRS>(t, gtile, smem, P.tile_digit, K);
+    const uint64_t tbase = dmb_tile_base(tile, P.tile_digit, K);
+    double* gtile = state + tbase;
+    dmb_tile_load_thread<MAXPAIRS>(t, state, tbase, smem, P.tile_digit, K, S);
     __syncthreads();
     for (int i = 0; i < P.n_ops; ++i) {
       dmb_tile_op_thread(t, P.ops[i], smem, K);
@@ -116,13 +119,21 @@ __device__ __forceinline__ void cp_async16s(uint32_t smem_dst, const void* gsrc)
 // STAGES-deep ring of 32 KiB stages per CTA: tiles k+1 .. k+STAGES-1 are in flight while the
 // op run executes on tile k.  (STAGES, CTAs per SM) = (2, 3) or (3, 2) fit the 227 KB of
 // shared memory; chosen at run time (dmb_set_tile_variant / DMB_LEAN_STAGES).
-template <int STAGES, int CTAS>
+template <int STAGES, int CTAS, bool REMOTE>
 __global__ void __launch_bounds__(DMB_TILE_THREADS, CTAS)
-k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L) {
+k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L,
+             const __grid_constant__ dmb_remote_src S) {
   extern __shared__ __align__(128) unsigned char lean_smem[];
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
   dmb_lean_thread T;
   dmb_lean_thread_init(threadIdx.x, L, T);
+  // source of pair i of the tile at element offset `tb`: in place, or (fused exchange) the peer
+  // buffer that holds those coefficients in the old layout
+  auto src_of = [&](uint64_t tb, int i) -> const double* {
+    const uint64_t idx = tb + (T.goff | L.pair_goff[i]);
+    if (REMOTE) return reinterpret_cast<const double*>(S.tab[idx >> S.shift]) + idx;
+    return state + idx;
+  };
   const uint64_t first = blockIdx.x;
   if (first >= L.n_tiles) return;
   const uint64_t stride = gridDim.x;
@@ -131,10 +142,10 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
   for (int s = 0; s < STAGES - 1; ++s) {
     const uint64_t tl = first + (uint64_t)s * stride;
     if (tl < L.n_tiles) {
-      const double* g = state + dmb_tile_base(tl, L.td, DMB_LEAN_K) + T.goff;
+      const uint64_t tb = dmb_tile_base(tl, L.td, DMB_LEAN_K);
       const uint32_t dst = smem0 + (uint32_t)s * DMB_LEAN_TILE_BYTES;
 #pragma unroll
-      for (int i = 0; i < DMB_LEAN_PAIRS; ++i) cp_async16s(dst + (T.soff ^ L.pair_soff[i]), g + L.pair_goff[i]);
+      for (int i = 0; i < DMB_LEAN_PAIRS; ++i) cp_async16s(dst + (T.soff ^ L.pair_soff[i]), src_of(tb, i));
     }
     cp_async_commit();
   }
@@ -143,10 +154,10 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
   for (uint64_t tile = first; tile < L.n_tiles; tile += stride) {
     const uint64_t ahead = tile + (uint64_t)(STAGES - 1) * stride;
     if (ahead < L.n_tiles) {
-      const double* g = state + dmb_tile_base(ahead, L.td, DMB_LEAN_K) + T.goff;
+      const uint64_t tb = dmb_tile_base(ahead, L.td, DMB_LEAN_K);
       const uint32_t dst = smem0 + fill * DMB_LEAN_TILE_BYTES;
 #pragma unroll
-      for (int i = 0; i < DMB_LEAN_PAIRS; ++i) cp_async16s(dst + (T.soff ^ L.pair_soff[i]), g + L.pair_goff[i]);
+      for (int i = 0; i < DMB_LEAN_PAIRS; ++i) cp_async16s(dst + (T.soff ^ L.pair_soff[i]), src_of(tb, i));
     }
     cp_async_commit();
     cp_async_wait<STAGES - 1>();
@@ -304,8 +315,11 @@ static inline unsigned grid_for(uint64_t count, int block, int sm_count) {
   return (unsigned)g;
 }
 
+static dmb_remote_src g_no_remote;      // zero-initialised: enabled == 0
+
 template <int K>
-static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass& P) {
+static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass& P,
+                            const dmb_remote_src& S = g_no_remote) {
   const uint64_t n_tiles = 1ull << (n_bits - 2 * K);
   const size_t smem = sizeof(double) << (2 * K);
   static bool attr_done = false;
@@ -314,22 +328,23 @@ static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_p
     attr_done = true;
   }
   const uint64_t grid = n_tiles < 0x7fffffffull ? n_tiles : 0x7fffffffull;
-  k_tile_pass<K><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, P, n_tiles);
+  k_tile_pass<K><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, P, n_tiles, S);
   CU_TRY(cudaGetLastError());
   return 0;
 }
 
-template <int STAGES, int CTAS>
-static int launch_lean(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
+template <int STAGES, int CTAS, bool REMOTE>
+static int launch_lean(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, const dmb_remote_src& S = g_no_remote) {
   const size_t smem = (size_t)STAGES * DMB_LEAN_TILE_BYTES;
   static bool attr_done = false;
   if (!attr_done) {
-    CU_TRY(cudaFuncSetAttribute(k_tile_pass6<STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_tile_pass6<STAGES, CTAS, REMOTE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
     attr_done = true;
   }
   uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
   if (grid > L.n_tiles) grid = L.n_tiles;
-  k_tile_pass6<STAGES, CTAS><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, L);
+  k_tile_pass6<STAGES, CTAS, REMOTE><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, L, S);
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -360,9 +375,9 @@ static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_
   static dmb_lean_pass L;                 // 6.5 KB: keep it off the stack; single-threaded per ctx
   dmb_make_lean_pass(P, n_bits, L);
   switch (ctx->tile_variant) {
-    case 2: return launch_lean<3, 2>(ctx, state, L);
-    case 3: return launch_lean<2, 2>(ctx, state, L);
-    default: return launch_lean<2, 3>(ctx, state, L);
+    case 2: return launch_lean<3, 2, false>(ctx, state, L);
+    case 3: return launch_lean<2, 2, false>(ctx, state, L);
+    default: return launch_lean<2, 3, false>(ctx, state, L);
   }
 }
 
@@ -512,6 +527,85 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
     ctx->stats.fused_ops += (uint64_t)P.n_ops;
     ctx->stats.state_bytes_moved += 16ull << n_bits;
   }
+  return 0;
+}
+
+int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb_pass* pass,
+                          const uint64_t* src_tab, int tab_bits, int block_shift) {
+  if (!ctx || !dst_state || !pass || !src_tab) return fail("dmb_apply_pass_remote", "null argument");
+  if (tab_bits < 0 || (1 << tab_bits) > DMB_REMOTE_MAX) return fail("dmb_apply_pass_remote", "table too large");
+  if (block_shift + tab_bits != n_bits) return fail("dmb_apply_pass_remote", "block_shift + tab_bits != n_bits");
+  CU_TRY(cudaSetDevice(ctx->device));
+  const dmb_pass& P = *pass;
+  if (validate_pass(P, n_bits)) return 1;
+  dmb_remote_src S;
+  memset(&S, 0, sizeof(S));
+  for (int i = 0; i < (1 << tab_bits); ++i) S.tab[i] = src_tab[i];
+  S.shift = block_shift;
+  S.enabled = 1;
+  int rc = 0;
+  switch (P.n_tile_digits) {
+    case 2: rc = launch_tile_pass<2>(ctx, dst_state, n_bits, P, S); break;
+    case 3: rc = launch_tile_pass<3>(ctx, dst_state, n_bits, P, S); break;
+    case 4: rc = launch_tile_pass<4>(ctx, dst_state, n_bits, P, S); break;
+    case 5: rc = launch_tile_pass<5>(ctx, dst_state, n_bits, P, S); break;
+    case 6: {
+      static dmb_lean_pass L;
+      dmb_make_lean_pass(P, n_bits, L);
+      rc = launch_lean<2, 3, true>(ctx, dst_state, L, S);
+      break;
+    }
+    default: return fail("dmb_apply_pass_remote", "unsupported tile size");
+  }
+  if (rc) return rc;
+  ctx->stats.tile_pass_launches++;
+  ctx->stats.fused_ops += (uint64_t)P.n_ops;
+  ctx->stats.state_bytes_moved += 16ull << n_bits;
+  return 0;
+}
+
+int dmb_ipc_export(dmb_ctx* ctx, const void* dev_ptr, unsigned char* handle64, uint64_t* offset) {
+  if (!ctx || !dev_ptr || !handle64 || !offset) return fail("dmb_ipc_export", "null argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  // the handle names the whole allocation: find its base through the driver API, resolved at
+  // run time so that the library still loads on machines without libcuda (build/CI boxes)
+  typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+  static range_fn get_range = nullptr;
+  if (!get_range) {
+    void* drv = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (drv) get_range = (range_fn)dlsym(drv, "cuMemGetAddressRange_v2");
+    if (!get_range) return fail("dmb_ipc_export", "cuMemGetAddressRange_v2 not available");
+  }
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (get_range(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) != 0)
+    return fail("dmb_ipc_export", "cuMemGetAddressRange failed");
+  cudaIpcMemHandle_t h;
+  CU_TRY(cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  *offset = (uint64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
+  return 0;
+}
+
+int dmb_ipc_open(dmb_ctx* ctx, const unsigned char* handle64, uint64_t offset, void** out_ptr) {
+  if (!ctx || !handle64 || !out_ptr) return fail("dmb_ipc_open", "null argument");
+  CU_TRY(cudaSetDevice(ctx->device));
+  // an allocation can be mapped only once per process: remember what is already open
+  // (PyTorch's caching allocator hands the same allocation to successive engines)
+  static std::map<std::string, void*> opened;
+  const std::string key((const char*)handle64, 64);
+  auto it = opened.find(key);
+  void* base = nullptr;
+  if (it != opened.end()) {
+    base = it->second;
+  } else {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CU_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    opened[key] = base;
+  }
+  *out_ptr = (void*)((char*)base + offset);
   return 0;
 }
 

@@ -112,6 +112,23 @@ class TorchCommunicator:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
 
+    def peer_addresses(self, ctx, ptrs):
+        """Addresses, valid in THIS process, of every rank's buffers ``ptrs`` (one list per
+        buffer): CUDA IPC handles exchanged through torch.distributed, peers mapped over
+        NVLink.  Returns None when the buffers are not CUDA memory (gloo CPU tests)."""
+        if not self.torch.cuda.is_available() or self.dist.get_backend(self.group) != "nccl":
+            return None
+        mine = [ctx.ipc_export(p) for p in ptrs]
+        everyone = [None] * self.world
+        self.dist.all_gather_object(everyone, mine, group=self.group)
+        out = []
+        for b in range(len(ptrs)):
+            row = []
+            for r in range(self.world):
+                row.append(ptrs[b] if r == self.rank else ctx.ipc_open(*everyone[r][b]))
+            out.append(row)
+        return out
+
     def all_reduce_sum(self, tensor):
         self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, group=self.group)
 
@@ -157,6 +174,11 @@ class ShardedPauliEngine(PauliEngine):
         self.relabel_local = bool(int(os.environ.get("DMB_RELABEL", "1")))
         self.exchanges = 0
         self.nvlink_bytes_sent = 0
+        # fused exchange: the pass after a slot swap pulls its tiles from the peers' buffers
+        self.peers = None
+        if bool(int(os.environ.get("DMB_FUSED_EXCHANGE", "1"))) and callable(getattr(comm, "peer_addresses", None)):
+            self.peers = comm.peer_addresses(self.ctx, [self.alloc.ptr(self.state), self.alloc.ptr(self.scratch)])
+        self._cur = 0                    # which of the two registered buffers is `state`
 
     # -- layout -------------------------------------------------------------------------------
     def is_local(self, q):
@@ -262,17 +284,49 @@ class ShardedPauliEngine(PauliEngine):
         return steps
 
     def run_steps(self, steps):
-        for step in steps:
+        i = 0
+        while i < len(steps):
+            step = steps[i]
             if step[0] == "passes":
                 self.run_passes(step[1])
+            elif self.peers is not None and i + 1 < len(steps) and steps[i + 1][0] == "passes":
+                nxt = steps[i + 1][1]
+                self.exchange(first_pass=nxt[:1])
+                self.run_passes(nxt[1:])
+                i += 1
             else:
                 self.exchange()
+            i += 1
 
-    def exchange(self):
-        self.comm.exchange(self.plan_x, self.state, self.scratch)
+    def exchange(self, first_pass=None):
+        """Swap the m global slots with the m top local slots.  With peer-mapped buffers this is
+        ONE tile-kernel launch that pulls every tile from the rank holding it in the old layout
+        (NVLink loads), applies ``first_pass``'s fused ops and writes the new layout; otherwise
+        an out-of-place NCCL block exchange."""
+        px = self.plan_x
+        if self.peers is not None:
+            if first_pass is None or len(first_pass) == 0:
+                first_pass = np.zeros(1, dtype=capi.PASS_DTYPE)
+                K = min(capi.MAX_TILE_DIGITS, self.nd)
+                first_pass[0]["n_tile_digits"] = K
+                first_pass[0]["tile_digit"][:K] = list(range(K))
+            self.ctx.sync()
+            self.comm.barrier()              # every rank's old buffer is final
+            old = self.peers[self._cur]
+            tab = np.zeros(1 << px.block_bits, dtype=np.uint64)
+            for d in range(1 << px.block_bits):
+                sr, sb = px.image(self.rank, d)
+                tab[d] = (old[sr] + ((sb - d) << px.B) * 8) % (1 << 64)
+            self.ctx.set_stream(self.alloc.stream())
+            self.ctx.apply_pass_remote(self.alloc.ptr(self.scratch), self.n_bits,
+                                       np.ascontiguousarray(first_pass), tab, px.B)
+            self.passes_run += 1
+            self._cur ^= 1
+        else:
+            self.comm.exchange(px, self.state, self.scratch)
         self.state, self.scratch = self.scratch, self.state
         self.exchanges += 1
-        self.nvlink_bytes_sent += self.plan_x.bytes_sent()
+        self.nvlink_bytes_sent += px.bytes_sent()
 
     def flush(self):
         saved = list(self.pos)
@@ -409,15 +463,32 @@ class ShardedCircuitRunner:
         e = self.engine
         e.init_product([[1, 0, 0, 1]] * self.n, 0.5 ** self.n)
         cuda = torch.cuda.is_available()
-        for st in self.steps:
-            if st[0] == "passes" and cuda:
+
+        def timed(passes):
+            if len(passes) == 0:
+                return
+            if cuda:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                e.run_passes(st[1])
+                e.run_passes(passes)
                 b.record()
-                self._ev.append((a, b))
+                self._ev.append((a, b, len(passes)))
             else:
-                e.run_steps([st])
+                e.run_passes(passes)
+
+        i = 0
+        while i < len(self.steps):
+            st = self.steps[i]
+            if st[0] == "passes":
+                timed(st[1])
+            elif e.peers is not None and i + 1 < len(self.steps) and self.steps[i + 1][0] == "passes":
+                nxt = self.steps[i + 1][1]
+                e.exchange(first_pass=nxt[:1])        # fused: exchange + first pass in one launch
+                timed(nxt[1:])
+                i += 1
+            else:
+                e.exchange()
+            i += 1
         e.pos = list(self.final_pos)
         e.pending = list(self.final_pending)
         self.probs = e.marginal_probabilities("Z", self.err)
@@ -435,7 +506,10 @@ class ShardedCircuitRunner:
     def pass_ms_total(self):
         import torch
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in self._ev)
+        return sum(ev[0].elapsed_time(ev[1]) for ev in self._ev)
+
+    def timed_pass_launches(self):
+        return sum(ev[2] for ev in self._ev)
 
     def e2e(self, args, circ_fn, opts, n_gates, device=0):
         """Public-API timing on the sharded engine: backend.run(qobj).result() on every rank,

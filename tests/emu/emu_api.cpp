@@ -51,14 +51,18 @@ static int validate_pass(const dmb_pass& P, int n_bits) {
   return 0;
 }
 
+static dmb_remote_src g_no_remote;   // zero-initialised: in place
+
 template <int K>
-static void run_tile_pass(double* state, int n_bits, const dmb_pass& P) {
+static void run_tile_pass(double* state, int n_bits, const dmb_pass& P, const dmb_remote_src& S = g_no_remote) {
   constexpr int MAXPAIRS = ((1 << (2 * K - 1)) + DMB_TILE_THREADS - 1) / DMB_TILE_THREADS;
   const uint64_t n_tiles = 1ull << (n_bits - 2 * K);
   alignas(16) static thread_local double smem[1 << 12];
   for (uint64_t tile = 0; tile < n_tiles; ++tile) {
-    double* gtile = state + dmb_tile_base(tile, P.tile_digit, K);
-    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_tile_load_thread<MAXPAIRS>(t, gtile, smem, P.tile_digit, K);
+    const uint64_t tbase = dmb_tile_base(tile, P.tile_digit, K);
+    double* gtile = state + tbase;
+    for (int t = 0; t < DMB_TILE_THREADS; ++t)
+      dmb_tile_load_thread<MAXPAIRS>(t, state, tbase, smem, P.tile_digit, K, S);
     for (int i = 0; i < P.n_ops; ++i)
       for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_tile_op_thread(t, P.ops[i], smem, K);
     for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_tile_store_thread<MAXPAIRS>(t, gtile, smem, P.tile_digit, K);
@@ -66,17 +70,18 @@ static void run_tile_pass(double* state, int n_bits, const dmb_pass& P) {
 }
 
 // lean K = 6 path: same per-thread bodies as k_tile_pass6, tiles processed one after another
-static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P) {
-  static dmb_lean_pass L;
+static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const dmb_remote_src& S = g_no_remote) {
+  static thread_local dmb_lean_pass L;
   dmb_make_lean_pass(P, n_bits, L);
-  alignas(128) static unsigned char stage[DMB_LEAN_TILE_BYTES];
-  static dmb_lean_thread T[DMB_TILE_THREADS];
+  alignas(128) static thread_local unsigned char stage[DMB_LEAN_TILE_BYTES];
+  static thread_local dmb_lean_thread T[DMB_TILE_THREADS];
   for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_thread_init(t, L, T[t]);
   dmb_host_mem mem;
   mem.base = stage;
   for (uint64_t tile = 0; tile < L.n_tiles; ++tile) {
-    double* gtile = state + dmb_tile_base(tile, L.td, DMB_LEAN_K);
-    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, gtile, mem);
+    const uint64_t tbase = dmb_tile_base(tile, L.td, DMB_LEAN_K);
+    double* gtile = state + tbase;
+    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, state, tbase, S, mem);
     for (int i = 0; i < L.n_ops; ++i)
       for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_dispatch(T[t], L.ops[i], mem);
     for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_store_thread(T[t], L, gtile, mem);
@@ -88,11 +93,11 @@ static long g_r3_passes = 0, g_r3_phases = 0, g_r3_ops = 0;
 extern "C" void dmb_emu_r3_counters(long* out) { out[0] = g_r3_passes; out[1] = g_r3_phases; out[2] = g_r3_ops; }
 
 static bool run_tile_pass_r3(double* state, int n_bits, const dmb_pass& P) {
-  static dmb_r3_pass R;
+  static thread_local dmb_r3_pass R;
   if (!dmb_make_r3_pass(P, n_bits, R)) return false;
   g_r3_passes++; g_r3_phases += R.n_phases; g_r3_ops += P.n_ops;
-  alignas(128) static unsigned char stage[DMB_LEAN_TILE_BYTES];
-  static dmb_r3_thread T[DMB_R3_THREADS];
+  alignas(128) static thread_local unsigned char stage[DMB_LEAN_TILE_BYTES];
+  static thread_local dmb_r3_thread T[DMB_R3_THREADS];
   for (int t = 0; t < DMB_R3_THREADS; ++t) dmb_r3_thread_init(t, R, T[t]);
   dmb_host_mem mem;
   mem.base = stage;
@@ -171,6 +176,46 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
     ctx->stats.fused_ops += (uint64_t)P.n_ops;
     ctx->stats.state_bytes_moved += 16ull << n_bits;
   }
+  return 0;
+}
+
+int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb_pass* pass,
+                          const uint64_t* src_tab, int tab_bits, int block_shift) {
+  if ((1 << tab_bits) > DMB_REMOTE_MAX) return fail("dmb_apply_pass_remote", "table too large");
+  if (block_shift + tab_bits != n_bits) return fail("dmb_apply_pass_remote", "block_shift + tab_bits != n_bits");
+  const dmb_pass& P = *pass;
+  if (validate_pass(P, n_bits)) return 1;
+  dmb_remote_src S;
+  memset(&S, 0, sizeof(S));
+  for (int i = 0; i < (1 << tab_bits); ++i) S.tab[i] = src_tab[i];
+  S.shift = block_shift;
+  S.enabled = 1;
+  switch (P.n_tile_digits) {
+    case 2: run_tile_pass<2>(dst_state, n_bits, P, S); break;
+    case 3: run_tile_pass<3>(dst_state, n_bits, P, S); break;
+    case 4: run_tile_pass<4>(dst_state, n_bits, P, S); break;
+    case 5: run_tile_pass<5>(dst_state, n_bits, P, S); break;
+    case 6: run_tile_pass6(dst_state, n_bits, P, S); break;
+    default: return fail("dmb_apply_pass_remote", "unsupported tile size");
+  }
+  ctx->stats.tile_pass_launches++;
+  ctx->stats.fused_ops += (uint64_t)P.n_ops;
+  ctx->stats.state_bytes_moved += 16ull << n_bits;
+  return 0;
+}
+
+// in the emulation "peers" are threads of one process: a handle is just the pointer
+int dmb_ipc_export(dmb_ctx*, const void* dev_ptr, unsigned char* handle64, uint64_t* offset) {
+  memset(handle64, 0, 64);
+  memcpy(handle64, &dev_ptr, sizeof(dev_ptr));
+  *offset = 0;
+  return 0;
+}
+
+int dmb_ipc_open(dmb_ctx*, const unsigned char* handle64, uint64_t offset, void** out_ptr) {
+  void* p = nullptr;
+  memcpy(&p, handle64, sizeof(p));
+  *out_ptr = (char*)p + offset;
   return 0;
 }
 

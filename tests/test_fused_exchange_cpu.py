@@ -1,0 +1,115 @@
+"""CPU test of the fused exchange (tile pass that pulls its input from peer buffers): the ranks
+are threads of one process, so "peer-mapped" pointers are ordinary pointers and the CPU
+emulation of the kernels can follow them.  Covers the source-table arithmetic of
+``ShardedPauliEngine.exchange`` and ``dmb_apply_pass_remote`` for world sizes 2 / 4 / 8
+(including half-digit sharding) against the oracle, and against the NCCL-style block exchange."""
+import copy
+import threading
+
+import numpy as np
+import pytest
+
+import cases
+from emu_backend import NumpyAllocator, emu_lib
+from oracle import dm_oracle
+from qiskit_aakash_b200 import assemble, circuits as C, distributed
+from qiskit_aakash_b200.dm_simulator import DmSimulatorB200
+
+
+class ThreadCluster:
+    def __init__(self, world):
+        self.world = world
+        self.bar = threading.Barrier(world, timeout=120)
+        self.slots = [None] * world
+
+
+class ThreadComm:
+    """In-process stand-in for TorchCommunicator (same interface)."""
+
+    def __init__(self, cluster, rank, fused):
+        self.c, self.rank, self.world, self.fused = cluster, rank, cluster.world, fused
+        if not fused:
+            self.peer_addresses = None
+
+    def barrier(self):
+        self.c.bar.wait()
+
+    def _share(self, obj):
+        self.c.slots[self.rank] = obj
+        self.c.bar.wait()
+        got = list(self.c.slots)
+        self.c.bar.wait()
+        return got
+
+    def exchange(self, plan, src, dst):
+        bufs = self._share(src)
+        be = plan.block_elems
+        for d in range(1 << plan.block_bits):
+            sr, sb = plan.image(self.rank, d)
+            dst[d * be:(d + 1) * be] = bufs[sr][sb * be:(sb + 1) * be]
+        self.c.bar.wait()
+
+    def all_reduce_sum(self, tensor):
+        total = np.sum(np.stack([np.array(x, copy=True) for x in self._share(tensor)]), axis=0)
+        self.c.bar.wait()                 # everyone has read before anyone overwrites
+        tensor[:] = total
+        self.c.bar.wait()
+
+    def all_gather_host(self, arr):
+        return self._share(arr)
+
+    def peer_addresses(self, ctx, ptrs):
+        everyone = self._share(list(ptrs))
+        return [[everyone[r][b] for r in range(self.world)] for b in range(len(ptrs))]
+
+
+def _run_world(world, n, circ, opts, fused):
+    cluster = ThreadCluster(world)
+    out, errs = [None] * world, []
+
+    def work(rank):
+        try:
+            comm = ThreadComm(cluster, rank, fused)
+            engines = []
+
+            def factory(nq):
+                e = distributed.ShardedPauliEngine(nq, comm, lib=emu_lib(), allocator=NumpyAllocator(), max_ops_per_pass=4)
+                engines.append(e)
+                return e
+
+            be = DmSimulatorB200(_engine_factory=factory)
+            c2 = C.Circuit(n)
+            c2.instructions = copy.deepcopy(circ.instructions)
+            res = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
+            out[rank] = (res, engines[0].exchanges, engines[0].peers is not None)
+        except Exception as exc:                     # pragma: no cover - surfaced below
+            errs.append(exc)
+            cluster.bar.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errs:
+        raise errs[0]
+    return out
+
+
+@pytest.mark.parametrize("world,n,seed,mode", [(2, 6, 1, "rand"), (2, 7, 2, "layered"), (4, 7, 3, "rand"),
+                                               (4, 8, 4, "layered"), (8, 8, 5, "rand"), (8, 8, 6, "layered"),
+                                               (8, 7, 7, "rand")])
+def test_fused_exchange_matches_oracle(world, n, seed, mode):
+    circ = cases._rand_circuit(n, 50, seed) if mode == "rand" else C.random_layered(n, 6, seed, readout=False)
+    circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="XYZ"[seed % 3])
+    opts = dict(cases.FULL_NOISE, compute_densitymatrix=False)
+    ref = dm_oracle.run_oracle(n, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
+    p_ref = np.array(list(ref["data"]["ensemble_probability"].values()))
+    for fused in (True, False):
+        outs = _run_world(world, n, circ, opts, fused)
+        for rank, (res, exchanges, has_peers) in enumerate(outs):
+            assert has_peers == fused
+            assert exchanges >= 1
+            p = np.array(list(res["data"]["ensemble_probability"].values()))
+            assert np.max(np.abs(p - p_ref)) <= 1e-10
+            assert np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])) <= 1e-10
