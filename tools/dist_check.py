@@ -50,7 +50,7 @@ def main():
             d_c = float(np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])))
             worst = max(worst, d_p, d_c)
             print(json.dumps({"check": "sharded_vs_oracle", "world": world, "n": n, "mode": mode, "d_prob": d_p,
-                              "d_coeff": d_c, "exchanges": engines[0].exchanges,
+                              "d_coeff": d_c, "exchanges": engines[0].exchanges, "fused_exchange": engines[0].peers is not None,
                               "nvlink_bytes_sent_per_rank": engines[0].nvlink_bytes_sent}))
         dist.barrier()
     if rank == 0:
