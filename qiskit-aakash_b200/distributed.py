@@ -165,7 +165,7 @@ class ShardedPauliEngine(PauliEngine):
         self.pos = [self.n - 1 - q for q in range(self.n)]      # qubit -> slot
         self.pending = [None] * self.n
         self.queue = []
-        self.max_ops_per_pass = int(max_ops_per_pass or os.environ.get("DMB_MAX_OPS_PER_PASS", 8))
+        self.max_ops_per_pass = int(max_ops_per_pass or os.environ.get("DMB_MAX_OPS_PER_PASS", 10))
         self.reserve_low = int(reserve_low if reserve_low is not None else os.environ.get("DMB_RESERVE_LOW", 2))
         self.passes_run = 0
         self.h2d_bytes = 0
