@@ -105,6 +105,7 @@ int dmb_reset_stats(dmb_ctx* ctx);
  *   2 / 3 = same with 3 stages x 2 CTAs/SM / 2 stages x 2 CTAs/SM
  *   4 / 5 = three digits per thread (ops grouped into register phases), 2 stages x 3 CTAs/SM /
  *           1 stage x 4 CTAs/SM
+ *   6 / 7 = two digits per thread without prefetch ring, 1 stage x 4 / 5 CTAs/SM
  *   1 = the generic register-staged kernel (one tile per CTA), kept as A/B baseline. */
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant);
 

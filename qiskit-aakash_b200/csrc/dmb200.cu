@@ -365,7 +365,7 @@ static int launch_r3(dmb_ctx* ctx, double* state, const dmb_r3_pass& R) {
 }
 
 static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass& P) {
-  if (ctx->tile_variant >= 4) {
+  if (ctx->tile_variant == 4 || ctx->tile_variant == 5) {
     static dmb_r3_pass R;
     if (dmb_make_r3_pass(P, n_bits, R)) {
       ctx->stats.r3_phases += (uint64_t)R.n_phases;
@@ -377,6 +377,8 @@ static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_
   switch (ctx->tile_variant) {
     case 2: return launch_lean<3, 2, false>(ctx, state, L);
     case 3: return launch_lean<2, 2, false>(ctx, state, L);
+    case 6: return launch_lean<1, 4, false>(ctx, state, L);
+    case 7: return launch_lean<1, 5, false>(ctx, state, L);
     default: return launch_lean<2, 3, false>(ctx, state, L);
   }
 }
@@ -475,7 +477,7 @@ int dmb_reset_stats(dmb_ctx* ctx) {
 
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant) {
   if (!ctx) return fail("dmb_set_tile_variant", "null context");
-  if (variant < 0 || variant > 5) return fail("dmb_set_tile_variant", "variant must be 0..5");
+  if (variant < 0 || variant > 7) return fail("dmb_set_tile_variant", "variant must be 0..7");
   ctx->tile_variant = variant;
   return 0;
 }

@@ -132,7 +132,7 @@ int dmb_sync(dmb_ctx*) { return 0; }
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out) { *out = ctx->stats; return 0; }
 int dmb_reset_stats(dmb_ctx* ctx) { memset(&ctx->stats, 0, sizeof(dmb_stats)); return 0; }
 int dmb_set_tile_variant(dmb_ctx*, int variant) {
-  if (variant < 0 || variant > 5) return fail("dmb_set_tile_variant", "variant must be 0..5");
+  if (variant < 0 || variant > 7) return fail("dmb_set_tile_variant", "variant must be 0..7");
   g_variant = variant;
   return 0;
 }
@@ -167,7 +167,7 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
       case 5: run_tile_pass<5>(state, n_bits, P); break;
       case 6:
         if (g_variant == 1) run_tile_pass<6>(state, n_bits, P);
-        else if (g_variant >= 4 && run_tile_pass_r3(state, n_bits, P)) {}
+        else if ((g_variant == 4 || g_variant == 5) && run_tile_pass_r3(state, n_bits, P)) {}
         else run_tile_pass6(state, n_bits, P);
         break;
       default: return fail("dmb_apply_passes", "unsupported tile size");
