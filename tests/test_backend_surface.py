@@ -1,0 +1,140 @@
+"""The reference-facing surface of the backend: result-dict schema,
+option handling incl. the reference's sticky/leaky quirks, error behaviour, provider lookup.
+Runs on the CPU emulation of the kernels (host logic is what is under test)."""
+import copy
+
+import numpy as np
+import pytest
+
+from emu_backend import emu_backend
+from oracle import dm_oracle
+from qiskit_aakash_b200 import BasicAer, BasicAerError, Circuit, assemble, circuits as C
+from qiskit_aakash_b200.dm_simulator import DmSimulatorB200
+
+
+def _run(be, circ, **opts):
+    return be.run(assemble(circ), backend_options=opts).result()
+
+
+def test_result_dict_schema():
+    """dm_simulator.py:938-946 and :1189-1196."""
+    res = _run(emu_backend(), C.qft(3))
+    assert set(res) == {"backend_name", "backend_version", "qobj_id", "job_id", "results", "status", "success",
+                        "time_taken", "header"}
+    assert res["backend_name"] == "dm_simulator" and res["status"] == "COMPLETED" and res["success"] is True
+    r = res["results"][0]
+    assert set(r) == {"name", "number_of_clock_cycles", "data", "status", "success", "processing_time_taken",
+                      "running_time_taken", "header"}
+    assert r["status"] == "DONE" and r["name"] == "qft3"
+    assert list(r["data"]) == ["ensemble_probability", "coeffmatrix", "densitymatrix"]
+    assert r["data"]["coeffmatrix"].shape == (64,) and r["data"]["densitymatrix"].shape == (8, 8)
+    assert list(r["data"]["ensemble_probability"])[:3] == ["000", "001", "010"]
+
+
+def test_several_experiments_in_one_qobj():
+    be = emu_backend()
+    res = be.run(assemble([C.ghz(2), C.ghz(3)]), backend_options={}).result()
+    assert [r["name"] for r in res["results"]] == ["ghz2", "ghz3"]
+    assert res["results"][1]["data"]["coeffmatrix"].size == 64
+
+
+def test_rotation_error_leaks_into_later_runs_like_the_reference():
+    """_set_options mutates the default dict in place (dm_simulator.py:182,212-213)."""
+    be = emu_backend()
+    c = Circuit(1); c.h(0)
+    clean = _run(be, c)["results"][0]["data"]["coeffmatrix"].copy()
+    _run(be, c, rotation_error={"rz": [0.9, 0.0]})
+    leaked = _run(be, c)["results"][0]["data"]["coeffmatrix"]
+    ref = dm_oracle.run_oracle(1, copy.deepcopy(c.instructions), {"rotation_error": {"rz": [0.9, 0.0]}})
+    assert not np.allclose(leaked, clean)
+    assert np.allclose(leaked, ref["data"]["coeffmatrix"], atol=1e-15)
+    fresh = _run(emu_backend(), c)["results"][0]["data"]["coeffmatrix"]
+    assert np.allclose(fresh, clean, atol=1e-15)
+
+
+def test_custom_densitymatrix_and_compute_flag_are_sticky():
+    """dm_simulator.py:200-205 (never reset) and :247-248."""
+    be = emu_backend()
+    c = Circuit(2)
+    d1 = _run(be, c, custom_densitymatrix="max_mixed", compute_densitymatrix=False)["results"][0]["data"]
+    assert "densitymatrix" not in d1 and np.allclose(d1["coeffmatrix"], [0.25] + [0] * 15)
+    d2 = _run(be, c)["results"][0]["data"]
+    assert "densitymatrix" not in d2 and np.allclose(d2["coeffmatrix"], [0.25] + [0] * 15)
+
+
+def test_bell_depolarization_factor_is_ineffective():
+    """dm_simulator.py:240 stores it under an attribute nobody reads."""
+    c = Circuit(3); c.h(0); c.cx(0, 1); c.measure(0, 0, basis="Bell", add_param="12")
+    a = _run(emu_backend(), c)["results"][0]["data"]
+    b = _run(emu_backend(), c, bell_depolarization_factor=0.1)["results"][0]["data"]
+    assert a["bell_probabilities12"] == b["bell_probabilities12"]
+    assert np.array_equal(a["coeffmatrix"], b["coeffmatrix"])
+
+
+def test_bad_options_raise_basicaererror():
+    be = emu_backend()
+    with pytest.raises(BasicAerError):
+        _run(be, Circuit(1), rotation_error=[1.0, 0.0])
+    with pytest.raises(BasicAerError):
+        _run(be, Circuit(1), rotation_error={"rq": [1.0, 0.0]})
+    with pytest.raises(BasicAerError):
+        _run(be, Circuit(1), tsp_model_error=[1.5, 0.0])
+    with pytest.raises(BasicAerError):
+        _run(emu_backend(), Circuit(2), custom_densitymatrix="binary_string", initial_densitymatrix="011")
+    with pytest.raises(BasicAerError):
+        _run(emu_backend(), Circuit(1), custom_densitymatrix="no_such_state")
+    with pytest.raises(BasicAerError):      # a bare vector is rejected exactly like the reference (:344-345)
+        _run(emu_backend(), Circuit(1), initial_densitymatrix=[0.5, 0, 0, 0.5])
+
+
+def test_unknown_instruction_and_too_many_qubits():
+    be = emu_backend()
+    c = Circuit(1)
+    c.instructions.append(C.instr("unitary", [0], [np.eye(2)]))
+    with pytest.raises(Exception):
+        _run(be, c)
+    big = Circuit(DmSimulatorB200.MAX_QUBITS_MEMORY + 1)
+    with pytest.raises(BasicAerError):
+        _run(be, big)
+
+
+def test_job_object_and_provider():
+    be = emu_backend()
+    job = be.run(assemble(C.ghz(2)), backend_options={})
+    assert job.status() == "DONE" and isinstance(job.job_id(), str) and job.backend() is be
+    assert BasicAer.get_backend("dm_simulator") is BasicAer.get_backend("dm_simulator_py")
+    assert BasicAer.get_backend("dm_simulator").name() == "dm_simulator"
+    assert BasicAer.get_backend().configuration().basis_gates == ["u1", "u2", "u3", "cx", "id", "unitary"]
+    with pytest.raises(BasicAerError):
+        BasicAer.get_backend("qasm_simulator")
+
+
+def test_show_final_state_flag_and_symbol_like_params():
+    """params may arrive as sympy.Symbol (the reference's assembler): only str() is used."""
+    class Sym:
+        def __init__(self, s):
+            self.s = s
+
+        def __str__(self):
+            return self.s
+
+    c = C.ghz(3)
+    c.barrier()
+    c.instructions.append(C.instr("measure", [0], [Sym("Ensemble"), Sym("X")], memory=[0]))
+    c.barrier()
+    be = emu_backend()
+    be.SHOW_FINAL_STATE = False
+    d = _run(be, c)["results"][0]["data"]
+    assert list(d) == ["ensemble_probability"]
+    assert abs(d["ensemble_probability"]["000"] - 0.25) < 1e-15
+
+
+def test_store_and_compare_round_trip(case_dir):
+    """store_densitymatrix writes stored_coefficients.npy at the ensemble measure; compare reads it
+    back and reports fidelity = dot(a, b) * 2^n = purity for the same state (dm_simulator.py:476-480)."""
+    c = C.ghz(3); c.measure([0, 1, 2], [0, 1, 2], basis="Ensemble", add_param="Z")
+    _run(emu_backend(), c, store_densitymatrix=True)
+    stored = np.load("stored_coefficients.npy")
+    assert stored.shape == (64,) and abs(stored[0] * 8 - 1) < 1e-15
+    d = _run(emu_backend(), c, compare=True)["results"][0]["data"]
+    assert abs(d["fidelity"] - 1.0) < 1e-12
