@@ -32,7 +32,7 @@ import os
 import numpy as np
 
 from . import capi, schedule
-from .engine import PauliEngine, TorchCudaAllocator, cx_coefficients, shared_context
+from .engine import PauliEngine, TorchCudaAllocator, shared_context
 from .exceptions import BasicAerError
 
 

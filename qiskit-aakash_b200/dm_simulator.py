@@ -18,7 +18,6 @@ from __future__ import annotations
 import logging
 import time
 import uuid
-from math import log2
 from types import SimpleNamespace
 
 import numpy as np

@@ -29,8 +29,6 @@ import numpy as np
 from . import capi, schedule
 from .exceptions import BasicAerError
 
-I4 = np.eye(4)
-
 
 # --------------------------------------------------------------------------------------
 # single-qubit maps on (I, X, Y, Z)
@@ -184,7 +182,9 @@ class PauliEngine:
         self.h2d_bytes = 0
         # launch queued two-qubit ops as soon as this many have accumulated, so that the GPU
         # works while the host is still lowering later levels (0 = only at readouts)
-        self.drain_threshold = int(os.environ.get("DMB_DRAIN_THRESHOLD", 256))
+        # (the threshold doubles after every drain: start the GPU early, fuse over long windows later)
+        self.drain_threshold = int(os.environ.get("DMB_DRAIN_THRESHOLD", 64))
+        self.drain_threshold_max = 1024
         # dynamic relabelling of the two low digit positions (schedule.build_passes_relabel)
         self.relabel = bool(int(os.environ.get("DMB_RELABEL", "1"))) if relabel is None else bool(relabel)
         if os.environ.get("DMB_TILE_VARIANT"):
@@ -281,6 +281,7 @@ class PauliEngine:
         passes = self._schedule(final=False)
         self.queue = []
         self.run_passes(passes)
+        self.drain_threshold = min(2 * self.drain_threshold, getattr(self, "drain_threshold_max", 1024))
 
     def apply_diag2(self, qa, qb, weights):
         """v[digit(qa)][digit(qb)] *= weights[i][j] (Bell mask, ``dm_simulator.py:749-756``)."""

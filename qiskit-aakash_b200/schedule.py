@@ -20,8 +20,6 @@ import numpy as np
 
 from . import capi
 
-IDENT = None
-
 
 class DevOp:
     """A two-digit op on physical digit positions ``da`` (matrix ``pa``) and ``db`` (``pb``)."""
