@@ -229,6 +229,11 @@ def run_ours(args):
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": pass_ms, "algorithmic_bytes_per_launch": per_launch_bytes,
                 "fused_ops_per_launch": counters["fused_ops"] / max(1, counters["tile_pass_launches"])}
+    if world == 1:
+        roofline.update(unfused_launch_points(runner.engine, n, peak))
+        roofline["note"] = ("launches that fuse more than ~3 ops are shared-memory-bandwidth bound (one 64 KiB round "
+                            "trip per tile and op), so frac against HBM falls as fusion grows while circuit time "
+                            "improves; see staging_only / one_gate_per_launch for the HBM-bound operating points")
     prof = os.path.join(ROOT, "profiles", "r01_tile_pass_ncu_summary.json")
     if os.path.exists(prof):
         try:
@@ -291,6 +296,36 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def unfused_launch_points(e, n, peak):
+    """The same kernel at its HBM-bound operating points, measured live: a launch that only stages
+    the tiles (0 ops) and a launch that applies ONE gate (TSP CNOT + two single-qubit maps) -- the
+    reference's own granularity of one sweep per gate."""
+    import torch
+    from qiskit_aakash_b200 import capi, engine as eng, schedule
+    rng = np.random.default_rng(0)
+    rot = lambda: eng.gate_matrix("u3", rng.uniform(0, 6, 3), {"rz": [0.999, 0.0], "ry": [0.999, 0.0]})
+    tile = list(range(6))
+    out = {}
+    for name, ops in (("staging_only", []),
+                      ("one_gate_per_launch", [schedule.DevOp(capi.OP_CX_TSP, 2, 3, rot(), rot(),
+                                                              eng.cx_coefficients([0.999, 0.0]))])):
+        passes = schedule.encode_passes([(tile, ops)])
+        for _ in range(3):
+            e.ctx.apply_passes(e.sptr, e.n_bits, passes)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        a.record()
+        for _ in range(reps):
+            e.ctx.apply_passes(e.sptr, e.n_bits, passes)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        ach = 16.0 * 4 ** n / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "achieved": ach, "frac": ach / peak}
+    return out
 
 
 class SingleGpuRunner:
