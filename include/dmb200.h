@@ -135,9 +135,12 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits,
  * with n_ops == 0 is a pure exchange.  All ranks must have finished writing their old buffers
  * (host barrier) before the call, and must not overwrite them until every rank has finished.
  * dmb_ipc_export / dmb_ipc_open turn a device pointer of one process into a mapped pointer of
- * another (cudaIpcGetMemHandle / cudaIpcOpenMemHandle; mappings live until process exit). */
+ * another (cudaIpcGetMemHandle / cudaIpcOpenMemHandle; mappings live until process exit).
+ * push != 0 selects the mirror image: the pass runs in place on `dst_state` (this rank's
+ * current buffer, old layout) and STORES every tile to  (double*)src_tab[idx >> block_shift] + idx,
+ * i.e. into the buffers of the ranks that own the data after the swap (remote stores). */
 int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb_pass* pass,
-                          const uint64_t* src_tab, int tab_bits, int block_shift);
+                          const uint64_t* src_tab, int tab_bits, int block_shift, int push);
 int dmb_ipc_export(dmb_ctx* ctx, const void* dev_ptr, unsigned char* handle64, uint64_t* offset);
 int dmb_ipc_open(dmb_ctx* ctx, const unsigned char* handle64, uint64_t offset, void** out_ptr);
 

@@ -55,7 +55,7 @@ _SIGNATURES = {
     "dmb_set_tile_variant": (_i, [_vp, _i]),
     "dmb_init_product": (_i, [_vp, _vp, _i, _u64, _i, _vp, _vp, _vp, _d]),
     "dmb_apply_passes": (_i, [_vp, _vp, _i, _vp, _sz]),
-    "dmb_apply_pass_remote": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i]),
+    "dmb_apply_pass_remote": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i]),
     "dmb_ipc_export": (_i, [_vp, _vp, _vp, _vp]),
     "dmb_ipc_open": (_i, [_vp, _vp, _u64, _vp]),
     "dmb_marginal": (_i, [_vp, _vp, _i, _u64, _i, _vp, _vp, _vp, _vp]),
@@ -148,14 +148,15 @@ class Context:
         assert passes.dtype == PASS_DTYPE and passes.flags["C_CONTIGUOUS"]
         self._check(self.lib.dmb_apply_passes(self._h, state_ptr, int(n_bits), _ptr(passes), len(passes)))
 
-    def apply_pass_remote(self, dst_ptr, n_bits, one_pass, src_tab, block_shift):
-        """One tile pass whose input is pulled from peer buffers (fused exchange)."""
+    def apply_pass_remote(self, dst_ptr, n_bits, one_pass, src_tab, block_shift, push=False):
+        """One tile pass fused with the exchange: pulls its input from peer buffers, or (push)
+        runs in place and stores its output into peer buffers."""
         assert one_pass.dtype == PASS_DTYPE and len(one_pass) == 1
         tab = np.ascontiguousarray(src_tab, dtype=np.uint64)
         tab_bits = int(len(tab)).bit_length() - 1
         assert (1 << tab_bits) == len(tab)
         self._check(self.lib.dmb_apply_pass_remote(self._h, dst_ptr, int(n_bits), _ptr(one_pass), _ptr(tab),
-                                                   tab_bits, int(block_shift)))
+                                                   tab_bits, int(block_shift), 1 if push else 0))
 
     def ipc_export(self, dev_ptr):
         handle = (ctypes.c_ubyte * 64)()

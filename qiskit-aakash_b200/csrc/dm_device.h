@@ -102,16 +102,23 @@ DMB_HD void dmb_tile_load_thread(int t, const double* __restrict__ state, uint64
   }
 }
 
+// "push" flavour of the fused exchange: the pass BEFORE a slot swap writes every tile straight
+// into the buffer of the rank that owns it in the new layout (same table convention).
+DMB_HD double* dmb_dst_ptr(const dmb_remote_src& D, double* local, uint64_t idx) {
+  if (!D.enabled) return local + idx;
+  return reinterpret_cast<double*>(D.tab[idx >> D.shift]) + idx;
+}
+
 template <int MAXPAIRS>
-DMB_HD void dmb_tile_store_thread(int t, double* __restrict__ gtile, const double* smem,
-                                  const int32_t* td, int K) {
+DMB_HD void dmb_tile_store_thread(int t, double* __restrict__ state, uint64_t tile_base, const double* smem,
+                                  const int32_t* td, int K, const dmb_remote_src& D) {
   const uint32_t npairs = 1u << (2 * K - 1);
 #pragma unroll
   for (int i = 0; i < MAXPAIRS; ++i) {
     const uint32_t p = (uint32_t)t + (uint32_t)i * DMB_TILE_THREADS;
     if (p < npairs) {
       const dmb_d2 w = *reinterpret_cast<const dmb_d2*>(smem + dmb_swz(2u * p));
-      *reinterpret_cast<dmb_d2*>(gtile + dmb_tile_off(2u * p, td, K)) = w;
+      *reinterpret_cast<dmb_d2*>(dmb_dst_ptr(D, state, tile_base + dmb_tile_off(2u * p, td, K))) = w;
     }
   }
 }
@@ -584,13 +591,14 @@ DMB_HD void dmb_lean_load_thread(const dmb_lean_thread& T, const dmb_lean_pass& 
 }
 
 template <class Mem>
-DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass& L, double* gtile,
-                                  const Mem& mem) {
+DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass& L, double* state,
+                                  uint64_t tile_base, const dmb_remote_src& D, const Mem& mem) {
   dmb_d2 w[DMB_LEAN_PAIRS];
 #pragma unroll
   for (int i = 0; i < DMB_LEAN_PAIRS; ++i) w[i] = mem.ld128(T.soff ^ L.pair_soff[i]);
 #pragma unroll
-  for (int i = 0; i < DMB_LEAN_PAIRS; ++i) *reinterpret_cast<dmb_d2*>(gtile + (T.goff | L.pair_goff[i])) = w[i];
+  for (int i = 0; i < DMB_LEAN_PAIRS; ++i)
+    *reinterpret_cast<dmb_d2*>(dmb_dst_ptr(D, state, tile_base + (T.goff | L.pair_goff[i]))) = w[i];
 }
 
 // ---------------------------------------------------------------------------------------

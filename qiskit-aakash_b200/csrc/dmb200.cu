@@ -56,20 +56,19 @@ static const size_t kScratchElems = 1 << 16;
 template <int K>
 __global__ void __launch_bounds__(DMB_TILE_THREADS, (K == 6 ? 3 : 1))
 k_tile_pass(double* __restrict__ state, const __grid_constant__ dmb_pass P, uint64_t n_tiles,
-            const __grid_constant__ dmb_remote_src S) {
+            const __grid_constant__ dmb_remote_src S, const __grid_constant__ dmb_remote_src D) {
   extern __shared__ __align__(16) double smem[];
   constexpr int MAXPAIRS = ((1 << (2 * K - 1)) + DMB_TILE_THREADS - 1) / DMB_TILE_THREADS;
   const int t = threadIdx.x;
   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint64_t tbase = dmb_tile_base(tile, P.tile_digit, K);
-    double* gtile = state + tbase;
     dmb_tile_load_thread<MAXPAIRS>(t, state, tbase, smem, P.tile_digit, K, S);
     __syncthreads();
     for (int i = 0; i < P.n_ops; ++i) {
       dmb_tile_op_thread(t, P.ops[i], smem, K);
       __syncthreads();
     }
-    dmb_tile_store_thread<MAXPAIRS>(t, gtile, smem, P.tile_digit, K);
+    dmb_tile_store_thread<MAXPAIRS>(t, state, tbase, smem, P.tile_digit, K, D);
     __syncthreads();
   }
 }
@@ -90,6 +89,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ const dmb_remote_src g_no_remote_dev = {};   // enabled == 0
 
 // shared-window accessor: 32-bit addresses, one LDS/STS per access
 struct dmb_smem_mem {
@@ -119,7 +120,7 @@ __device__ __forceinline__ void cp_async16s(uint32_t smem_dst, const void* gsrc)
 // STAGES-deep ring of 32 KiB stages per CTA: tiles k+1 .. k+STAGES-1 are in flight while the
 // op run executes on tile k.  (STAGES, CTAs per SM) = (2, 3) or (3, 2) fit the 227 KB of
 // shared memory; chosen at run time (dmb_set_tile_variant / DMB_LEAN_STAGES).
-template <int STAGES, int CTAS, bool REMOTE>
+template <int STAGES, int CTAS, int REMOTE>      // REMOTE: 0 in place, 1 pull (remote loads), 2 push (remote stores)
 __global__ void __launch_bounds__(DMB_TILE_THREADS, CTAS)
 k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L,
              const __grid_constant__ dmb_remote_src S) {
@@ -131,7 +132,7 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
   // buffer that holds those coefficients in the old layout
   auto src_of = [&](uint64_t tb, int i) -> const double* {
     const uint64_t idx = tb + (T.goff | L.pair_goff[i]);
-    if (REMOTE) return reinterpret_cast<const double*>(S.tab[idx >> S.shift]) + idx;
+    if (REMOTE == 1) return reinterpret_cast<const double*>(S.tab[idx >> S.shift]) + idx;
     return state + idx;
   };
   const uint64_t first = blockIdx.x;
@@ -168,7 +169,8 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
       dmb_lean_op_dispatch(T, L.ops[i], mem);
       __syncthreads();
     }
-    dmb_lean_store_thread(T, L, state + dmb_tile_base(tile, L.td, DMB_LEAN_K), mem);
+    if (REMOTE == 2) dmb_lean_store_thread(T, L, state, dmb_tile_base(tile, L.td, DMB_LEAN_K), S, mem);
+    else dmb_lean_store_thread(T, L, state, dmb_tile_base(tile, L.td, DMB_LEAN_K), g_no_remote_dev, mem);
     __syncthreads();
     cur = (cur + 1 == STAGES) ? 0 : cur + 1;
     fill = (fill + 1 == STAGES) ? 0 : fill + 1;
@@ -319,7 +321,7 @@ static dmb_remote_src g_no_remote;      // zero-initialised: enabled == 0
 
 template <int K>
 static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass& P,
-                            const dmb_remote_src& S = g_no_remote) {
+                            const dmb_remote_src& S = g_no_remote, const dmb_remote_src& D = g_no_remote) {
   const uint64_t n_tiles = 1ull << (n_bits - 2 * K);
   const size_t smem = sizeof(double) << (2 * K);
   static bool attr_done = false;
@@ -328,12 +330,12 @@ static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_p
     attr_done = true;
   }
   const uint64_t grid = n_tiles < 0x7fffffffull ? n_tiles : 0x7fffffffull;
-  k_tile_pass<K><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, P, n_tiles, S);
+  k_tile_pass<K><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, P, n_tiles, S, D);
   CU_TRY(cudaGetLastError());
   return 0;
 }
 
-template <int STAGES, int CTAS, bool REMOTE>
+template <int STAGES, int CTAS, int REMOTE>
 static int launch_lean(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, const dmb_remote_src& S = g_no_remote) {
   const size_t smem = (size_t)STAGES * DMB_LEAN_TILE_BYTES;
   static bool attr_done = false;
@@ -375,11 +377,11 @@ static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_
   static dmb_lean_pass L;                 // 6.5 KB: keep it off the stack; single-threaded per ctx
   dmb_make_lean_pass(P, n_bits, L);
   switch (ctx->tile_variant) {
-    case 2: return launch_lean<3, 2, false>(ctx, state, L);
-    case 3: return launch_lean<2, 2, false>(ctx, state, L);
-    case 6: return launch_lean<1, 4, false>(ctx, state, L);
-    case 7: return launch_lean<1, 5, false>(ctx, state, L);
-    default: return launch_lean<2, 3, false>(ctx, state, L);
+    case 2: return launch_lean<3, 2, 0>(ctx, state, L);
+    case 3: return launch_lean<2, 2, 0>(ctx, state, L);
+    case 6: return launch_lean<1, 4, 0>(ctx, state, L);
+    case 7: return launch_lean<1, 5, 0>(ctx, state, L);
+    default: return launch_lean<2, 3, 0>(ctx, state, L);
   }
 }
 
@@ -533,7 +535,7 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
 }
 
 int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb_pass* pass,
-                          const uint64_t* src_tab, int tab_bits, int block_shift) {
+                          const uint64_t* src_tab, int tab_bits, int block_shift, int push) {
   if (!ctx || !dst_state || !pass || !src_tab) return fail("dmb_apply_pass_remote", "null argument");
   if (tab_bits < 0 || (1 << tab_bits) > DMB_REMOTE_MAX) return fail("dmb_apply_pass_remote", "table too large");
   if (block_shift + tab_bits != n_bits) return fail("dmb_apply_pass_remote", "block_shift + tab_bits != n_bits");
@@ -546,15 +548,17 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
   S.shift = block_shift;
   S.enabled = 1;
   int rc = 0;
+  const dmb_remote_src& ld = push ? g_no_remote : S;     // pull: table drives the loads
+  const dmb_remote_src& st = push ? S : g_no_remote;     // push: table drives the stores
   switch (P.n_tile_digits) {
-    case 2: rc = launch_tile_pass<2>(ctx, dst_state, n_bits, P, S); break;
-    case 3: rc = launch_tile_pass<3>(ctx, dst_state, n_bits, P, S); break;
-    case 4: rc = launch_tile_pass<4>(ctx, dst_state, n_bits, P, S); break;
-    case 5: rc = launch_tile_pass<5>(ctx, dst_state, n_bits, P, S); break;
+    case 2: rc = launch_tile_pass<2>(ctx, dst_state, n_bits, P, ld, st); break;
+    case 3: rc = launch_tile_pass<3>(ctx, dst_state, n_bits, P, ld, st); break;
+    case 4: rc = launch_tile_pass<4>(ctx, dst_state, n_bits, P, ld, st); break;
+    case 5: rc = launch_tile_pass<5>(ctx, dst_state, n_bits, P, ld, st); break;
     case 6: {
       static dmb_lean_pass L;
       dmb_make_lean_pass(P, n_bits, L);
-      rc = launch_lean<2, 3, true>(ctx, dst_state, L, S);
+      rc = push ? launch_lean<2, 3, 2>(ctx, dst_state, L, S) : launch_lean<2, 3, 1>(ctx, dst_state, L, S);
       break;
     }
     default: return fail("dmb_apply_pass_remote", "unsupported tile size");

@@ -179,6 +179,9 @@ class ShardedPauliEngine(PauliEngine):
         if bool(int(os.environ.get("DMB_FUSED_EXCHANGE", "1"))) and callable(getattr(comm, "peer_addresses", None)):
             self.peers = comm.peer_addresses(self.ctx, [self.alloc.ptr(self.state), self.alloc.ptr(self.scratch)])
         self._cur = 0                    # which of the two registered buffers is `state`
+        self.exchange_mode = os.environ.get("DMB_EXCHANGE", "pull")      # pull | push | nccl
+        if self.exchange_mode == "nccl":
+            self.peers = None
 
     # -- layout -------------------------------------------------------------------------------
     def is_local(self, q):
@@ -283,43 +286,69 @@ class ShardedPauliEngine(PauliEngine):
         self.pos = pos
         return steps
 
-    def run_steps(self, steps):
-        i = 0
-        while i < len(steps):
-            step = steps[i]
-            if step[0] == "passes":
-                self.run_passes(step[1])
-            elif self.peers is not None and i + 1 < len(steps) and steps[i + 1][0] == "passes":
-                nxt = steps[i + 1][1]
-                self.exchange(first_pass=nxt[:1])
-                self.run_passes(nxt[1:])
+    def run_steps(self, steps, run_passes=None):
+        """Execute compiled steps.  A slot swap is fused into an adjacent tile pass when the peers'
+        buffers are mapped: ``pull`` fuses it into the pass AFTER the swap (remote loads), ``push``
+        into the pass BEFORE it (remote stores).  ``run_passes`` lets a caller time the ordinary
+        in-place passes."""
+        rp = run_passes or self.run_passes
+        mode = self.exchange_mode if self.peers is not None else "nccl"
+        i, n = 0, len(steps)
+        while i < n:
+            st = steps[i]
+            if st[0] == "passes":
+                P = st[1]
+                if mode == "push" and i + 1 < n and steps[i + 1][0] == "exchange" and len(P):
+                    rp(P[:-1])
+                    self.exchange(fused_pass=P[-1:])
+                    i += 2
+                    continue
+                rp(P)
                 i += 1
-            else:
-                self.exchange()
+                continue
+            if mode == "pull" and i + 1 < n and steps[i + 1][0] == "passes" and len(steps[i + 1][1]):
+                nxt = steps[i + 1][1]
+                self.exchange(fused_pass=nxt[:1])
+                rp(nxt[1:])
+                i += 2
+                continue
+            self.exchange()
             i += 1
 
-    def exchange(self, first_pass=None):
+    def exchange(self, fused_pass=None):
         """Swap the m global slots with the m top local slots.  With peer-mapped buffers this is
-        ONE tile-kernel launch that pulls every tile from the rank holding it in the old layout
-        (NVLink loads), applies ``first_pass``'s fused ops and writes the new layout; otherwise
-        an out-of-place NCCL block exchange."""
+        ONE tile-kernel launch: in ``pull`` mode it reads every tile from the rank holding it in
+        the old layout (NVLink loads), applies ``fused_pass``'s ops and writes the new layout
+        locally; in ``push`` mode it runs ``fused_pass`` in place on the old layout and stores
+        every tile into the rank that owns it in the new layout (NVLink stores).  Without mapped
+        peers: an out-of-place NCCL block exchange."""
         px = self.plan_x
-        if self.peers is not None:
-            if first_pass is None or len(first_pass) == 0:
-                first_pass = np.zeros(1, dtype=capi.PASS_DTYPE)
+        mode = self.exchange_mode if self.peers is not None else "nccl"
+        if mode in ("pull", "push"):
+            if fused_pass is None or len(fused_pass) == 0:
+                fused_pass = np.zeros(1, dtype=capi.PASS_DTYPE)
                 K = min(capi.MAX_TILE_DIGITS, self.nd)
-                first_pass[0]["n_tile_digits"] = K
-                first_pass[0]["tile_digit"][:K] = list(range(K))
-            self.ctx.sync()
-            self.comm.barrier()              # every rank's old buffer is final
-            old = self.peers[self._cur]
+                fused_pass[0]["n_tile_digits"] = K
+                fused_pass[0]["tile_digit"][:K] = list(range(K))
+            fused_pass = np.ascontiguousarray(fused_pass)
             tab = np.zeros(1 << px.block_bits, dtype=np.uint64)
-            for d in range(1 << px.block_bits):
-                sr, sb = px.image(self.rank, d)
-                tab[d] = (old[sr] + ((sb - d) << px.B) * 8) % (1 << 64)
             self.ctx.set_stream(self.alloc.stream())
-            self.ctx.apply_pass_remote(self.alloc.ptr(self.scratch), self.n_bits,
-                                       np.ascontiguousarray(first_pass), tab, px.B)
+            if mode == "pull":
+                self.ctx.sync()
+                self.comm.barrier()          # every rank's old buffer is final
+                old = self.peers[self._cur]
+                for d in range(1 << px.block_bits):
+                    sr, sb = px.image(self.rank, d)
+                    tab[d] = (old[sr] + ((sb - d) << px.B) * 8) % (1 << 64)
+                self.ctx.apply_pass_remote(self.alloc.ptr(self.scratch), self.n_bits, fused_pass, tab, px.B)
+            else:
+                new = self.peers[self._cur ^ 1]      # the peers' idle buffers (free since the last barrier)
+                for s_blk in range(1 << px.block_bits):
+                    dr, db = px.image(self.rank, s_blk)
+                    tab[s_blk] = (new[dr] + ((db - s_blk) << px.B) * 8) % (1 << 64)
+                self.ctx.apply_pass_remote(self.sptr, self.n_bits, fused_pass, tab, px.B, push=True)
+                self.ctx.sync()
+                self.comm.barrier()          # all remote stores have landed
             self.passes_run += 1
             self._cur ^= 1
         else:
@@ -476,19 +505,7 @@ class ShardedCircuitRunner:
             else:
                 e.run_passes(passes)
 
-        i = 0
-        while i < len(self.steps):
-            st = self.steps[i]
-            if st[0] == "passes":
-                timed(st[1])
-            elif e.peers is not None and i + 1 < len(self.steps) and self.steps[i + 1][0] == "passes":
-                nxt = self.steps[i + 1][1]
-                e.exchange(first_pass=nxt[:1])        # fused: exchange + first pass in one launch
-                timed(nxt[1:])
-                i += 1
-            else:
-                e.exchange()
-            i += 1
+        e.run_steps(self.steps, run_passes=timed)
         e.pos = list(self.final_pos)
         e.pending = list(self.final_pending)
         self.probs = e.marginal_probabilities("Z", self.err)

@@ -54,23 +54,25 @@ static int validate_pass(const dmb_pass& P, int n_bits) {
 static dmb_remote_src g_no_remote;   // zero-initialised: in place
 
 template <int K>
-static void run_tile_pass(double* state, int n_bits, const dmb_pass& P, const dmb_remote_src& S = g_no_remote) {
+static void run_tile_pass(double* state, int n_bits, const dmb_pass& P, const dmb_remote_src& S = g_no_remote,
+                          const dmb_remote_src& D = g_no_remote) {
   constexpr int MAXPAIRS = ((1 << (2 * K - 1)) + DMB_TILE_THREADS - 1) / DMB_TILE_THREADS;
   const uint64_t n_tiles = 1ull << (n_bits - 2 * K);
   alignas(16) static thread_local double smem[1 << 12];
   for (uint64_t tile = 0; tile < n_tiles; ++tile) {
     const uint64_t tbase = dmb_tile_base(tile, P.tile_digit, K);
-    double* gtile = state + tbase;
     for (int t = 0; t < DMB_TILE_THREADS; ++t)
       dmb_tile_load_thread<MAXPAIRS>(t, state, tbase, smem, P.tile_digit, K, S);
     for (int i = 0; i < P.n_ops; ++i)
       for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_tile_op_thread(t, P.ops[i], smem, K);
-    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_tile_store_thread<MAXPAIRS>(t, gtile, smem, P.tile_digit, K);
+    for (int t = 0; t < DMB_TILE_THREADS; ++t)
+      dmb_tile_store_thread<MAXPAIRS>(t, state, tbase, smem, P.tile_digit, K, D);
   }
 }
 
 // lean K = 6 path: same per-thread bodies as k_tile_pass6, tiles processed one after another
-static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const dmb_remote_src& S = g_no_remote) {
+static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const dmb_remote_src& S = g_no_remote,
+                           const dmb_remote_src& D = g_no_remote) {
   static thread_local dmb_lean_pass L;
   dmb_make_lean_pass(P, n_bits, L);
   alignas(128) static thread_local unsigned char stage[DMB_LEAN_TILE_BYTES];
@@ -80,11 +82,10 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const d
   mem.base = stage;
   for (uint64_t tile = 0; tile < L.n_tiles; ++tile) {
     const uint64_t tbase = dmb_tile_base(tile, L.td, DMB_LEAN_K);
-    double* gtile = state + tbase;
     for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, state, tbase, S, mem);
     for (int i = 0; i < L.n_ops; ++i)
       for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_dispatch(T[t], L.ops[i], mem);
-    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_store_thread(T[t], L, gtile, mem);
+    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_store_thread(T[t], L, state, tbase, D, mem);
   }
 }
 
@@ -180,7 +181,7 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
 }
 
 int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb_pass* pass,
-                          const uint64_t* src_tab, int tab_bits, int block_shift) {
+                          const uint64_t* src_tab, int tab_bits, int block_shift, int push) {
   if ((1 << tab_bits) > DMB_REMOTE_MAX) return fail("dmb_apply_pass_remote", "table too large");
   if (block_shift + tab_bits != n_bits) return fail("dmb_apply_pass_remote", "block_shift + tab_bits != n_bits");
   const dmb_pass& P = *pass;
@@ -190,12 +191,14 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
   for (int i = 0; i < (1 << tab_bits); ++i) S.tab[i] = src_tab[i];
   S.shift = block_shift;
   S.enabled = 1;
+  const dmb_remote_src& ld = push ? g_no_remote : S;
+  const dmb_remote_src& st = push ? S : g_no_remote;
   switch (P.n_tile_digits) {
-    case 2: run_tile_pass<2>(dst_state, n_bits, P, S); break;
-    case 3: run_tile_pass<3>(dst_state, n_bits, P, S); break;
-    case 4: run_tile_pass<4>(dst_state, n_bits, P, S); break;
-    case 5: run_tile_pass<5>(dst_state, n_bits, P, S); break;
-    case 6: run_tile_pass6(dst_state, n_bits, P, S); break;
+    case 2: run_tile_pass<2>(dst_state, n_bits, P, ld, st); break;
+    case 3: run_tile_pass<3>(dst_state, n_bits, P, ld, st); break;
+    case 4: run_tile_pass<4>(dst_state, n_bits, P, ld, st); break;
+    case 5: run_tile_pass<5>(dst_state, n_bits, P, ld, st); break;
+    case 6: run_tile_pass6(dst_state, n_bits, P, ld, st); break;
     default: return fail("dmb_apply_pass_remote", "unsupported tile size");
   }
   ctx->stats.tile_pass_launches++;

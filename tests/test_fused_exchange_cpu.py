@@ -63,7 +63,7 @@ class ThreadComm:
         return [[everyone[r][b] for r in range(self.world)] for b in range(len(ptrs))]
 
 
-def _run_world(world, n, circ, opts, fused):
+def _run_world(world, n, circ, opts, fused, mode="pull"):
     cluster = ThreadCluster(world)
     out, errs = [None] * world, []
 
@@ -74,6 +74,7 @@ def _run_world(world, n, circ, opts, fused):
 
             def factory(nq):
                 e = distributed.ShardedPauliEngine(nq, comm, lib=emu_lib(), allocator=NumpyAllocator(), max_ops_per_pass=4)
+                e.exchange_mode = mode
                 engines.append(e)
                 return e
 
@@ -105,8 +106,8 @@ def test_fused_exchange_matches_oracle(world, n, seed, mode):
     opts = dict(cases.FULL_NOISE, compute_densitymatrix=False)
     ref = dm_oracle.run_oracle(n, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
     p_ref = np.array(list(ref["data"]["ensemble_probability"].values()))
-    for fused in (True, False):
-        outs = _run_world(world, n, circ, opts, fused)
+    for fused, xmode in ((True, "pull"), (True, "push"), (False, "nccl")):
+        outs = _run_world(world, n, circ, opts, fused, xmode)
         for rank, (res, exchanges, has_peers) in enumerate(outs):
             assert has_peers == fused
             assert exchanges >= 1
