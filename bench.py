@@ -246,7 +246,8 @@ def run_ours(args):
     if world == 1:
         backend = BasicAer.get_backend("dm_simulator")
         run_opts = dict(opts, compute_densitymatrix=False)
-        qobj_fn = lambda: assemble(circuits.random_layered(n, depth, seed))
+        qobj = assemble(circuits.random_layered(n, depth, seed))    # the backend never mutates it
+        qobj_fn = lambda: qobj
         for _ in range(2):
             res = backend.run(qobj_fn(), backend_options=copy.deepcopy(run_opts)).result()
             del res
