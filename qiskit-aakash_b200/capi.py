@@ -20,7 +20,7 @@ OP_MATS, OP_CX, OP_CX_TSP, OP_DIAG2, OP_SWAP = 0, 1, 2, 3, 4
 HAS_PA, HAS_PB = 1, 2
 
 OP_DTYPE = np.dtype([("kind", "<i4"), ("flags", "<i4"), ("a", "i1"), ("b", "i1"), ("fd", "i1", (4,)),
-                     ("pad_", "i1", (2,)), ("pa", "<f8", (12,)), ("pb", "<f8", (12,)),
+                     ("post_swap", "i1"), ("post_swap_with", "i1"), ("pa", "<f8", (12,)), ("pb", "<f8", (12,)),
                      ("coef", "<f8", (16,))])
 PASS_DTYPE = np.dtype([("n_tile_digits", "<i4"), ("n_ops", "<i4"), ("tile_digit", "<i4", (MAX_TILE_DIGITS,)),
                        ("ops", OP_DTYPE, (MAX_OPS,))])

@@ -166,7 +166,15 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
     dmb_smem_mem mem;
     mem.base = smem0 + cur * DMB_LEAN_TILE_BYTES;
     for (int i = 0; i < L.n_ops; ++i) {
-      dmb_lean_op_dispatch(T, L.ops[i], mem);
+      const dmb_lean_op& op = L.ops[i];
+      if (op.post_swap == 1 || op.post_swap == 2) {    // fused layout remap: all loads before any store
+        double v[4][4];
+        const uint32_t sb = dmb_lean_op_load_math(T, op, mem, v);
+        __syncthreads();
+        dmb_lean_op_store_swapped(T, op, mem, sb, v);
+      } else {
+        dmb_lean_op_dispatch(T, op, mem);
+      }
       __syncthreads();
     }
     if (REMOTE == 2) dmb_lean_store_thread(T, L, state, dmb_tile_base(tile, L.td, DMB_LEAN_K), S, mem);
@@ -406,6 +414,10 @@ static int validate_pass(const dmb_pass& P, int n_bits) {
         return fail("dmb_apply_passes", "op free-digit list is not a permutation");
       seen |= 1u << op.fd[m];
     }
+    if (op.post_swap < 0 || op.post_swap > 3) return fail("dmb_apply_passes", "post_swap out of range");
+    if ((op.post_swap == 1 || op.post_swap == 2) &&
+        (op.post_swap_with < 0 || op.post_swap_with >= K || op.post_swap_with == op.a || op.post_swap_with == op.b))
+      return fail("dmb_apply_passes", "post_swap_with invalid");
   }
   return 0;
 }
@@ -512,8 +524,20 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
   if (!ctx || !state || (!passes && n_passes)) return fail("dmb_apply_passes", "null argument");
   CU_TRY(cudaSetDevice(ctx->device));
   for (size_t i = 0; i < n_passes; ++i) {
-    const dmb_pass& P = passes[i];
-    if (validate_pass(P, n_bits)) return 1;
+    if (validate_pass(passes[i], n_bits)) return 1;
+    // only the lean K = 6 kernel fuses a layout remap into an op's store; everything else runs
+    // it as explicit swap ops
+    const bool lean = passes[i].n_tile_digits == 6 && ctx->tile_variant != 1 && ctx->tile_variant != 4 &&
+                      ctx->tile_variant != 5;
+    static dmb_pass expanded[2];
+    int n_run = 1;
+    const dmb_pass* run = &passes[i];
+    if (!lean && dmb_pass_has_post_swap(passes[i])) {
+      n_run = dmb_expand_post_swaps(passes[i], expanded);
+      run = expanded;
+    }
+   for (int r = 0; r < n_run; ++r) {
+    const dmb_pass& P = run[r];
     int rc = 0;
     switch (P.n_tile_digits) {
       case 2: rc = launch_tile_pass<2>(ctx, state, n_bits, P); break;
@@ -530,6 +554,7 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
     ctx->stats.tile_pass_launches++;
     ctx->stats.fused_ops += (uint64_t)P.n_ops;
     ctx->stats.state_bytes_moved += 16ull << n_bits;
+   }
   }
   return 0;
 }
@@ -540,8 +565,14 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
   if (tab_bits < 0 || (1 << tab_bits) > DMB_REMOTE_MAX) return fail("dmb_apply_pass_remote", "table too large");
   if (block_shift + tab_bits != n_bits) return fail("dmb_apply_pass_remote", "block_shift + tab_bits != n_bits");
   CU_TRY(cudaSetDevice(ctx->device));
-  const dmb_pass& P = *pass;
-  if (validate_pass(P, n_bits)) return 1;
+  if (validate_pass(*pass, n_bits)) return 1;
+  static dmb_pass expanded_r[2];
+  const dmb_pass* pp = pass;
+  if (pass->n_tile_digits != 6 && dmb_pass_has_post_swap(*pass)) {
+    if (dmb_expand_post_swaps(*pass, expanded_r) != 1) return fail("dmb_apply_pass_remote", "pass too long after expanding remaps");
+    pp = expanded_r;
+  }
+  const dmb_pass& P = *pp;
   dmb_remote_src S;
   memset(&S, 0, sizeof(S));
   for (int i = 0; i < (1 << tab_bits); ++i) S.tab[i] = src_tab[i];

@@ -23,7 +23,7 @@ from . import capi
 
 class DevOp:
     """A two-digit op on physical digit positions ``da`` (matrix ``pa``) and ``db`` (``pb``)."""
-    __slots__ = ("kind", "da", "db", "pa", "pb", "coef")
+    __slots__ = ("kind", "da", "db", "pa", "pb", "coef", "post_swap", "post_swap_with")
 
     def __init__(self, kind, da, db, pa=None, pb=None, coef=None):
         self.kind = kind
@@ -32,6 +32,8 @@ class DevOp:
         self.pa = pa
         self.pb = pb
         self.coef = coef
+        self.post_swap = 0    # 1/2: after the op exchange digit da/db with post_swap_with; 3: da <-> db
+        self.post_swap_with = None
 
     def digits(self):
         return (self.da,) if self.db is None else (self.da, self.db)
@@ -55,6 +57,35 @@ def lane_order(K, a, b):
     return first + [d for d in free if d not in first]
 
 
+def fuse_swaps(devops):
+    """Fold SWAP ops of one pass into the store of the nearest earlier op that touches one of
+    their digits (``dmb_op.post_swap``): the remap then costs an address permutation instead of
+    a shared-memory round trip of the tile.  A swap commutes backwards past ops on other digits,
+    so this is exact; swaps that meet another swap, a lone single-digit op or an op that already
+    carries a remap stay explicit."""
+    out = []
+    for op in devops:
+        fused = False
+        if op.kind == capi.OP_SWAP and op.pa is None and op.pb is None and op.post_swap == 0 and op.db is not None:
+            x, y = op.da, op.db
+            for k in range(len(out) - 1, -1, -1):
+                o = out[k]
+                dg = o.digits()
+                if x in dg or y in dg:
+                    if o.kind != capi.OP_SWAP and o.post_swap == 0 and o.db is not None:
+                        if x in dg and y in dg:
+                            o.post_swap = 3
+                        else:
+                            touched = y if y in dg else x
+                            o.post_swap = 1 if o.da == touched else 2
+                            o.post_swap_with = x if touched == y else y
+                        fused = True
+                    break
+        if not fused:
+            out.append(op)
+    return out
+
+
 def _rows13(m):
     m = np.asarray(m, dtype=np.float64)
     if m.shape != (4, 4):
@@ -65,7 +96,7 @@ def _rows13(m):
 
 
 def build_passes(ops, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_OPS, window=256,
-                 reserve_low=2):
+                 reserve_low=2, fuse=True):
     """ops: list of DevOp in program order -> numpy array of ``capi.PASS_DTYPE``.
 
     ``reserve_low`` digit positions 0..reserve_low-1 are part of every tile, which makes the
@@ -108,7 +139,7 @@ def build_passes(ops, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_
             if d not in tile:
                 tile.add(d)
             d += 1
-        plans.append((sorted(tile), chosen))
+        plans.append((sorted(tile), fuse_swaps(chosen) if fuse else chosen))
         remaining = keep
     return encode_passes(plans)
 
@@ -134,7 +165,8 @@ def _greedy_select(remaining, start_set, cap, max_ops, window, n_qubits):
     return chosen, tile
 
 
-def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_OPS, window=256):
+def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_OPS, window=256,
+                         swap_weight=0.0, fuse=True):
     """Like ``build_passes`` but with dynamic relabelling of the two low digit positions.
 
     ``qops`` are DevOps whose ``da``/``db`` are QUBIT ids; ``pos[q]`` is the digit position of
@@ -187,12 +219,13 @@ def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max
                 active.update(op.digits())
             cands = [q for q in in_tile if q in active]
             best = (len(_greedy_select(remaining, cur, K, real_ops_cap, window, n_qubits)[0]), 0, tuple(cur))
+            score = lambda cnt, swaps: (cnt - swap_weight * swaps, -swaps)
             for i in range(len(cands)):
                 for j in range(i + 1, len(cands)):
                     pair = (cands[i], cands[j])
                     swaps = sum(1 for q in pair if q not in cur)
                     cnt = len(_greedy_select(remaining, pair, K, real_ops_cap, window, n_qubits)[0])
-                    if (cnt, -swaps) > (best[0], -best[1]):
+                    if score(cnt, swaps) > score(best[0], best[1]):
                         best = (cnt, swaps, pair)
             targets = list(best[2])
             keep = [q for q in cur if q in targets]
@@ -209,7 +242,7 @@ def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max
                     pos[other] = src
                 else:
                     owner.pop(src, None)
-        plans.append((sorted(tile_d), devops))
+        plans.append((sorted(tile_d), fuse_swaps(devops) if fuse else devops))
     return encode_passes(plans)
 
 
@@ -240,6 +273,9 @@ def encode_passes(plans):
                 flags |= capi.HAS_PB
             o["flags"] = flags
             o["a"], o["b"] = a, b
+            o["post_swap"] = op.post_swap
+            if op.post_swap in (1, 2):
+                o["post_swap_with"] = local[op.post_swap_with]
             fd = lane_order(K, a, b)
             o["fd"][:len(fd)] = fd
             if op.coef is not None:

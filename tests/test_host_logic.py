@@ -264,6 +264,12 @@ def test_relabel_scheduler_is_a_valid_reordering(n_qubits, max_ops):
                 assert last.get(q, -1) < tag
                 last[q] = tag
             seen.append(tag)
+            if o["post_swap"] == 3:                      # fused layout remaps
+                sim[da], sim[db] = sim.get(db), sim.get(da)
+            elif o["post_swap"] in (1, 2):
+                dx, dt = tile[o["post_swap_with"]], (da if o["post_swap"] == 1 else db)
+                assert dx not in (da, db)
+                sim[dx], sim[dt] = sim.get(dt), sim.get(dx)
     assert sorted(seen) == list(range(len(qops)))
     for q in range(n_qubits):
         assert sim[pos[q]] == q
