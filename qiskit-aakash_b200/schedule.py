@@ -16,6 +16,8 @@ disjoint digits commute, so hoisting past skipped ops is exact).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import capi
@@ -57,6 +59,12 @@ def lane_order(K, a, b):
     return first + [d for d in free if d not in first]
 
 
+#: Folding remap swaps into the preceding op's store is implemented and parity-tested, but on
+#: B200 it measured no faster than explicit swap ops (310.7 vs 305.4 ms for config 3: the fused
+#: store is 64-bit with bank conflicts and runs the unspecialised op body), so it is opt-in.
+FUSE_SWAPS_DEFAULT = bool(int(os.environ.get("DMB_FUSE_SWAPS", "0")))
+
+
 def fuse_swaps(devops):
     """Fold SWAP ops of one pass into the store of the nearest earlier op that touches one of
     their digits (``dmb_op.post_swap``): the remap then costs an address permutation instead of
@@ -96,7 +104,7 @@ def _rows13(m):
 
 
 def build_passes(ops, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_OPS, window=256,
-                 reserve_low=2, fuse=True):
+                 reserve_low=2, fuse=None):
     """ops: list of DevOp in program order -> numpy array of ``capi.PASS_DTYPE``.
 
     ``reserve_low`` digit positions 0..reserve_low-1 are part of every tile, which makes the
@@ -104,6 +112,7 @@ def build_passes(ops, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_
     K = min(max_tile, n_digits)
     if K < 2:
         raise ValueError("state must have at least 2 digit positions")
+    fuse = FUSE_SWAPS_DEFAULT if fuse is None else fuse
     max_ops = min(max_ops, capi.MAX_OPS)
     remaining = list(ops)
     plans = []
@@ -166,7 +175,7 @@ def _greedy_select(remaining, start_set, cap, max_ops, window, n_qubits):
 
 
 def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_OPS, window=256,
-                         swap_weight=0.0, fuse=True):
+                         swap_weight=0.0, fuse=None):
     """Like ``build_passes`` but with dynamic relabelling of the two low digit positions.
 
     ``qops`` are DevOps whose ``da``/``db`` are QUBIT ids; ``pos[q]`` is the digit position of
@@ -182,6 +191,7 @@ def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max
     K = min(max_tile, n_digits)
     if K < 2:
         raise ValueError("state must have at least 2 digit positions")
+    fuse = FUSE_SWAPS_DEFAULT if fuse is None else fuse
     max_ops = min(max_ops, capi.MAX_OPS)
     real_ops_cap = max(1, max_ops - 2) if K >= 4 else max_ops     # leave room for two swaps
     owner = {pos[q]: q for q in range(n_qubits)}                  # digit position -> qubit (phantoms absent)

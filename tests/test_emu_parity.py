@@ -26,3 +26,13 @@ def run_case(name, backend=None):
 @pytest.mark.parametrize("name", list(cases.CASES))
 def test_backend_on_emulated_kernels_matches_golden(name, golden, case_dir):
     check_against_golden(golden, name, run_case(name))
+
+
+@pytest.mark.parametrize("name", ["layered_n8_d6_noisy", "layered_n9_d4_memnoise", "layered_n10_d3_noisy", "rand_n7_fullnoise",
+                                  "qft8_binary", "grover4_noisy"])
+def test_fused_remap_swaps_match_golden(name, golden, case_dir, monkeypatch):
+    """dmb_op.post_swap (remap swap folded into the previous op's store), opt-in via
+    schedule.FUSE_SWAPS_DEFAULT: same numbers as explicit swap ops."""
+    from qiskit_aakash_b200 import schedule
+    monkeypatch.setattr(schedule, "FUSE_SWAPS_DEFAULT", True)
+    check_against_golden(golden, name, run_case(name))

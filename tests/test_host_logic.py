@@ -242,7 +242,7 @@ def test_relabel_scheduler_is_a_valid_reordering(n_qubits, max_ops):
     nd = max(n_qubits, 2)
     pos = [n_qubits - 1 - q for q in range(n_qubits)]
     sim = {p: q for q, p in enumerate(pos)}                  # digit position -> qubit
-    passes = schedule.build_passes_relabel(qops, pos, nd, max_ops=max_ops)
+    passes = schedule.build_passes_relabel(qops, pos, nd, max_ops=max_ops, fuse=(max_ops % 4 != 0))
     last, seen = {}, []
     for p in passes:
         K = int(p["n_tile_digits"])
