@@ -180,6 +180,7 @@ class ShardedPauliEngine(PauliEngine):
             self.peers = comm.peer_addresses(self.ctx, [self.alloc.ptr(self.state), self.alloc.ptr(self.scratch)])
         self._cur = 0                    # which of the two registered buffers is `state`
         self.exchange_mode = os.environ.get("DMB_EXCHANGE", "pull")      # pull | push | nccl
+        self.plain_exchange = bool(int(os.environ.get("DMB_EXCHANGE_PLAIN", "0")))   # op-free pull pass
         if self.exchange_mode == "nccl":
             self.peers = None
 
@@ -306,7 +307,8 @@ class ShardedPauliEngine(PauliEngine):
                 rp(P)
                 i += 1
                 continue
-            if mode == "pull" and i + 1 < n and steps[i + 1][0] == "passes" and len(steps[i + 1][1]):
+            if mode == "pull" and not self.plain_exchange and i + 1 < n and steps[i + 1][0] == "passes" \
+                    and len(steps[i + 1][1]):
                 nxt = steps[i + 1][1]
                 self.exchange(fused_pass=nxt[:1])
                 rp(nxt[1:])
