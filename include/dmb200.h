@@ -63,8 +63,8 @@ typedef struct dmb_op {
   int8_t fd[4];     /* the other tile-local digits, in the order thread-index bit pairs are
                        dealt to them (chosen by the host for conflict-free shared memory)  */
   int8_t post_swap; /* 0 none; after the op exchange tile digit `post_swap_with` with digit a (1)
-                       or digit b (2), or exchange a and b (3) -- a layout remap fused into the
-                       op's store instead of a separate DMB_OP_SWAP round trip               */
+                       or digit b (2), or exchange a and b (3): a layout remap attached to the
+                       op (executed by the library as a DMB_OP_SWAP right after it)          */
   int8_t post_swap_with;
   double pa[12];    /* rows 1..3 of the matrix on digit a, row-major [3][4]                */
   double pb[12];    /* rows 1..3 of the matrix on digit b                                  */

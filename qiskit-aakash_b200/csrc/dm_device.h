@@ -296,10 +296,6 @@ struct alignas(16) dmb_lean_op {
   uint32_t sj[4];      // swizzled BYTE offset of digit-b value j
   uint32_t sh[4];      // left shift (bits) placing thread digit m at its tile digit
   int32_t kind, flags, mode, variant;   // variant: compile-time specialisation id, -1 = generic
-  // fused layout remap (dmb_op.post_swap): sx = swizzled byte offsets of the values of the
-  // partner digit x, ps_m = which of the thread's four index digits is x
-  uint32_t sx[4];
-  int32_t post_swap, ps_m, pad2_[2];
   double pa[12], pb[12], coef[16];
 };
 
@@ -345,14 +341,6 @@ inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L) 
       q.sh[i] = (uint32_t)(2 * o.fd[i]);
     }
     q.kind = o.kind;
-    q.post_swap = o.post_swap;
-    q.ps_m = 0;
-    q.pad2_[0] = q.pad2_[1] = 0;
-    for (int i = 0; i < 4; ++i) q.sx[i] = 0;
-    if (o.post_swap == 1 || o.post_swap == 2) {
-      for (int i = 0; i < 4; ++i) q.sx[i] = dmb_swz((uint32_t)i << (2 * o.post_swap_with)) << 3;
-      for (int m = 0; m < 4; ++m) if (o.fd[m] == o.post_swap_with) q.ps_m = m;
-    }
     q.flags = o.flags & (DMB_HAS_PA | DMB_HAS_PB);
     q.mode = o.a == 0 ? DMB_MODE_PAIR_A : (o.b == 0 ? DMB_MODE_PAIR_B : DMB_MODE_A);
     for (int i = 0; i < 12; ++i) { q.pa[i] = o.pa[i]; q.pb[i] = o.pb[i]; }
@@ -363,7 +351,7 @@ inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L) 
     const int kx = (o.kind == DMB_OP_CX_TSP && (q.flags & DMB_TSP_ZERO_MEAN)) ? DMB_KIND_TSP0 : o.kind;
     const int ma = !(q.flags & DMB_HAS_PA) ? 0 : ((q.flags & DMB_PA_COL0) ? 2 : 1);
     const int mb = !(q.flags & DMB_HAS_PB) ? 0 : ((q.flags & DMB_PB_COL0) ? 2 : 1);
-    q.variant = (dmb_variant_is_specialised(kx, ma, mb) && o.post_swap == 0) ? dmb_variant_id(kx, ma, mb, q.mode) : -1;
+    q.variant = dmb_variant_is_specialised(kx, ma, mb) ? dmb_variant_id(kx, ma, mb, q.mode) : -1;
   }
 }
 
@@ -438,13 +426,12 @@ struct dmb_host_mem {
   void st128(uint32_t off, dmb_d2 v) const { *reinterpret_cast<dmb_d2*>(base + off) = v; }
 };
 
-// generic op body, first half: load the thread's 16-block and apply the arithmetic
 template <class Mem>
-DMB_HD uint32_t dmb_lean_op_load_math(const dmb_lean_thread& T, const dmb_lean_op& op, const Mem& mem,
-                                      double (&v)[4][4]) {
+DMB_HD void dmb_lean_op_thread(const dmb_lean_thread& T, const dmb_lean_op& op, const Mem& mem) {
   const uint32_t bl = (T.tq[0] << op.sh[0]) | (T.tq[1] << op.sh[1]) | (T.tq[2] << op.sh[2]) | (T.tq[3] << op.sh[3]);
   const uint32_t sb = dmb_swz(bl) << 3;
   const int mode = op.mode;
+  double v[4][4];
   if (mode == DMB_MODE_A) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -468,13 +455,6 @@ DMB_HD uint32_t dmb_lean_op_load_math(const dmb_lean_thread& T, const dmb_lean_o
     }
   }
   dmb_lean_math(op, v);
-  return sb;
-}
-
-// generic op body, second half: store the block (same addresses as the load)
-template <class Mem>
-DMB_HD void dmb_lean_op_store(const dmb_lean_op& op, const Mem& mem, uint32_t sb, const double (&v)[4][4]) {
-  const int mode = op.mode;
   if (mode == DMB_MODE_A) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -499,43 +479,6 @@ DMB_HD void dmb_lean_op_store(const dmb_lean_op& op, const Mem& mem, uint32_t sb
       mem.st128(o ^ 16u, p1);
     }
   }
-}
-
-// second half for an op with a fused layout remap (post_swap 1 / 2): element (i, j) of the block
-// of a thread whose partner-digit value is xv goes where digit x = i (resp. j) and the op digit =
-// xv.  Every element is read by one thread and written by one (other) thread, so ALL loads of
-// the op must be complete before the first of these stores: the caller puts a block barrier
-// between dmb_lean_op_load_math and this function.
-template <class Mem>
-DMB_HD void dmb_lean_op_store_swapped(const dmb_lean_thread& T, const dmb_lean_op& op, const Mem& mem,
-                                      uint32_t sb, const double (&v)[4][4]) {
-  const uint32_t xv = T.tq[op.ps_m];
-  if (op.post_swap == 1) {
-    const uint32_t c = sb ^ op.sx[xv] ^ op.sa[xv];       // clear x = xv, set a = xv
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) mem.st64(c ^ op.sx[i] ^ op.sj[j], v[i][j]);
-  } else {
-    const uint32_t c = sb ^ op.sx[xv] ^ op.sj[xv];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) mem.st64(c ^ op.sa[i] ^ op.sx[j], v[i][j]);
-  }
-}
-
-template <class Mem>
-DMB_HD void dmb_lean_op_thread(const dmb_lean_thread& T, const dmb_lean_op& op, const Mem& mem) {
-  double v[4][4];
-  const uint32_t sb = dmb_lean_op_load_math(T, op, mem, v);
-  if (op.post_swap == 3) {                   // exchange a and b: transpose the block in registers
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = i + 1; j < 4; ++j) { const double tmp = v[i][j]; v[i][j] = v[j][i]; v[j][i] = tmp; }
-  }
-  dmb_lean_op_store(op, mem, sb, v);
 }
 
 // Compile-time specialised op body: KINDX in {MATS, CX, CX_TSP, SWAP, DMB_KIND_TSP0},
@@ -648,19 +591,21 @@ DMB_HD void dmb_lean_load_thread(const dmb_lean_thread& T, const dmb_lean_pass& 
               *reinterpret_cast<const dmb_d2*>(dmb_src_ptr(S, state, tile_base + (T.goff | L.pair_goff[i]))));
 }
 
-template <class Mem>
+template <bool PUSH, class Mem>
 DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass& L, double* state,
                                   uint64_t tile_base, const dmb_remote_src& D, const Mem& mem) {
   dmb_d2 w[DMB_LEAN_PAIRS];
 #pragma unroll
   for (int i = 0; i < DMB_LEAN_PAIRS; ++i) w[i] = mem.ld128(T.soff ^ L.pair_soff[i]);
 #pragma unroll
-  for (int i = 0; i < DMB_LEAN_PAIRS; ++i)
-    *reinterpret_cast<dmb_d2*>(dmb_dst_ptr(D, state, tile_base + (T.goff | L.pair_goff[i]))) = w[i];
+  for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
+    const uint64_t idx = tile_base + (T.goff | L.pair_goff[i]);
+    double* dst = PUSH ? reinterpret_cast<double*>(D.tab[idx >> D.shift]) + idx : state + idx;
+    *reinterpret_cast<dmb_d2*>(dst) = w[i];
+  }
 }
 
-// Kernels without the fused store (generic K < 6, A/B variants, R3) run a pass whose ops carry
-// post_swap by materialising the remap as explicit DMB_OP_SWAP ops.  Returns the number of
+// A pass whose ops carry post_swap is run by materialising the remap as explicit DMB_OP_SWAP ops.  Returns the number of
 // passes written to out[0..1] (the expanded op list can exceed DMB_MAX_OPS).
 inline int dmb_expand_post_swaps(const dmb_pass& P, dmb_pass* out) {
   dmb_op list[2 * DMB_MAX_OPS];

@@ -90,8 +90,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ const dmb_remote_src g_no_remote_dev = {};   // enabled == 0
-
 // shared-window accessor: 32-bit addresses, one LDS/STS per access
 struct dmb_smem_mem {
   uint32_t base;
@@ -166,19 +164,10 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
     dmb_smem_mem mem;
     mem.base = smem0 + cur * DMB_LEAN_TILE_BYTES;
     for (int i = 0; i < L.n_ops; ++i) {
-      const dmb_lean_op& op = L.ops[i];
-      if (op.post_swap == 1 || op.post_swap == 2) {    // fused layout remap: all loads before any store
-        double v[4][4];
-        const uint32_t sb = dmb_lean_op_load_math(T, op, mem, v);
-        __syncthreads();
-        dmb_lean_op_store_swapped(T, op, mem, sb, v);
-      } else {
-        dmb_lean_op_dispatch(T, op, mem);
-      }
+      dmb_lean_op_dispatch(T, L.ops[i], mem);
       __syncthreads();
     }
-    if (REMOTE == 2) dmb_lean_store_thread(T, L, state, dmb_tile_base(tile, L.td, DMB_LEAN_K), S, mem);
-    else dmb_lean_store_thread(T, L, state, dmb_tile_base(tile, L.td, DMB_LEAN_K), g_no_remote_dev, mem);
+    dmb_lean_store_thread<REMOTE == 2>(T, L, state, dmb_tile_base(tile, L.td, DMB_LEAN_K), S, mem);
     __syncthreads();
     cur = (cur + 1 == STAGES) ? 0 : cur + 1;
     fill = (fill + 1 == STAGES) ? 0 : fill + 1;
@@ -525,14 +514,13 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
   CU_TRY(cudaSetDevice(ctx->device));
   for (size_t i = 0; i < n_passes; ++i) {
     if (validate_pass(passes[i], n_bits)) return 1;
-    // only the lean K = 6 kernel fuses a layout remap into an op's store; everything else runs
-    // it as explicit swap ops
-    const bool lean = passes[i].n_tile_digits == 6 && ctx->tile_variant != 1 && ctx->tile_variant != 4 &&
-                      ctx->tile_variant != 5;
+    // dmb_op.post_swap (a layout remap attached to an op) is executed as an explicit swap op:
+    // folding it into the op's store was implemented and measured -- no faster, and the extra
+    // registers slowed every other op by 3 % -- so the kernels do not carry that path
     static dmb_pass expanded[2];
     int n_run = 1;
     const dmb_pass* run = &passes[i];
-    if (!lean && dmb_pass_has_post_swap(passes[i])) {
+    if (dmb_pass_has_post_swap(passes[i])) {
       n_run = dmb_expand_post_swaps(passes[i], expanded);
       run = expanded;
     }
@@ -568,7 +556,7 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
   if (validate_pass(*pass, n_bits)) return 1;
   static dmb_pass expanded_r[2];
   const dmb_pass* pp = pass;
-  if (pass->n_tile_digits != 6 && dmb_pass_has_post_swap(*pass)) {
+  if (dmb_pass_has_post_swap(*pass)) {
     if (dmb_expand_post_swaps(*pass, expanded_r) != 1) return fail("dmb_apply_pass_remote", "pass too long after expanding remaps");
     pp = expanded_r;
   }

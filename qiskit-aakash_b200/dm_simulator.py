@@ -406,6 +406,7 @@ class DmSimulatorB200:
         n = self._number_of_qubits = experiment.config.n_qubits
         self._number_of_cmembits = getattr(experiment.config, "memory_slots", 0)
         data = {}
+        self._engine = None          # release the previous run's device buffers before allocating
         engine = self._engine = self._engine_factory(n)
         self._initialize_densitymatrix(engine)
         self._initialize_errors()

@@ -59,9 +59,12 @@ def lane_order(K, a, b):
     return first + [d for d in free if d not in first]
 
 
-#: Folding remap swaps into the preceding op's store is implemented and parity-tested, but on
-#: B200 it measured no faster than explicit swap ops (310.7 vs 305.4 ms for config 3: the fused
-#: store is 64-bit with bank conflicts and runs the unspecialised op body), so it is opt-in.
+#: Attaching remap swaps to the preceding op (``dmb_op.post_swap``) is supported by the ABI and
+#: parity-tested.  Folding such a swap into the op's *store* (an address permutation instead of a
+#: shared-memory round trip) was implemented and measured on B200: no faster than explicit swap
+#: ops (310.7 vs 305.4 ms for config 3 -- the permuted store is 64-bit with bank conflicts and
+#: cost every op 8 more registers), so the kernels run post_swap as an explicit swap and the
+#: scheduler does not emit it by default.
 FUSE_SWAPS_DEFAULT = bool(int(os.environ.get("DMB_FUSE_SWAPS", "0")))
 
 

@@ -87,18 +87,9 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const d
   for (uint64_t tile = 0; tile < L.n_tiles; ++tile) {
     const uint64_t tbase = dmb_tile_base(tile, L.td, DMB_LEAN_K);
     for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, state, tbase, S, mem);
-    for (int i = 0; i < L.n_ops; ++i) {
-      const dmb_lean_op& op = L.ops[i];
-      if (op.post_swap == 1 || op.post_swap == 2) {
-        static thread_local double vbuf[DMB_TILE_THREADS][4][4];
-        static thread_local uint32_t sbuf[DMB_TILE_THREADS];
-        for (int t = 0; t < DMB_TILE_THREADS; ++t) sbuf[t] = dmb_lean_op_load_math(T[t], op, mem, vbuf[t]);
-        for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_store_swapped(T[t], op, mem, sbuf[t], vbuf[t]);
-      } else {
-        for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_dispatch(T[t], op, mem);
-      }
-    }
-    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_store_thread(T[t], L, state, tbase, D, mem);
+    for (int i = 0; i < L.n_ops; ++i)
+      for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_dispatch(T[t], L.ops[i], mem);
+    for (int t = 0; t < DMB_TILE_THREADS; ++t) { if (D.enabled) dmb_lean_store_thread<true>(T[t], L, state, tbase, D, mem); else dmb_lean_store_thread<false>(T[t], L, state, tbase, D, mem); }
   }
 }
 
@@ -173,11 +164,10 @@ int dmb_init_product(dmb_ctx* ctx, double* state, int n_bits, uint64_t rank_bits
 int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* passes, size_t n_passes) {
   for (size_t i = 0; i < n_passes; ++i) {
     if (validate_pass(passes[i], n_bits)) return 1;
-    const bool lean = passes[i].n_tile_digits == 6 && g_variant != 1 && g_variant != 4 && g_variant != 5;
     static thread_local dmb_pass expanded[2];
     int n_run = 1;
     const dmb_pass* run = &passes[i];
-    if (!lean && dmb_pass_has_post_swap(passes[i])) {
+    if (dmb_pass_has_post_swap(passes[i])) {
       n_run = dmb_expand_post_swaps(passes[i], expanded);
       run = expanded;
     }
@@ -210,7 +200,7 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
   if (validate_pass(*pass, n_bits)) return 1;
   static thread_local dmb_pass expanded_r[2];
   const dmb_pass* pp = pass;
-  if (pass->n_tile_digits != 6 && dmb_pass_has_post_swap(*pass)) {
+  if (dmb_pass_has_post_swap(*pass)) {
     if (dmb_expand_post_swaps(*pass, expanded_r) != 1) return fail("dmb_apply_pass_remote", "pass too long");
     pp = expanded_r;
   }
