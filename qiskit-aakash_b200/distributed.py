@@ -540,8 +540,7 @@ class ShardedCircuitRunner:
         import torch
         from .dm_simulator import DmSimulatorB200, assemble
         comm = self.comm
-        self.engine = None                      # free the resident plan's buffers
-        torch.cuda.empty_cache()
+        self.engine = None                      # the resident plan's buffers go back to torch's cache
         be = DmSimulatorB200(_engine_factory=lambda nq: ShardedPauliEngine(nq, comm, device=device))
         be.SHOW_FINAL_STATE = False
         run_opts = dict(opts, compute_densitymatrix=False)
