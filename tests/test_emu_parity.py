@@ -36,3 +36,29 @@ def test_fused_remap_swaps_match_golden(name, golden, case_dir, monkeypatch):
     from qiskit_aakash_b200 import schedule
     monkeypatch.setattr(schedule, "FUSE_SWAPS_DEFAULT", True)
     check_against_golden(golden, name, run_case(name))
+
+
+def test_mid_circuit_readouts_vs_oracle_on_emulated_kernels():
+    """Same scenario as the GPU test of that name, n = 7, against the oracle."""
+    import copy
+    from oracle import dm_oracle
+    n = 7
+    circ = cases._rand_circuit(n, 40, 8011)
+    circ.measure(2, 2, basis="X")
+    circ.u3(0.3, 0.2, 0.1, 2); circ.cx(2, n - 1)
+    circ.measure([0, 3, n - 2], [0, 3, n - 2], basis="Z")
+    circ.reset(1); circ.u3(1.0, 0.5, 0.25, 1); circ.cx(1, n - 3)
+    circ.measure(0, 0, basis="Bell", add_param="0%d" % (n - 1))
+    circ.cx(n - 1, 0); circ.u3(0.7, 0.1, 0.9, n - 1)
+    circ.measure(0, 0, basis="Expect", add_param=("ZXIY" * n)[:n])
+    circ.cx(0, 1)
+    circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="Y")
+    opts = dict(cases.FULL_NOISE)
+    got = emu_backend().run(assemble(circ), backend_options=copy.deepcopy(opts)).result()["results"][0]
+    ref = dm_oracle.run_oracle(n, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
+    assert got["number_of_clock_cycles"] == ref["number_of_clock_cycles"] and set(got["data"]) == set(ref["data"])
+    for k, v in ref["data"].items():
+        a = np.array(list(v.values())) if isinstance(v, dict) else np.asarray(v)
+        w = got["data"][k]
+        b = np.array(list(w.values())) if isinstance(w, dict) else np.asarray(w)
+        assert np.max(np.abs(a - b)) <= 1e-10, k

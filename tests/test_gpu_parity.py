@@ -76,6 +76,24 @@ def test_random_circuits_vs_oracle(backend, n, seed):
     _compare_with_oracle(backend, n, circ.instructions, opts)
 
 
+@pytest.mark.parametrize("n,seed", [(8, 11), (9, 12), (10, 13)])
+def test_mid_circuit_measure_reset_bell_expect_vs_oracle(backend, n, seed):
+    """Every state-changing readout in the middle of a noisy circuit, then more gates (the lazy
+    queue is flushed by each readout; layouts are relabelled in between)."""
+    circ = cases._rand_circuit(n, 40, 8000 + seed)
+    circ.measure(2, 2, basis="X")                       # single projective measurement
+    circ.u3(0.3, 0.2, 0.1, 2); circ.cx(2, n - 1)
+    circ.measure([0, 3, n - 2], [0, 3, n - 2], basis="Z")    # partial measurement of three qubits
+    circ.reset(1); circ.u3(1.0, 0.5, 0.25, 1); circ.cx(1, n - 3)
+    circ.measure(0, 0, basis="Bell", add_param="0%d" % (n - 1))
+    circ.cx(n - 1, 0); circ.u3(0.7, 0.1, 0.9, n - 1)
+    circ.measure(0, 0, basis="Expect", add_param=("ZXIY" * n)[:n])
+    circ.cx(0, 1)
+    circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="Y")
+    opts = dict(cases.FULL_NOISE, compute_densitymatrix=(n <= 8))
+    _compare_with_oracle(backend, n, circ.instructions, opts)
+
+
 def test_baseline_configs_at_oracle_sizes(backend):
     from qiskit_aakash_b200 import circuits as C
     _compare_with_oracle(backend, 10, C.qft(10).instructions, {"compute_densitymatrix": False})
