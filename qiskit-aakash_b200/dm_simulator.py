@@ -418,8 +418,10 @@ class DmSimulatorB200:
         data = {}
         self._engine = None          # release the previous run's device buffers before allocating
         engine = self._engine = self._engine_factory(n)
+        t_pre1 = time.time()
         self._initialize_densitymatrix(engine)
         self._initialize_errors()
+        t_pre2 = time.time()
         ops = hostpass.merge_single_qubit_gates(experiment.instructions, n, self.MERGE)
         levels, n_levels = hostpass.partition_levels(ops, n)
         if self.SHOW_PARTITION:
@@ -454,6 +456,8 @@ class DmSimulatorB200:
         engine.sync()
         self.last_engine_stats = dict(engine.stats(), passes=engine.passes_run, h2d_bytes=engine.h2d_bytes,
                                       t_host_pre=end_processing - start_processing,
+                                      t_pre_engine=t_pre1 - start_processing, t_pre_init=t_pre2 - t_pre1,
+                                      t_pre_lower=end_processing - t_pre2,
                                       t_levels=t_levels - start_runtime, t_final_compute=t_dl0 - t_levels,
                                       t_download=t_dl1 - t_dl0)
         end_runtime = time.time()
