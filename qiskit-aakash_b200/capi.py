@@ -71,9 +71,15 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 
+_LIBRARIES = {}
+
+
 def load_library(path=None):
-    """dlopen the CUDA library and type its entry points.  Raises if it is missing."""
-    path = path or DEFAULT_LIB
+    """dlopen the CUDA library and type its entry points (once per path: engines share the
+    handle, and with it the per-device ``dmb_ctx``).  Raises if it is missing."""
+    path = os.path.abspath(path or DEFAULT_LIB)
+    if path in _LIBRARIES:
+        return _LIBRARIES[path]
     if not os.path.exists(path):
         raise DmbError("CUDA library %s not found -- build it with `python -c 'import __graft_entry__ as g; "
                        "g.build()'` (nvcc, sm_100a); this package has no CPU fallback" % path)
@@ -86,6 +92,7 @@ def load_library(path=None):
         raise DmbError("ABI version mismatch")
     if lib.dmb_sizeof_op() != OP_DTYPE.itemsize or lib.dmb_sizeof_pass() != PASS_DTYPE.itemsize:
         raise DmbError("struct layout mismatch between capi.py and libdmb200.so")
+    _LIBRARIES[path] = lib
     return lib
 
 

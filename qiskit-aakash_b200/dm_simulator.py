@@ -15,6 +15,7 @@ The qobj is read duck-typed exactly like the reference does: ``qobj.config.n_qub
 """
 from __future__ import annotations
 
+import functools
 import gc
 import logging
 import time
@@ -74,6 +75,12 @@ class DmJob:
 
     def backend(self):
         return self._backend
+
+
+@functools.lru_cache(maxsize=8)
+def _bit_strings(nbits):
+    """Outcome labels '00..0' .. '11..1' (cached: 2^n string formats per readout add up)."""
+    return tuple(format(i, "0%db" % nbits) for i in range(2 ** nbits)) if nbits else ("",)
 
 
 class DmSimulatorB200:
@@ -291,7 +298,7 @@ class DmSimulatorB200:
         return n
 
     def _keys(self, nbits):
-        return [format(i, "0%db" % nbits) for i in range(2 ** nbits)] if nbits else [""]
+        return _bit_strings(nbits)
 
     def _add_ensemble_measure(self, engine, basis, add_param, err_param):
         """``_add_ensemble_measure`` (``:427-481``): state is not modified."""

@@ -185,6 +185,11 @@ class PauliEngine:
         # (the threshold doubles after every drain: start the GPU early, fuse over long windows later)
         self.drain_threshold = int(os.environ.get("DMB_DRAIN_THRESHOLD", 64))
         self.drain_threshold_max = 1024
+        # streaming drain (relabel scheduler): every `drain_chunk` new ops, launch all passes but
+        # keep the newest `drain_tail` ops queued as look-ahead
+        self.drain_tail = int(os.environ.get("DMB_DRAIN_TAIL", max(64, 6 * self.n)))
+        self.drain_chunk = int(os.environ.get("DMB_DRAIN_CHUNK", 64))
+        self._chunk_now = min(16, self.drain_chunk)      # small first chunks: the GPU starts early
         # dynamic relabelling of the two low digit positions (schedule.build_passes_relabel)
         self.relabel = bool(int(os.environ.get("DMB_RELABEL", "1"))) if relabel is None else bool(relabel)
         if os.environ.get("DMB_TILE_VARIANT"):
@@ -252,8 +257,13 @@ class PauliEngine:
         else:
             kind, coef = capi.OP_CX_TSP, cx_coefficients(tsp)
         self.queue.append(("2q", kind, ctrl, tgt, self._take(ctrl), self._take(tgt), coef))
-        if self.drain_threshold and len(self.queue) >= self.drain_threshold:
-            self.drain()
+        if self.drain_threshold:
+            if getattr(self, "relabel", False) and getattr(self, "drain_tail", 0) > 0:
+                if len(self.queue) >= self.drain_tail + getattr(self, "_chunk_now", self.drain_chunk):
+                    self.drain()
+                    self._chunk_now = min(2 * getattr(self, "_chunk_now", self.drain_chunk), self.drain_chunk)
+            elif len(self.queue) >= self.drain_threshold:
+                self.drain()
 
     def _schedule(self, final):
         """Outstanding work -> PASS array.  With relabelling the ops are scheduled on qubit ids
@@ -277,7 +287,20 @@ class PauliEngine:
         return schedule.build_passes(ops, self.nd, max_ops=self.max_ops_per_pass, reserve_low=self.reserve_low)
 
     def drain(self):
-        """Schedule and launch the queued two-qubit ops now (pending matrices stay pending)."""
+        """Schedule and launch queued two-qubit ops now (pending matrices stay pending).  With
+        relabelling the last ``drain_tail`` ops stay queued: the scheduler's look-ahead then sees
+        the same ops it would see in a one-shot schedule, so streaming costs no extra passes."""
+        tail = getattr(self, "drain_tail", 0)
+        if getattr(self, "relabel", False) and tail > 0:
+            if len(self.queue) <= tail:
+                return
+            qops = [schedule.DevOp(kind, qa, qb, pa, pb, coef) for (_, kind, qa, qb, pa, pb, coef) in self.queue]
+            item_of = {id(op): item for op, item in zip(qops, self.queue)}
+            passes, left = schedule.build_passes_relabel(qops, self.pos, self.nd, max_ops=self.max_ops_per_pass,
+                                                         min_tail=tail)
+            self.queue = [item_of[id(op)] for op in left]
+            self.run_passes(passes)
+            return
         passes = self._schedule(final=False)
         self.queue = []
         self.run_passes(passes)

@@ -178,8 +178,12 @@ def _greedy_select(remaining, start_set, cap, max_ops, window, n_qubits):
 
 
 def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_OPS, window=256,
-                         swap_weight=0.0, fuse=None):
+                         swap_weight=0.0, fuse=None, min_tail=0):
     """Like ``build_passes`` but with dynamic relabelling of the two low digit positions.
+
+    With ``min_tail`` > 0 scheduling stops as soon as no more than ``min_tail`` ops are left and
+    ``(passes, leftover ops)`` is returned: a caller that is still producing ops keeps the tail
+    queued, so that pass boundaries do not depend on where the stream was cut.
 
     ``qops`` are DevOps whose ``da``/``db`` are QUBIT ids; ``pos[q]`` is the digit position of
     qubit q (mutated to the layout after the last pass).  Digit positions 0 and 1 are part of
@@ -204,7 +208,7 @@ def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max
     def lows():
         return [owner[d] for d in (0, 1) if d in owner and d < n_digits]
 
-    while remaining:
+    while len(remaining) > min_tail:
         chosen, tile_q = _greedy_select(remaining, lows(), K, real_ops_cap, window, n_qubits)
         if not chosen:
             raise RuntimeError("scheduler made no progress")
@@ -256,6 +260,8 @@ def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max
                 else:
                     owner.pop(src, None)
         plans.append((sorted(tile_d), fuse_swaps(devops) if fuse else devops))
+    if min_tail > 0:
+        return encode_passes(plans), remaining
     return encode_passes(plans)
 
 

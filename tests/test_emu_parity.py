@@ -62,3 +62,25 @@ def test_mid_circuit_readouts_vs_oracle_on_emulated_kernels():
         w = got["data"][k]
         b = np.array(list(w.values())) if isinstance(w, dict) else np.asarray(w)
         assert np.max(np.abs(a - b)) <= 1e-10, k
+
+
+@pytest.mark.parametrize("tail,chunk", [(3, 2), (8, 4)])
+@pytest.mark.parametrize("name", ["layered_n8_d6_noisy", "layered_n10_d3_noisy", "rand_n7_fullnoise", "qft8_binary"])
+def test_streaming_drain_matches_golden(name, tail, chunk, golden, case_dir, monkeypatch):
+    """The engine launches passes while later levels are still being lowered, keeping the newest
+    ``drain_tail`` ops queued as look-ahead (engine.PauliEngine.drain).  Forced here with tiny
+    tails so that small circuits drain many times."""
+    monkeypatch.setenv("DMB_DRAIN_TAIL", str(tail))
+    monkeypatch.setenv("DMB_DRAIN_CHUNK", str(chunk))
+    engines = []
+    from emu_backend import emu_engine
+    from qiskit_aakash_b200.dm_simulator import DmSimulatorB200
+
+    def factory(n):
+        e = emu_engine(n)
+        engines.append(e)
+        return e
+
+    check_against_golden(golden, name, run_case(name, DmSimulatorB200(_engine_factory=factory)))
+    assert engines[0].drain_tail == tail
+    assert engines[0].passes_run >= 2

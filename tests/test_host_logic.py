@@ -309,3 +309,30 @@ def test_gate_matrix_matches_sequential_rotations():
         w[k0], w[k1] = c * w[k0] - s * w[k1], c * w[k1] + s * w[k0]
     assert np.allclose(m @ v, w, atol=1e-15)
     assert np.array_equal(m[0], [1, 0, 0, 0])
+
+
+def test_streaming_schedule_equals_one_shot_schedule():
+    """build_passes_relabel(min_tail=...) called repeatedly on a growing op stream produces the
+    same passes as one call on the whole stream once the tail covers the look-ahead."""
+    from qiskit_aakash_b200 import schedule
+    rng = np.random.default_rng(3)
+    n = 10
+    qops = []
+    for layer in range(40):
+        for q in range(layer % 2, n - 1, 2):
+            a, b = (q, q + 1) if rng.integers(2) else (q + 1, q)
+            qops.append(schedule.DevOp(capi.OP_CX, a, b, None, None, None))
+    pos0 = [n - 1 - q for q in range(n)]
+    pos_a = list(pos0)
+    whole = schedule.build_passes_relabel(list(qops), pos_a, n, max_ops=10)
+    pos_b = list(pos0)
+    queue, parts = [], []
+    for i, op in enumerate(qops):
+        queue.append(op)
+        if len(queue) >= 64 + 16:
+            p, queue = schedule.build_passes_relabel(queue, pos_b, n, max_ops=10, min_tail=64)
+            parts.append(p)
+    parts.append(schedule.build_passes_relabel(queue, pos_b, n, max_ops=10))
+    streamed = np.concatenate(parts)
+    assert len(parts) > 3 and pos_a == pos_b
+    assert streamed.tobytes() == whole.tobytes()
