@@ -586,13 +586,31 @@ class DmSimulatorB200:
 # provider shim + execute()   (qiskit/providers/basicaer/basicaerprovider.py:34-67, execute.py)
 # ----------------------------------------------------------------------------------------------
 
+class _OutOfScopeBackend:
+    """Placeholder for the reference's other BasicAer simulators (``basicaerprovider.py:34-39``),
+    so that scripts which fetch several backends up front still reach their dm_simulator part;
+    running a circuit on it raises."""
+
+    def __init__(self, name):
+        self._name = name
+
+    def name(self):
+        return self._name
+
+    def run(self, qobj, backend_options=None):
+        raise BasicAerError('The "%s" backend is not provided by this package (only dm_simulator is)' % self._name)
+
+
 class _Provider:
     _ALIASES = {"dm_simulator": "dm_simulator", "dm_simulator_py": "dm_simulator"}
+    _OTHERS = ("qasm_simulator", "statevector_simulator", "unitary_simulator")
 
     def __init__(self):
         self._backends = {}
 
     def get_backend(self, name="dm_simulator", **kwargs):
+        if name in self._OTHERS:
+            return _OutOfScopeBackend(name)
         if name not in self._ALIASES:
             raise BasicAerError('The "%s" backend is not provided by this package' % name)
         key = self._ALIASES[name]
@@ -608,17 +626,23 @@ BasicAer = _Provider()
 
 
 def assemble(circuits, qobj_id=None):
-    """Minimal ``assemble``: our ``circuits.Circuit`` objects -> a qobj-shaped namespace."""
+    """Minimal ``assemble`` (``assembler/assemble_circuits.py``): ``frontend.QuantumCircuit`` objects
+    (lowered like the reference's transpile + assemble) or ``circuits.Circuit`` gate lists
+    (taken as they are) -> a qobj-shaped namespace."""
     if not isinstance(circuits, (list, tuple)):
         circuits = [circuits]
     exps = []
     for c in circuits:
+        if hasattr(c, "to_experiment"):
+            exps.append(c.to_experiment())
+            continue
         exps.append(SimpleNamespace(
             config=SimpleNamespace(n_qubits=c.n_qubits, memory_slots=c.n_qubits),
             header=SimpleNamespace(name=c.name, as_dict=(lambda nm=c.name: {"name": nm})),
             instructions=list(c.instructions)))
     return SimpleNamespace(qobj_id=qobj_id or str(uuid.uuid4()),
-                           config=SimpleNamespace(n_qubits=max(c.n_qubits for c in circuits)),
+                           config=SimpleNamespace(n_qubits=max(e.config.n_qubits for e in exps),
+                                                  memory_slots=max(e.config.memory_slots for e in exps)),
                            header=SimpleNamespace(as_dict=lambda: {}),
                            experiments=exps)
 

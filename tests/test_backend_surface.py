@@ -106,7 +106,11 @@ def test_job_object_and_provider():
     assert BasicAer.get_backend("dm_simulator").name() == "dm_simulator"
     assert BasicAer.get_backend().configuration().basis_gates == ["u1", "u2", "u3", "cx", "id", "unitary"]
     with pytest.raises(BasicAerError):
-        BasicAer.get_backend("qasm_simulator")
+        BasicAer.get_backend("ibmq_qasm_simulator")
+    other = BasicAer.get_backend("qasm_simulator")        # out of scope: placeholder that refuses to run
+    assert other.name() == "qasm_simulator"
+    with pytest.raises(BasicAerError):
+        other.run(assemble(C.ghz(2)))
 
 
 def test_show_final_state_flag_and_symbol_like_params():

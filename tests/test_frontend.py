@@ -1,0 +1,164 @@
+"""qiskit_aakash_b200.frontend against the unmodified reference front-end.
+
+tests/golden/frontend_golden.json holds, for every builder in tests/frontend_cases.py, the
+instruction list that the reference's own QuantumCircuit -> Unroller -> RemoveResetInZeroState ->
+dag_to_circuit -> Instruction.assemble chain produces (tests/golden/make_frontend_golden.py).
+The facade must reproduce it exactly: names, order, qubit / clbit indices, parameter bits."""
+import copy
+import json
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+import frontend_cases
+from qiskit_aakash_b200 import frontend
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "frontend_golden.json")))
+API = SimpleNamespace(QuantumCircuit=frontend.QuantumCircuit, QuantumRegister=frontend.QuantumRegister,
+                      ClassicalRegister=frontend.ClassicalRegister, pi=frontend.pi)
+
+
+def plain(p):
+    if isinstance(p, np.ndarray):
+        return {"array": [float(x).hex() for x in p.reshape(-1)]}
+    if isinstance(p, str):
+        return {"symbol": p}
+    return {"float": float(p).hex()}
+
+
+def as_records(instrs):
+    out = []
+    for ins in instrs:
+        rec = {"name": ins.name}
+        if hasattr(ins, "qubits"):
+            rec["qubits"] = list(ins.qubits)
+        if hasattr(ins, "memory"):
+            rec["memory"] = list(ins.memory)
+        if hasattr(ins, "params"):
+            rec["params"] = [plain(p) for p in ins.params]
+        out.append(rec)
+    return out
+
+
+@pytest.mark.parametrize("name", list(frontend_cases.CASES))
+def test_lowered_instruction_list_equals_reference_front_end(name):
+    qc = frontend_cases.CASES[name](API)
+    n_q, n_c, instrs = qc.lowered()
+    gold = GOLDEN[name]
+    assert (n_q, n_c) == (gold["n_qubits"], gold["memory_slots"])
+    got = as_records(instrs)
+    assert len(got) == len(gold["instructions"])
+    for k, (a, b) in enumerate(zip(got, gold["instructions"])):
+        assert a == b, "instruction %d: %r != %r" % (k, a, b)
+
+
+def test_golden_covers_every_case():
+    assert set(GOLDEN) == set(frontend_cases.CASES)
+
+
+@pytest.mark.parametrize("name", ["readme_example", "measurement_modes", "mid_circuit_measures", "every_gate",
+                                  "two_registers", "resets", "random_mixed"])
+def test_execute_through_facade_matches_oracle_on_reference_instruction_list(name):
+    """End to end: facade circuit -> execute() on the emulated kernels == oracle run on the
+    instruction list the REFERENCE front-end produced for the same source."""
+    from emu_backend import emu_backend
+    from oracle import dm_oracle
+    from qiskit_aakash_b200 import execute
+    opts = {"decoherence_factor": 0.97, "decay_factor": 0.98, "thermal_factor": 0.4, "depolarization_factor": 0.99,
+            "rotation_error": {"rx": [0.999, 0.01], "ry": [0.998, 0.02], "rz": [0.997, 0.0]},
+            "tsp_model_error": [0.996, 0.01]}
+    qc = frontend_cases.CASES[name](API)
+    got = execute(qc, emu_backend(), **copy.deepcopy(opts)).result()["results"][0]
+    gold = GOLDEN[name]
+    instrs = []
+    for rec in gold["instructions"]:
+        ns = SimpleNamespace(name=rec["name"], qubits=list(rec.get("qubits", [])))
+        if "memory" in rec:
+            ns.memory = list(rec["memory"])
+        if "params" in rec:
+            ns.params = [np.array([float.fromhex(x) for x in p["array"]]) if "array" in p else
+                         p["symbol"] if "symbol" in p else float.fromhex(p["float"]) for p in rec["params"]]
+        instrs.append(ns)
+    ref = dm_oracle.run_oracle(gold["n_qubits"], instrs, copy.deepcopy(opts))
+    assert got["number_of_clock_cycles"] == ref["number_of_clock_cycles"]
+    assert set(got["data"]) == set(ref["data"])
+    for k, v in ref["data"].items():
+        a = np.array(list(v.values())) if isinstance(v, dict) else np.asarray(v)
+        w = got["data"][k]
+        b = np.array(list(w.values())) if isinstance(w, dict) else np.asarray(w)
+        assert a.shape == b.shape and np.max(np.abs(a - b)) <= 1e-10, k
+
+
+def test_readme_example_density_matrix():
+    """README.md:44-62 of the reference, verbatim apart from the import line."""
+    from emu_backend import emu_backend
+    from qiskit_aakash_b200 import QuantumCircuit, execute
+    qc = QuantumCircuit(2)
+    qc.x(1)
+    qc.cx(0, 1)
+    result = execute(qc, emu_backend()).result()
+    rho = result["results"][0]["data"]["densitymatrix"]
+    expect = np.zeros((4, 4))
+    expect[1, 1] = 1.0
+    assert np.max(np.abs(rho - expect)) <= 1e-12
+
+
+def test_registers_bits_and_errors():
+    q = frontend.QuantumRegister(3, "q")
+    assert repr(q) == "QuantumRegister(3, 'q')" and repr(q[1]) == "Qubit(QuantumRegister(3, 'q'), 1)"
+    assert q[-1] == q[2] and q[0:2] == [q[0], q[1]] and (q, 1) == q[1]
+    auto = frontend.QuantumRegister(2)
+    assert auto.name.startswith("q") and auto.name[1:].isdigit()
+    qc = frontend.QuantumCircuit(q, frontend.ClassicalRegister(3, "c"))
+    with pytest.raises(frontend.QiskitError):
+        qc.cx(q[0], q[0])                               # duplicate qubit arguments
+    with pytest.raises(frontend.QiskitError):
+        qc.h(5)                                         # index out of range
+    with pytest.raises(frontend.QiskitError):
+        qc.measure(q[0], 0, basis="N")                  # direction required
+    with pytest.raises(frontend.QiskitError):
+        qc.measure(q[0], 0, basis="X", add_param="Z")
+    with pytest.raises(frontend.QiskitError):
+        frontend.QuantumCircuit(q, frontend.QuantumRegister(1, "q"))
+    with pytest.raises(frontend.QiskitError):
+        frontend.QuantumRegister(2, "Q")                # invalid OPENQASM name
+    qc.u_base(0.1, 0.2, 0.3, q[0])
+    with pytest.raises(frontend.QiskitError):
+        qc.lowered()                                    # 'U' cannot be unrolled to the basis
+    with pytest.raises(frontend.QiskitError):
+        frontend.QuantumCircuit(1).x(0).c_if(None, 1)
+
+
+def test_install_as_qiskit_runs_reference_style_script(tmp_path):
+    """A script written for the reference runs unchanged once the facade is installed."""
+    import subprocess
+    script = tmp_path / "user_script.py"
+    script.write_text(
+        "import sys\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import qiskit_aakash_b200, emu_backend\n"
+        "qiskit_aakash_b200.install_as_qiskit()\n"
+        "import qiskit_aakash_b200.dm_simulator as d\n"
+        "d.BasicAer._backends = {}\n"
+        "d.BasicAer.get_backend = staticmethod(lambda name: emu_backend.emu_backend())\n"
+        "# ---- reference-style user code below ----\n"
+        "import numpy as np\n"
+        "from qiskit import QuantumCircuit, QuantumRegister, ClassicalRegister\n"
+        "from qiskit import BasicAer, execute\n"
+        "from qiskit.qasm import pi\n"
+        "backend = BasicAer.get_backend('dm_simulator')\n"
+        "q = QuantumRegister(3, 'q'); c = ClassicalRegister(3, 'c')\n"
+        "circ = QuantumCircuit(q, c)\n"
+        "circ.h(q[0]); circ.cx(q[0], q[1]); circ.cx(q[1], q[2]); circ.u1(pi / 2, q[2])\n"
+        "circ.measure(q, c, basis='Ensemble', add_param='X')\n"
+        "result = execute([circ], backend, decoherence_factor=0.99).result()\n"
+        "p = result['results'][0]['data']['ensemble_probability']\n"
+        "assert abs(sum(p.values()) - 1) < 1e-12 and len(p) == 8\n"
+        "print('OK', result['results'][0]['number_of_clock_cycles'])\n"
+        % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().startswith("OK")
