@@ -187,9 +187,54 @@ def _cases():
         dict(C.noisy_options(), compute_densitymatrix=False, **C.grover_options()))
     add("layered_n10_d3_noisy", C.random_layered(10, 3, 1000),
         dict(C.noisy_options(), compute_densitymatrix=False))
+    # circuits lowered by the reference's REAL front-end (tests/golden/frontend_golden.json, written by
+    # tests/golden/make_frontend_golden.py): golden results for these pin the whole reference stack,
+    # QuantumCircuit -> transpile -> assemble -> DmSimulatorPy
+    for name, opts in FRONTEND_CASES.items():
+        n, instrs = frontend_instructions(name)
+        circ = C.Circuit(n, "fe_" + name)
+        circ.instructions = instrs
+        add("fe_" + name, circ, opts)
     return cs
 
 
+FRONTEND_CASES = {
+    "readme_example": {},
+    "teleport_style": FULL_NOISE,
+    "phase_estimation_style": {"decoherence_factor": 0.95, "decay_factor": 0.97, "thermal_factor": 0.3},
+    "qft_register": dict(FULL_NOISE, compute_densitymatrix=False),
+    "every_gate": FULL_NOISE,
+    "two_registers": {"rotation_error": {"rx": [1.0, 0.0], "ry": [0.99, 0.02], "rz": [0.98, -0.01]}},
+    "broadcast_and_barriers": {"tsp_model_error": [0.97, 0.05]},
+    "resets": FULL_NOISE,
+    "measurement_modes": FULL_NOISE,
+    "mid_circuit_measures": FULL_NOISE,
+    "symbolic_parameters": {},
+    "random_mixed": dict(FULL_NOISE, compute_densitymatrix=False),
+}
+
+
+def frontend_instructions(name):
+    """(n_qubits, instruction namespaces) recorded from the reference front-end for a builder of
+    tests/frontend_cases.py."""
+    import json
+    import os
+    global _FE_GOLDEN
+    if _FE_GOLDEN is None:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frontend_golden.json")) as fh:
+            _FE_GOLDEN = json.load(fh)
+    gold = _FE_GOLDEN[name]
+    out = []
+    for rec in gold["instructions"]:
+        params = None
+        if "params" in rec:
+            params = [np.array([float.fromhex(x) for x in p["array"]]) if "array" in p else
+                      p["symbol"] if "symbol" in p else float.fromhex(p["float"]) for p in rec["params"]]
+        out.append(C.instr(rec["name"], rec.get("qubits", []), params, rec.get("memory")))
+    return gold["n_qubits"], out
+
+
+_FE_GOLDEN = None
 CASES = _cases()
 
 #: cases whose full coefficient vector is too large to commit; the fixture keeps a strided

@@ -162,3 +162,16 @@ def test_install_as_qiskit_runs_reference_style_script(tmp_path):
     out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.strip().startswith("OK")
+
+
+@pytest.mark.parametrize("name", list(__import__("cases").FRONTEND_CASES))
+def test_facade_end_to_end_matches_full_reference_stack(name, golden, case_dir):
+    """golden ``fe_<name>``: the reference's real front-end AND real simulator on this source.
+    Here: the facade's lowering + this package's backend (emulated kernels)."""
+    import cases
+    from emu_backend import emu_backend
+    from golden_check import check_against_golden
+    from qiskit_aakash_b200 import execute
+    qc = frontend_cases.CASES[name](API)
+    res = execute(qc, emu_backend(), **copy.deepcopy(cases.FRONTEND_CASES[name])).result()
+    check_against_golden(golden, "fe_" + name, res["results"][0])

@@ -206,3 +206,17 @@ def test_n14_noisy_invariants_and_schedule_independence(backend):
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+@pytest.mark.parametrize("name", list(cases.FRONTEND_CASES))
+def test_facade_on_cuda_matches_full_reference_stack(name, golden, backend, case_dir):
+    """User-level source (tests/frontend_cases.py) through frontend.QuantumCircuit + execute on the
+    GPU vs the reference's real front-end + real simulator (golden ``fe_<name>``)."""
+    import frontend_cases
+    from types import SimpleNamespace
+    from qiskit_aakash_b200 import execute, frontend
+    api = SimpleNamespace(QuantumCircuit=frontend.QuantumCircuit, QuantumRegister=frontend.QuantumRegister,
+                          ClassicalRegister=frontend.ClassicalRegister, pi=frontend.pi)
+    qc = frontend_cases.CASES[name](api)
+    res = execute(qc, backend(), **copy.deepcopy(cases.FRONTEND_CASES[name])).result()
+    check_against_golden(golden, "fe_" + name, res["results"][0])
