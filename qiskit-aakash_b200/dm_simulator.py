@@ -576,7 +576,9 @@ class DmSimulatorB200:
                     print("C-NOT", "   qubit", op.qubits)
                 elif op.name == "measure":
                     prm = op.params if op.params is not None else ["Z"]
-                    if str(prm[0]) == "Bell":
+                    # the reference compares param[0] == 'Bell' directly: true for a plain str, false for
+                    # the Symbol a front-end produces (which then prints as "[Bell, 12]")
+                    if type(prm[0]) is str and prm[0] == "Bell":
                         print("Bell Measure", "   qubit", [int(x) for x in str(prm[1])])
                     else:
                         print(op.name, "   qubit", op.qubits, "    ", prm)

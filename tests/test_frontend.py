@@ -175,3 +175,79 @@ def test_facade_end_to_end_matches_full_reference_stack(name, golden, case_dir):
     qc = frontend_cases.CASES[name](API)
     res = execute(qc, emu_backend(), **copy.deepcopy(cases.FRONTEND_CASES[name])).result()
     check_against_golden(golden, "fe_" + name, res["results"][0])
+
+
+NOTEBOOK_PARTITION_CELL_6 = """
+PARTITIONED CIRCUIT
+
+Partition  0
+U1    qubit [0]      [3.6]
+U3    qubit [2]      [3.141593, 1.570796, 5.741593]
+
+Partition  1
+C-NOT    qubit [0, 1]
+
+Partition  2
+measure    qubit [0]      [Y]
+measure    qubit [1]      [X]
+
+Partition  3
+C-NOT    qubit [1, 0]
+
+Partition  4
+measure    qubit [1]      [Bell, 12]
+
+Partition  5
+measure    qubit [0]      ['Z']
+
+Partition  6
+measure    qubit [0]      [Ensemble, X]
+measure    qubit [1]      [Ensemble, X]
+measure    qubit [2]      [Ensemble, X]
+"""
+
+
+def test_show_partition_reproduces_the_reference_notebook_output(capsys):
+    """dm_simulator_user_guide/features/partition.ipynb cell 6 of the reference: the user source
+    and the text its real execute() printed.  Exercises the facade's instruction order (the Y
+    measure on qubit 0 is listed before the earlier X measure on qubit 1), the U3 merge and the
+    partitioner in one go."""
+    from emu_backend import emu_backend
+    from qiskit_aakash_b200 import QuantumCircuit, QuantumRegister, ClassicalRegister, execute
+    q = QuantumRegister(3)
+    c = ClassicalRegister(3)
+    qc = QuantumCircuit(q, c)
+    qc.u1(3.6, 0)
+    qc.cx(0, 1)
+    qc.u1(2.6, 2)
+    qc.measure(1, 1, basis='X')
+    qc.measure(0, 0, basis='Y')
+    qc.cx(1, 0)
+    qc.s(2)
+    qc.y(2)
+    qc.measure(1, 1, basis='Bell', add_param='12')
+    qc.measure(0, 0)
+    qc.measure(q, c, basis='Ensemble', add_param='X')
+    capsys.readouterr()
+    execute(qc, emu_backend(), show_partition=True).result()
+    printed = capsys.readouterr().out
+    assert printed.strip() == NOTEBOOK_PARTITION_CELL_6.strip()
+
+
+def test_text_views_and_circuit_arithmetic():
+    from qiskit_aakash_b200 import QuantumCircuit, QuantumRegister, ClassicalRegister
+    q = QuantumRegister(2, "q")
+    c = ClassicalRegister(2, "c")
+    a = QuantumCircuit(q, c)
+    a.h(q[0])
+    b = QuantumCircuit(q, c)
+    b.cx(q[0], q[1])
+    b.measure(q[1], c[1], basis="X")
+    both = a + b
+    assert [i.name for i, _, _ in both.data] == ["h", "cx", "measure"] and len(a) == 1
+    a += b
+    assert a.count_ops() == {"h": 1, "cx": 1, "measure": 1} and a.size() == 3 and a.width() == 4
+    text = a.qasm()
+    assert text.splitlines()[:4] == ["OPENQASM 2.0;", 'include "qelib1.inc";', "qreg q[2];", "creg c[2];"]
+    assert "cx q[0],q[1];" in text and "measure q[1] -> c[1];  // basis X" in text
+    assert a.draw() == text == str(a)
