@@ -200,7 +200,17 @@ class ShardedPauliEngine(PauliEngine):
         self.queue = []
 
     def upload(self, vec):
-        raise BasicAerError("stored_density_matrix is not supported on a sharded state yet")
+        """``stored_density_matrix``: every rank uploads its contiguous slice of the reference-order
+        vector (the initial layout is the reference's, so slices are contiguous)."""
+        vec = np.ascontiguousarray(vec, dtype=np.float64).reshape(-1)
+        if vec.size != 4 ** self.n:
+            raise BasicAerError("Wrong input stored density matrix")
+        self.pos = [self.n - 1 - q for q in range(self.n)]
+        part = np.ascontiguousarray(vec[self.rank * self.size:(self.rank + 1) * self.size])
+        self.ctx.upload(self.sptr, part)
+        self.h2d_bytes += part.nbytes
+        self.pending = [None] * self.n
+        self.queue = []
 
     # -- scheduling with exchanges ------------------------------------------------------------
     def compile(self, final=True):
@@ -457,8 +467,31 @@ class ShardedPauliEngine(PauliEngine):
             return out
         return vec
 
+    def _to_current_layout(self, vec):
+        """Reference-order 4^n vector -> this rank's slice in the current slot layout."""
+        full = np.asarray(vec, dtype=np.float64).reshape([4] * self.n)          # axis q <-> qubit q
+        # target axis j holds slot n-1-j, i.e. the qubit q with pos[q] == n-1-j
+        owner = {self.pos[q]: q for q in range(self.n)}
+        axes = [owner[self.n - 1 - j] for j in range(self.n)]
+        flat = np.ascontiguousarray(np.transpose(full, axes)).reshape(-1)
+        return np.ascontiguousarray(flat[self.rank * self.size:(self.rank + 1) * self.size])
+
     def overlap_with(self, other_vec):
-        raise BasicAerError("compare is not supported on a sharded state yet")
+        """dot(other, state) over all shards (``_state_overlap``, ``:1277-1282``): the stored vector
+        is permuted to the current layout on the host, each rank reduces its slice on the device,
+        one all-reduce."""
+        self._localise_all_pending()
+        other_vec = np.ascontiguousarray(other_vec, dtype=np.float64).reshape(-1)
+        if other_vec.size != 4 ** self.n:
+            raise BasicAerError("stored coefficients have the wrong length")
+        self.ctx.upload(self.alloc.ptr(self.scratch), self._to_current_layout(other_vec))
+        part = self.ctx.dot(self.alloc.ptr(self.scratch), self.sptr, self.size)
+        t = self.alloc.empty(1)
+        self.ctx.upload(self.alloc.ptr(t), np.array([part]))
+        self.comm.all_reduce_sum(t)
+        out = np.empty(1)
+        self.ctx.download(self.alloc.ptr(t), out)
+        return float(out[0])
 
 
 class ShardedCircuitRunner:

@@ -80,6 +80,18 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
         circ.u3(0.1, 0.2, 0.3, 1); circ.cx(1, 0)
     circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="XYZ"[seed % 3])
     opts = dict(cases.FULL_NOISE, compute_densitymatrix=False)
+    if mode == "stored":
+        # start from a stored state and compare against stored coefficients (a4, a27) on shards
+        os.chdir(out_dir)
+        start = dm_oracle.run_oracle(n, copy.deepcopy(cases._rand_circuit(n, 20, seed + 100).instructions),
+                                     {"compute_densitymatrix": False})["data"]["coeffmatrix"]
+        other = dm_oracle.run_oracle(n, copy.deepcopy(cases._rand_circuit(n, 20, seed + 200).instructions),
+                                     {"compute_densitymatrix": False})["data"]["coeffmatrix"]
+        if rank == 0:
+            np.save("stored_density_matrix.npy", start)
+            np.save("stored_coefficients.npy", other)
+        dist.barrier()
+        opts.update(custom_densitymatrix="stored_density_matrix", initial_densitymatrix=True, compare=True)
     engines = []
 
     def factory(nq):
@@ -102,6 +114,8 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
             d_c = max(d_c, float(np.max(np.abs(np.asarray(val) - np.asarray(res["data"][key])))))
         elif key.startswith("bell_prob"):
             d_p = max(d_p, max(abs(val[k] - res["data"][key][k]) for k in val))
+        elif key == "fidelity":
+            d_c = max(d_c, float(abs(val - res["data"][key])))
     with open(os.path.join(out_dir, "r%d.txt" % rank), "w") as f:
         f.write("%r %r %d %d\n" % (d_p, d_c, engines[0].exchanges, res["number_of_clock_cycles"] - ref["number_of_clock_cycles"]))
     dist.barrier()
@@ -110,7 +124,8 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
 
 @pytest.mark.parametrize("world,n,seed,mode", [(2, 5, 1, "rand"), (2, 6, 2, "layered"), (4, 6, 3, "rand"),
                                                (4, 7, 4, "layered"), (8, 7, 5, "rand"), (8, 7, 6, "layered"),
-                                               (2, 5, 7, "expect"), (4, 6, 8, "bell"), (8, 7, 9, "expect")])
+                                               (2, 5, 7, "expect"), (4, 6, 8, "bell"), (8, 7, 9, "expect"),
+                                               (2, 5, 10, "stored"), (8, 7, 11, "stored")])
 def test_sharded_backend_matches_oracle(world, n, seed, mode, tmp_path):
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(HERE, "emu"))
