@@ -403,7 +403,64 @@ class ShardedPauliEngine(PauliEngine):
         return host
 
     def n_basis_probabilities(self, nvec, err):
-        raise BasicAerError("N-basis ensemble measurement is not supported on a sharded state yet")
+        """'N'-basis ensemble readout (``dm_simulator.py:446-458``) of a sharded state.
+
+        Every rank contracts its local digit slots on the device, one ``contract_digit`` launch per
+        slot: (I, n.(X,Y,Z)) -> 2 values, so the shard shrinks from 2^n_bits to 2^n_loc (x2 for the
+        half digit when the rank count is an odd power of two).  The global slots have one fixed
+        digit value per rank: their weights (with any pending single-qubit map folded in) scale
+        the rank's partial vector into its share of the 2^n marginal, which is summed with one
+        all-reduce and Walsh-Hadamard transformed on the device."""
+        self.flush()
+        n, n_loc = self.n, self.n_loc
+        unit = np.asarray(nvec, dtype=float)
+        owner = {self.pos[q]: q for q in range(n)}
+        src = self.sptr
+        base = self.alloc.ptr(self.scratch)
+        offset, count = 0, self.size
+        for slot in range(n_loc):
+            if self.pending[owner[slot]] is not None:
+                raise BasicAerError("internal: local qubit with a pending map after flush")
+            count //= 2
+            dst = base + 8 * offset
+            self.ctx.contract_digit(src, dst, 1 << (self.n_bits - 2 * (slot + 1)), 1 << slot, unit * err)
+            src = dst
+            offset = count if offset == 0 else 0        # ping-pong inside the scratch shard
+        rem = 1 << (self.n_bits - 2 * n_loc)             # 1, or 2 = low bit of the straddling digit
+        partial = np.empty(rem << n_loc)
+        self.ctx.download(src, partial)
+        cur = partial.reshape(rem, 1 << n_loc)
+
+        def weights(slot):
+            P = self.pending[owner[slot]]
+            P = np.eye(4) if P is None else np.asarray(P, dtype=float)
+            return np.stack([P[0, :], err * (unit @ P[1:4, :])])           # [result bit][digit value]
+
+        g_index = self.rank << self.n_bits
+        slot = n_loc
+        if rem == 2:                                     # digit = 2 * (rank bit) + (local bit)
+            W = weights(slot)
+            hi = (g_index >> (2 * slot + 1)) & 1
+            cur = np.stack([W[c, 2 * hi] * cur[0] + W[c, 2 * hi + 1] * cur[1] for c in (0, 1)]).reshape(-1)
+            slot += 1
+        else:
+            cur = cur.reshape(-1)
+        while slot < n:
+            W = weights(slot)
+            d = (g_index >> (2 * slot)) & 3
+            cur = np.concatenate([W[0, d] * cur, W[1, d] * cur])
+            slot += 1
+        # index bit p of `cur` <-> slot p; the result wants bit n-1-q <-> qubit q
+        arr = cur.reshape([2] * n)                       # axis j <-> slot n-1-j
+        arr = np.ascontiguousarray(np.transpose(arr, [n - 1 - self.pos[q] for q in range(n)])).reshape(-1)
+        out = self.alloc.empty(2 ** n)
+        self.ctx.upload(self.alloc.ptr(out), arr)
+        self.ctx.sync()
+        self.comm.all_reduce_sum(out)
+        self.ctx.fwht(self.alloc.ptr(out), n)
+        host = np.empty(2 ** n)
+        self.ctx.download(self.alloc.ptr(out), host)
+        return host
 
     def read_coefficients(self, digit_tuples):
         """Coefficients a[p_0..p_{n-1}] of a sharded state: the owning rank reads, one all-reduce
@@ -427,8 +484,22 @@ class ShardedPauliEngine(PauliEngine):
         return out
 
     def to_matrix(self):
-        raise BasicAerError("compute_densitymatrix is not supported on a sharded state; pass "
-                            "compute_densitymatrix=False")
+        """``_compute_densitymatrix`` of a sharded state: result formatting for registers small
+        enough that the 2^n x 2^n matrix is wanted at all -- the coefficient vector is gathered
+        (``download``) and converted by the single-device kernels on every rank's own GPU."""
+        n = self.n
+        if 3 * 16 * 4 ** n > (64 << 30):
+            raise BasicAerError("compute_densitymatrix on %d sharded qubits would need a %d GiB matrix; pass "
+                                "compute_densitymatrix=False" % (n, (16 * 4 ** n) >> 30))
+        vec = self.download()
+        src = self.alloc.empty(4 ** n)
+        self.ctx.upload(self.alloc.ptr(src), vec)
+        work = self.alloc.empty(2 * 4 ** n)
+        out = self.alloc.empty(2 * 4 ** n)
+        self.ctx.to_matrix(self.alloc.ptr(src), n, self.alloc.ptr(work), self.alloc.ptr(out))
+        host = np.empty(2 * 4 ** n)
+        self.ctx.download(self.alloc.ptr(out), host)
+        return host.view(np.complex128).reshape(2 ** n, 2 ** n)
 
     def _localise_all_pending(self):
         """Apply pending maps of global qubits too (costs exchanges): needed before the state

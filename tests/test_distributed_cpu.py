@@ -78,8 +78,21 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
     elif mode == "bell":
         circ.measure(0, 0, basis="Bell", add_param="0%d" % (n - 1))
         circ.u3(0.1, 0.2, 0.3, 1); circ.cx(1, 0)
-    circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="XYZ"[seed % 3])
+    if mode == "nbasis":
+        def ensemble_n(vec):
+            circ.barrier()
+            for q in range(n):
+                circ.instructions.append(C.instr("measure", [q], ["Ensemble", ["N", np.array(vec)]], memory=[q]))
+            circ.barrier()
+        ensemble_n([0.3, -1.1, 0.7])
+        for q in range(n):
+            circ.u3(0.4 + q, 0.1, 0.2, q)                       # pending maps on global qubits at the readout
+        ensemble_n([1.0, 2.0, -0.5])
+    else:
+        circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="XYZ"[seed % 3])
     opts = dict(cases.FULL_NOISE, compute_densitymatrix=False)
+    if mode == "matrix":
+        opts["compute_densitymatrix"] = True
     if mode == "stored":
         # start from a stored state and compare against stored coefficients (a4, a27) on shards
         os.chdir(out_dir)
@@ -114,6 +127,8 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
             d_c = max(d_c, float(np.max(np.abs(np.asarray(val) - np.asarray(res["data"][key])))))
         elif key.startswith("bell_prob"):
             d_p = max(d_p, max(abs(val[k] - res["data"][key][k]) for k in val))
+        elif key == "densitymatrix":
+            d_c = max(d_c, float(np.max(np.abs(np.asarray(val) - np.asarray(res["data"][key])))))
         elif key == "fidelity":
             d_c = max(d_c, float(abs(val - res["data"][key])))
     with open(os.path.join(out_dir, "r%d.txt" % rank), "w") as f:
@@ -125,7 +140,9 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
 @pytest.mark.parametrize("world,n,seed,mode", [(2, 5, 1, "rand"), (2, 6, 2, "layered"), (4, 6, 3, "rand"),
                                                (4, 7, 4, "layered"), (8, 7, 5, "rand"), (8, 7, 6, "layered"),
                                                (2, 5, 7, "expect"), (4, 6, 8, "bell"), (8, 7, 9, "expect"),
-                                               (2, 5, 10, "stored"), (8, 7, 11, "stored")])
+                                               (2, 5, 10, "stored"), (8, 7, 11, "stored"),
+                                               (4, 6, 15, "matrix"),
+                                               (2, 5, 12, "nbasis"), (4, 6, 13, "nbasis"), (8, 7, 14, "nbasis")])
 def test_sharded_backend_matches_oracle(world, n, seed, mode, tmp_path):
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(HERE, "emu"))

@@ -27,10 +27,20 @@ def main():
     from qiskit_aakash_b200.dm_simulator import DmSimulatorB200
     comm = distributed.TorchCommunicator()
     worst = 0.0
-    for n, seed, mode in ((8, 1, "rand"), (9, 2, "layered"), (10, 3, "rand"), (10, 4, "layered")):
-        circ = cases._rand_circuit(n, 60, seed) if mode == "rand" else C.random_layered(n, 6, seed, readout=False)
-        circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="XYZ"[seed % 3])
-        opts = dict(cases.FULL_NOISE, compute_densitymatrix=False)
+    for n, seed, mode in ((8, 1, "rand"), (9, 2, "layered"), (10, 3, "rand"), (10, 4, "layered"), (9, 5, "nbasis"),
+                          (8, 6, "matrix")):
+        circ = cases._rand_circuit(n, 60, seed) if mode != "layered" else C.random_layered(n, 6, seed, readout=False)
+        if mode == "nbasis":                     # N-basis ensemble readout with pending maps on global qubits
+            for q in range(n):
+                circ.u3(0.4 + q, 0.1, 0.2, q)
+            circ.barrier()
+            for q in range(n):
+                circ.instructions.append(C.instr("measure", [q], ["Ensemble", ["N", np.array([1.0, 2.0, -0.5])]],
+                                                 memory=[q]))
+            circ.barrier()
+        else:
+            circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="XYZ"[seed % 3])
+        opts = dict(cases.FULL_NOISE, compute_densitymatrix=(mode == "matrix"))
         engines = []
 
         def factory(nq):
@@ -48,6 +58,8 @@ def main():
             p_ref = np.array(list(ref["data"]["ensemble_probability"].values()))
             d_p = float(np.max(np.abs(p_got - p_ref)))
             d_c = float(np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])))
+            if mode == "matrix":
+                d_c = max(d_c, float(np.max(np.abs(res["data"]["densitymatrix"] - ref["data"]["densitymatrix"]))))
             worst = max(worst, d_p, d_c)
             print(json.dumps({"check": "sharded_vs_oracle", "world": world, "n": n, "mode": mode, "d_prob": d_p,
                               "d_coeff": d_c, "exchanges": engines[0].exchanges, "fused_exchange": engines[0].peers is not None,
