@@ -88,6 +88,7 @@ typedef struct dmb_stats {
   uint64_t fused_ops;            /* dmb_op entries executed                                */
   uint64_t state_bytes_moved;    /* algorithmic HBM bytes of tile passes: 16 B x elements  */
   uint64_t r3_phases;            /* register phases executed by the 3-digits-per-thread kernel */
+  uint64_t folded_swaps;         /* trailing SWAP ops realised by the relabelling write-back instead */
 } dmb_stats;
 
 /* ---- context ------------------------------------------------------------------------ */

@@ -29,7 +29,7 @@ PASS_DTYPE = np.dtype([("n_tile_digits", "<i4"), ("n_ops", "<i4"), ("tile_digit"
 class Stats(ctypes.Structure):
     _fields_ = [("tile_pass_launches", ctypes.c_uint64), ("other_launches", ctypes.c_uint64),
                 ("fused_ops", ctypes.c_uint64), ("state_bytes_moved", ctypes.c_uint64),
-                ("r3_phases", ctypes.c_uint64)]
+                ("r3_phases", ctypes.c_uint64), ("folded_swaps", ctypes.c_uint64)]
 
 
 class DmbError(RuntimeError):

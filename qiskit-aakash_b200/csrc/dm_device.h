@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <string.h>
 #include "dmb200.h"
+#include <cstdlib>
 
 #if defined(__CUDACC__)
 #define DMB_HD __host__ __device__ __forceinline__
@@ -306,8 +307,22 @@ struct alignas(16) dmb_lean_pass {
   int32_t pad_;
   uint64_t pair_goff[DMB_LEAN_PAIRS];   // element offset of the uniform part (i << 9)
   uint32_t pair_soff[DMB_LEAN_PAIRS];   // swizzled byte offset of the uniform part
+  // relabelling store (trailing SWAP ops folded into the write-back, see dmb_make_lean_pass):
+  // store-index digit k is read from tile digit st_perm[k]
+  int32_t st_mode;                      // DMB_ST_PLAIN / DMB_ST_PERM128 / DMB_ST_SPLIT64
+  int32_t st_perm[DMB_LEAN_K];
+  uint32_t st_delta;                    // SPLIT64: byte-address XOR between the two elements of a pair
+  uint32_t st_pair_soff[DMB_LEAN_PAIRS];
   dmb_lean_op ops[DMB_MAX_OPS];
 };
+enum { DMB_ST_PLAIN = 0, DMB_ST_PERM128 = 1, DMB_ST_SPLIT64 = 2 };
+
+// tile-local index of the element that store index l2 (digits in NEW global order) reads
+DMB_HD uint32_t dmb_st_source(uint32_t l2, const int32_t* perm) {
+  uint32_t l = 0;
+  for (int k = 0; k < DMB_LEAN_K; ++k) l |= ((l2 >> (2 * k)) & 3u) << (2 * perm[k]);
+  return l;
+}
 
 // Specialisation ids: the hot (kind, matrix class, access mode) combinations get straight-line
 // code (no flag branches, no register moves at control-flow merges: 302 -> ~190 issued
@@ -322,7 +337,19 @@ inline bool dmb_variant_is_specialised(int kindx, int ma, int mb) {
 }
 
 // host-side conversion (runs once per pass, before the launch)
-inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L) {
+// With `fold_swaps` the SWAP ops at the END of the op list are not executed in shared memory:
+// a swap of two tile digits only renames which global digit position each of them is written
+// back to, so it is folded into the store addressing (the tile covers the same addresses).
+// The store then walks the tile in the NEW global order (coalescing unchanged: same global
+// offset tables) and gathers from the permuted shared-memory addresses -- as 128-bit pairs while
+// tile digit 0 stays in place, as two 64-bit reads per pair otherwise.  Saves one 64 KiB
+// shared-memory round trip per swap (0.13 ms at n = 14).
+inline bool dmb_fold_swaps_enabled() {         // DMB_FOLD_SWAPS=0 keeps trailing swaps as shared-memory ops (A/B switch)
+  static const bool on = [] { const char* e = getenv("DMB_FOLD_SWAPS"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, bool fold_swaps = false) {
   L.n_tiles = 1ull << (n_bits - 2 * DMB_LEAN_K);
   L.n_ops = P.n_ops;
   L.pad_ = 0;
@@ -332,7 +359,28 @@ inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L) 
     L.pair_goff[i] = dmb_tile_off(l, P.tile_digit, DMB_LEAN_K);
     L.pair_soff[i] = dmb_swz(l) << 3;
   }
-  for (int k = 0; k < P.n_ops; ++k) {
+  int dest[DMB_LEAN_K];                       // tile digit j's content ends up at tile digit dest[j]
+  for (int j = 0; j < DMB_LEAN_K; ++j) dest[j] = j;
+  if (fold_swaps) {
+    int first = P.n_ops;
+    while (first > 0 && P.ops[first - 1].kind == DMB_OP_SWAP && (P.ops[first - 1].flags & (DMB_HAS_PA | DMB_HAS_PB)) == 0 &&
+           P.ops[first - 1].post_swap == 0)
+      --first;
+    for (int k = first; k < P.n_ops; ++k) {
+      const int a = P.ops[k].a, b = P.ops[k].b;
+      for (int j = 0; j < DMB_LEAN_K; ++j) dest[j] = dest[j] == a ? b : (dest[j] == b ? a : dest[j]);
+    }
+    L.n_ops = first;
+  }
+  bool identity = true;
+  for (int j = 0; j < DMB_LEAN_K; ++j) {
+    L.st_perm[dest[j]] = j;
+    if (dest[j] != j) identity = false;
+  }
+  L.st_mode = identity ? DMB_ST_PLAIN : (L.st_perm[0] == 0 ? DMB_ST_PERM128 : DMB_ST_SPLIT64);
+  L.st_delta = dmb_swz(dmb_st_source(1u, L.st_perm)) << 3;
+  for (int i = 0; i < DMB_LEAN_PAIRS; ++i) L.st_pair_soff[i] = dmb_swz(dmb_st_source((uint32_t)i << 9, L.st_perm)) << 3;
+  for (int k = 0; k < L.n_ops; ++k) {
     const dmb_op& o = P.ops[k];
     dmb_lean_op& q = L.ops[k];
     for (int i = 0; i < 4; ++i) {
@@ -367,6 +415,7 @@ struct dmb_lean_thread {        // per-thread constants, computed once per launc
   uint32_t tq[4];               // the thread's four base-4 index digits
   uint64_t goff;                // global element offset of pair 0 (l = 2t)
   uint32_t soff;                // swizzled byte offset of pair 0
+  uint32_t st_soff;             // relabelling store: swizzled byte offset of the source of pair 0
 };
 
 DMB_HD void dmb_lean_thread_init(int t, const dmb_lean_pass& L, dmb_lean_thread& T) {
@@ -374,6 +423,7 @@ DMB_HD void dmb_lean_thread_init(int t, const dmb_lean_pass& L, dmb_lean_thread&
   T.tq[2] = ((uint32_t)t >> 4) & 3u; T.tq[3] = ((uint32_t)t >> 6) & 3u;
   T.goff = dmb_tile_off(2u * (uint32_t)t, L.td, DMB_LEAN_K);
   T.soff = dmb_swz(2u * (uint32_t)t) << 3;
+  T.st_soff = L.st_mode == DMB_ST_PLAIN ? T.soff : dmb_swz(dmb_st_source(2u * (uint32_t)t, L.st_perm)) << 3;
 }
 
 // arithmetic of one op on the thread's 16-block (shared by all access modes)
@@ -591,12 +641,22 @@ DMB_HD void dmb_lean_load_thread(const dmb_lean_thread& T, const dmb_lean_pass& 
               *reinterpret_cast<const dmb_d2*>(dmb_src_ptr(S, state, tile_base + (T.goff | L.pair_goff[i]))));
 }
 
-template <bool PUSH, class Mem>
+template <bool PUSH, int STMODE, class Mem>
 DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass& L, double* state,
                                   uint64_t tile_base, const dmb_remote_src& D, const Mem& mem) {
   dmb_d2 w[DMB_LEAN_PAIRS];
 #pragma unroll
-  for (int i = 0; i < DMB_LEAN_PAIRS; ++i) w[i] = mem.ld128(T.soff ^ L.pair_soff[i]);
+  for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
+    if constexpr (STMODE == DMB_ST_PLAIN) {
+      w[i] = mem.ld128(T.soff ^ L.pair_soff[i]);
+    } else if constexpr (STMODE == DMB_ST_PERM128) {
+      w[i] = mem.ld128(T.st_soff ^ L.st_pair_soff[i]);
+    } else {
+      const uint32_t a = T.st_soff ^ L.st_pair_soff[i];
+      w[i].x = mem.ld64(a);
+      w[i].y = mem.ld64(a ^ L.st_delta);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
     const uint64_t idx = tile_base + (T.goff | L.pair_goff[i]);

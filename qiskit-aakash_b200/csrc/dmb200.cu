@@ -118,7 +118,8 @@ __device__ __forceinline__ void cp_async16s(uint32_t smem_dst, const void* gsrc)
 // STAGES-deep ring of 32 KiB stages per CTA: tiles k+1 .. k+STAGES-1 are in flight while the
 // op run executes on tile k.  (STAGES, CTAs per SM) = (2, 3) or (3, 2) fit the 227 KB of
 // shared memory; chosen at run time (dmb_set_tile_variant / DMB_LEAN_STAGES).
-template <int STAGES, int CTAS, int REMOTE>      // REMOTE: 0 in place, 1 pull (remote loads), 2 push (remote stores)
+// STMODE: DMB_ST_PLAIN, or a relabelling store that realises the pass's trailing digit swaps
+template <int STAGES, int CTAS, int REMOTE, int STMODE = DMB_ST_PLAIN>      // REMOTE: 0 in place, 1 pull (remote loads), 2 push (remote stores)
 __global__ void __launch_bounds__(DMB_TILE_THREADS, CTAS)
 k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L,
              const __grid_constant__ dmb_remote_src S) {
@@ -167,7 +168,7 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
       dmb_lean_op_dispatch(T, L.ops[i], mem);
       __syncthreads();
     }
-    dmb_lean_store_thread<REMOTE == 2>(T, L, state, dmb_tile_base(tile, L.td, DMB_LEAN_K), S, mem);
+    dmb_lean_store_thread<REMOTE == 2, STMODE>(T, L, state, dmb_tile_base(tile, L.td, DMB_LEAN_K), S, mem);
     __syncthreads();
     cur = (cur + 1 == STAGES) ? 0 : cur + 1;
     fill = (fill + 1 == STAGES) ? 0 : fill + 1;
@@ -332,18 +333,18 @@ static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_p
   return 0;
 }
 
-template <int STAGES, int CTAS, int REMOTE>
+template <int STAGES, int CTAS, int REMOTE, int STMODE = DMB_ST_PLAIN>
 static int launch_lean(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, const dmb_remote_src& S = g_no_remote) {
   const size_t smem = (size_t)STAGES * DMB_LEAN_TILE_BYTES;
   static bool attr_done = false;
   if (!attr_done) {
-    CU_TRY(cudaFuncSetAttribute(k_tile_pass6<STAGES, CTAS, REMOTE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_tile_pass6<STAGES, CTAS, REMOTE, STMODE>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
   if (grid > L.n_tiles) grid = L.n_tiles;
-  k_tile_pass6<STAGES, CTAS, REMOTE><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, L, S);
+  k_tile_pass6<STAGES, CTAS, REMOTE, STMODE><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, L, S);
   CU_TRY(cudaGetLastError());
   return 0;
 }
@@ -372,13 +373,18 @@ static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_
     }
   }
   static dmb_lean_pass L;                 // 6.5 KB: keep it off the stack; single-threaded per ctx
-  dmb_make_lean_pass(P, n_bits, L);
+  const bool fold = ctx->tile_variant == 0 && dmb_fold_swaps_enabled();
+  dmb_make_lean_pass(P, n_bits, L, fold);
+  ctx->stats.folded_swaps += (uint64_t)(P.n_ops - L.n_ops);
   switch (ctx->tile_variant) {
     case 2: return launch_lean<3, 2, 0>(ctx, state, L);
     case 3: return launch_lean<2, 2, 0>(ctx, state, L);
     case 6: return launch_lean<1, 4, 0>(ctx, state, L);
     case 7: return launch_lean<1, 5, 0>(ctx, state, L);
-    default: return launch_lean<2, 3, 0>(ctx, state, L);
+    default:
+      if (L.st_mode == DMB_ST_PERM128) return launch_lean<2, 3, 0, DMB_ST_PERM128>(ctx, state, L);
+      if (L.st_mode == DMB_ST_SPLIT64) return launch_lean<2, 3, 0, DMB_ST_SPLIT64>(ctx, state, L);
+      return launch_lean<2, 3, 0>(ctx, state, L);
   }
 }
 

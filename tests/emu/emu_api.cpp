@@ -75,10 +75,13 @@ static void run_tile_pass(double* state, int n_bits, const dmb_pass& P, const dm
 }
 
 // lean K = 6 path: same per-thread bodies as k_tile_pass6, tiles processed one after another
+static int g_variant = 0;
+static thread_local long g_folded_swaps = 0;
 static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const dmb_remote_src& S = g_no_remote,
                            const dmb_remote_src& D = g_no_remote) {
   static thread_local dmb_lean_pass L;
-  dmb_make_lean_pass(P, n_bits, L);
+  dmb_make_lean_pass(P, n_bits, L, g_variant == 0 && dmb_fold_swaps_enabled() && !S.enabled && !D.enabled);
+  g_folded_swaps += P.n_ops - L.n_ops;
   alignas(128) static thread_local unsigned char stage[DMB_LEAN_TILE_BYTES];
   static thread_local dmb_lean_thread T[DMB_TILE_THREADS];
   for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_thread_init(t, L, T[t]);
@@ -89,7 +92,12 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const d
     for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, state, tbase, S, mem);
     for (int i = 0; i < L.n_ops; ++i)
       for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_dispatch(T[t], L.ops[i], mem);
-    for (int t = 0; t < DMB_TILE_THREADS; ++t) { if (D.enabled) dmb_lean_store_thread<true>(T[t], L, state, tbase, D, mem); else dmb_lean_store_thread<false>(T[t], L, state, tbase, D, mem); }
+    for (int t = 0; t < DMB_TILE_THREADS; ++t) {
+      if (D.enabled) dmb_lean_store_thread<true, DMB_ST_PLAIN>(T[t], L, state, tbase, D, mem);
+      else if (L.st_mode == DMB_ST_PERM128) dmb_lean_store_thread<false, DMB_ST_PERM128>(T[t], L, state, tbase, D, mem);
+      else if (L.st_mode == DMB_ST_SPLIT64) dmb_lean_store_thread<false, DMB_ST_SPLIT64>(T[t], L, state, tbase, D, mem);
+      else dmb_lean_store_thread<false, DMB_ST_PLAIN>(T[t], L, state, tbase, D, mem);
+    }
   }
 }
 
@@ -116,7 +124,6 @@ static bool run_tile_pass_r3(double* state, int n_bits, const dmb_pass& P) {
   return true;
 }
 
-static int g_variant = 0;
 
 extern "C" {
 
@@ -181,7 +188,8 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
       case 6:
         if (g_variant == 1) run_tile_pass<6>(state, n_bits, P);
         else if ((g_variant == 4 || g_variant == 5) && run_tile_pass_r3(state, n_bits, P)) {}
-        else run_tile_pass6(state, n_bits, P);
+        else { const long before = g_folded_swaps; run_tile_pass6(state, n_bits, P);
+               ctx->stats.folded_swaps += (uint64_t)(g_folded_swaps - before); }
         break;
       default: return fail("dmb_apply_passes", "unsupported tile size");
     }

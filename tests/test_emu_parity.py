@@ -84,3 +84,30 @@ def test_streaming_drain_matches_golden(name, tail, chunk, golden, case_dir, mon
     check_against_golden(golden, name, run_case(name, DmSimulatorB200(_engine_factory=factory)))
     assert engines[0].drain_tail == tail
     assert engines[0].passes_run >= 2
+
+
+def test_trailing_swaps_are_folded_into_the_store(golden, case_dir, monkeypatch):
+    """The relabelling store (dmb_make_lean_pass(fold_swaps)): trailing SWAP ops of a pass become
+    a digit permutation of the write-back.  Same numbers as running them as shared-memory ops
+    (bit for bit: a swap moves data, it does no arithmetic), and the counter shows it happened."""
+    import json
+    import subprocess
+    import sys
+    results = {}
+    for fold in ("1", "0"):
+        code = ("import os, sys, json; os.environ['DMB_FOLD_SWAPS']=%r; sys.path[:0]=%r; import numpy as np; "
+                "import cases, emu_backend; from qiskit_aakash_b200 import assemble, circuits as C; "
+                "from qiskit_aakash_b200.dm_simulator import DmSimulatorB200; "
+                "case=cases.get('layered_n10_d3_noisy'); c=C.Circuit(case['n']); c.instructions=case['instrs']; "
+                "es=[]; f=lambda n: (es.append(emu_backend.emu_engine(n)) or es[-1]); "
+                "r=DmSimulatorB200(_engine_factory=f).run(assemble(c), backend_options=case['options']).result(); "
+                "v=r['results'][0]['data']['coeffmatrix']; "
+                "print(json.dumps({'folded': es[0].stats()['folded_swaps'], 'sum': float(v.sum()).hex(), "
+                "'dot': float(v @ v).hex(), 'sample': [float(x).hex() for x in v[::4099]]}))"
+                % (fold, sys.path))
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        results[fold] = json.loads(out.stdout.strip().splitlines()[-1])
+    assert results["1"]["folded"] > 0 and results["0"]["folded"] == 0
+    for key in ("sum", "dot", "sample"):
+        assert results["1"][key] == results["0"][key]
