@@ -228,7 +228,8 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": "k_tile_pass<6>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": pass_ms, "algorithmic_bytes_per_launch": per_launch_bytes,
-                "fused_ops_per_launch": counters["fused_ops"] / max(1, counters["tile_pass_launches"])}
+                "fused_ops_per_launch": counters["fused_ops"] / max(1, counters["tile_pass_launches"]),
+                "swaps_folded_into_store_per_launch": counters.get("folded_swaps", 0) / max(1, counters["tile_pass_launches"])}
     if world == 1:
         roofline.update(unfused_launch_points(runner.engine, n, peak))
         roofline["note"] = ("launches that fuse more than ~3 ops are shared-memory-bandwidth bound (one 64 KiB round "

@@ -313,6 +313,11 @@ struct alignas(16) dmb_lean_pass {
   int32_t st_perm[DMB_LEAN_K];
   uint32_t st_delta;                    // SPLIT64: byte-address XOR between the two elements of a pair
   uint32_t st_pair_soff[DMB_LEAN_PAIRS];
+  // SPLIT64 walks the tile in its own thread order (bit k of the thread index is bit st_tbit[k] of
+  // the store index, the pair counter supplies the rest): chosen by the host so that the 16 lanes
+  // of a half-warp read 16 distinct 8-byte bank slots while a warp still writes whole 128-byte lines
+  int32_t st_tbit[8];
+  uint64_t st_pair_goff[DMB_LEAN_PAIRS];
   dmb_lean_op ops[DMB_MAX_OPS];
 };
 enum { DMB_ST_PLAIN = 0, DMB_ST_PERM128 = 1, DMB_ST_SPLIT64 = 2 };
@@ -344,6 +349,43 @@ inline bool dmb_variant_is_specialised(int kindx, int ma, int mb) {
 // offset tables) and gathers from the permuted shared-memory addresses -- as 128-bit pairs while
 // tile digit 0 stays in place, as two 64-bit reads per pair otherwise.  Saves one 64 KiB
 // shared-memory round trip per swap (0.13 ms at n = 14).
+// Thread order of the SPLIT64 store.  Store-index bits 1..3 (high bit of the new digit 0 and the
+// new digit 1) must be lane bits so that a warp's 16-byte stores fill whole 128-byte lines; the
+// other two lane bits are free.  Among the orders that satisfy this, take one whose half-warps
+// (lanes 0-15, 64-bit loads) hit the fewest equal bank slots -- the swizzle spreads the OLD digits
+// 0 and 1 over the slots, and after the swap old digit 0 is a high digit of the store index.
+inline void dmb_choose_split_order(const int32_t* perm, int32_t* tbit, int* ibit) {
+  int best_cost = 1 << 30, best[5] = {1, 2, 3, 4, 5};
+  for (int e0 = 4; e0 <= 11; ++e0)
+    for (int e1 = e0 + 1; e1 <= 11; ++e1) {
+      const int five[5] = {1, 2, 3, e0, e1};
+      for (int top = 0; top < 5; ++top) {              // which of the five is lane bit 4
+        int lanes[5], w = 0;
+        for (int k = 0; k < 5; ++k) if (k != top) lanes[w++] = five[k];
+        lanes[4] = five[top];
+        int cost = 0;
+        for (int lo = 0; lo < 2; ++lo) {
+          int count[16] = {0};
+          for (int lane = 0; lane < 16; ++lane) {
+            uint32_t l2 = (uint32_t)lo;
+            for (int k = 0; k < 4; ++k) l2 |= (((uint32_t)lane >> k) & 1u) << lanes[k];
+            ++count[dmb_swz(dmb_st_source(l2, perm)) & 15u];
+          }
+          for (int sl = 0; sl < 16; ++sl) if (count[sl] > cost) cost = count[sl];
+        }
+        if (cost < best_cost) { best_cost = cost; for (int k = 0; k < 5; ++k) best[k] = lanes[k]; }
+      }
+    }
+  bool used[12] = {false};
+  used[0] = true;
+  for (int k = 0; k < 5; ++k) { tbit[k] = best[k]; used[best[k]] = true; }
+  int next = 5;
+  for (int b = 1; b <= 11; ++b) {
+    if (used[b]) continue;
+    if (next < 8) tbit[next++] = b; else ibit[next++ - 8] = b;
+  }
+}
+
 inline bool dmb_fold_swaps_enabled() {         // DMB_FOLD_SWAPS=0 keeps trailing swaps as shared-memory ops (A/B switch)
   static const bool on = [] { const char* e = getenv("DMB_FOLD_SWAPS"); return !(e && e[0] == '0'); }();
   return on;
@@ -379,7 +421,15 @@ inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, 
   }
   L.st_mode = identity ? DMB_ST_PLAIN : (L.st_perm[0] == 0 ? DMB_ST_PERM128 : DMB_ST_SPLIT64);
   L.st_delta = dmb_swz(dmb_st_source(1u, L.st_perm)) << 3;
-  for (int i = 0; i < DMB_LEAN_PAIRS; ++i) L.st_pair_soff[i] = dmb_swz(dmb_st_source((uint32_t)i << 9, L.st_perm)) << 3;
+  int ibit[3] = {9, 10, 11};
+  for (int k = 0; k < 8; ++k) L.st_tbit[k] = k + 1;
+  if (L.st_mode == DMB_ST_SPLIT64) dmb_choose_split_order(L.st_perm, L.st_tbit, ibit);
+  for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
+    uint32_t l2 = 0;
+    for (int k = 0; k < 3; ++k) l2 |= (((uint32_t)i >> k) & 1u) << ibit[k];
+    L.st_pair_soff[i] = dmb_swz(dmb_st_source(l2, L.st_perm)) << 3;
+    L.st_pair_goff[i] = dmb_tile_off(l2, P.tile_digit, DMB_LEAN_K);
+  }
   for (int k = 0; k < L.n_ops; ++k) {
     const dmb_op& o = P.ops[k];
     dmb_lean_op& q = L.ops[k];
@@ -416,6 +466,7 @@ struct dmb_lean_thread {        // per-thread constants, computed once per launc
   uint64_t goff;                // global element offset of pair 0 (l = 2t)
   uint32_t soff;                // swizzled byte offset of pair 0
   uint32_t st_soff;             // relabelling store: swizzled byte offset of the source of pair 0
+  uint64_t st_goff;             // SPLIT64 store: global element offset of the thread part
 };
 
 DMB_HD void dmb_lean_thread_init(int t, const dmb_lean_pass& L, dmb_lean_thread& T) {
@@ -423,7 +474,10 @@ DMB_HD void dmb_lean_thread_init(int t, const dmb_lean_pass& L, dmb_lean_thread&
   T.tq[2] = ((uint32_t)t >> 4) & 3u; T.tq[3] = ((uint32_t)t >> 6) & 3u;
   T.goff = dmb_tile_off(2u * (uint32_t)t, L.td, DMB_LEAN_K);
   T.soff = dmb_swz(2u * (uint32_t)t) << 3;
-  T.st_soff = L.st_mode == DMB_ST_PLAIN ? T.soff : dmb_swz(dmb_st_source(2u * (uint32_t)t, L.st_perm)) << 3;
+  uint32_t l2 = 0;
+  for (int k = 0; k < 8; ++k) l2 |= (((uint32_t)t >> k) & 1u) << L.st_tbit[k];
+  T.st_soff = L.st_mode == DMB_ST_PLAIN ? T.soff : dmb_swz(dmb_st_source(l2, L.st_perm)) << 3;
+  T.st_goff = dmb_tile_off(l2, L.td, DMB_LEAN_K);
 }
 
 // arithmetic of one op on the thread's 16-block (shared by all access modes)
@@ -659,7 +713,7 @@ DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass&
   }
 #pragma unroll
   for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
-    const uint64_t idx = tile_base + (T.goff | L.pair_goff[i]);
+    const uint64_t idx = tile_base + (STMODE == DMB_ST_SPLIT64 ? (T.st_goff | L.st_pair_goff[i]) : (T.goff | L.pair_goff[i]));
     double* dst = PUSH ? reinterpret_cast<double*>(D.tab[idx >> D.shift]) + idx : state + idx;
     *reinterpret_cast<dmb_d2*>(dst) = w[i];
   }

@@ -103,6 +103,24 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const d
 
 // R3 path (three digits per thread), same bodies as k_tile_pass_r3
 static long g_r3_passes = 0, g_r3_phases = 0, g_r3_ops = 0;
+// test hook: thread order chosen for a SPLIT64 store + worst number of half-warp lanes per bank slot
+extern "C" int dmb_emu_split_order(const int32_t* perm, int32_t* tbit_out) {
+  int ibit[3];
+  for (int k = 0; k < 8; ++k) tbit_out[k] = k + 1;
+  dmb_choose_split_order(perm, tbit_out, ibit);
+  int worst = 0;
+  for (int half = 0; half < 2; ++half)
+    for (int lo = 0; lo < 2; ++lo) {
+      int count[16] = {0};
+      for (int lane = 0; lane < 16; ++lane) {
+        uint32_t l2 = (uint32_t)lo | ((uint32_t)half << tbit_out[4]);
+        for (int k = 0; k < 4; ++k) l2 |= (((uint32_t)lane >> k) & 1u) << tbit_out[k];
+        ++count[dmb_swz(dmb_st_source(l2, perm)) & 15u];
+      }
+      for (int sl = 0; sl < 16; ++sl) if (count[sl] > worst) worst = count[sl];
+    }
+  return worst;
+}
 extern "C" void dmb_emu_r3_counters(long* out) { out[0] = g_r3_passes; out[1] = g_r3_phases; out[2] = g_r3_ops; }
 
 static bool run_tile_pass_r3(double* state, int n_bits, const dmb_pass& P) {

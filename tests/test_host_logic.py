@@ -336,3 +336,31 @@ def test_streaming_schedule_equals_one_shot_schedule():
     streamed = np.concatenate(parts)
     assert len(parts) > 3 and pos_a == pos_b
     assert streamed.tobytes() == whole.tobytes()
+
+
+def test_split_store_thread_order_is_bank_conflict_free():
+    """Relabelling store with tile digit 0 swapped away (two 64-bit shared-memory reads per pair):
+    the library picks a thread order whose half-warps read 16 distinct 8-byte bank slots, and whose
+    warps still cover store-index bits 1..3 (whole 128-byte lines in global memory)."""
+    import ctypes
+    import itertools
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "emu"))
+    import build_emu
+    lib = ctypes.CDLL(build_emu.build())
+    lib.dmb_emu_split_order.restype = ctypes.c_int
+    checked = 0
+    for perm in itertools.permutations(range(6)):
+        if perm[0] == 0:
+            continue                                   # digit 0 stays: 128-bit path, nothing to choose
+        moved = sum(1 for k in range(6) if perm[k] != k)
+        if moved > 4:
+            continue                                   # the scheduler emits at most two transpositions
+        p = (ctypes.c_int32 * 6)(*perm)
+        tb = (ctypes.c_int32 * 8)()
+        worst = lib.dmb_emu_split_order(p, tb)
+        assert worst == 1, (perm, list(tb), worst)
+        assert {1, 2, 3} <= set(tb[:5]) and len(set(tb)) == 8 and all(1 <= b <= 11 for b in tb)
+        checked += 1
+    assert checked > 50
