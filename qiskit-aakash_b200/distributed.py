@@ -172,6 +172,7 @@ class ShardedPauliEngine(PauliEngine):
         self.drain_threshold = 0         # exchanges are collectives: compile whole queues
         self.relabel = False
         self.relabel_local = bool(int(os.environ.get("DMB_RELABEL", "1")))
+        self.park_in_last_pass = bool(int(os.environ.get("DMB_PARK_IN_LAST_PASS", "1")))
         self.exchanges = 0
         self.nvlink_bytes_sent = 0
         # fused exchange: the pass after a slot swap pulls its tiles from the peers' buffers
@@ -234,6 +235,17 @@ class ShardedPauliEngine(PauliEngine):
                     run.append(item)
             use_relabel = self.relabel_local and self.nd >= 4
             chunks = []                      # PASS arrays of this exchange-free stretch
+            victims = []
+            if keep:
+                # evict the local qubits whose next use is farthest away (never-used first)
+                next_use = {}
+                for idx, (_, _, qa, qb, _, _, _) in enumerate(keep):
+                    next_use.setdefault(qa, idx)
+                    next_use.setdefault(qb, idx)
+                local = [q for q in range(self.n) if pos[q] < n_loc]
+                local.sort(key=lambda q: (-next_use.get(q, len(keep) + 1), pos[q]))
+                victims = local[:m]
+            moves = [(v, n_loc - m + i) for i, v in enumerate(victims)]
             if use_relabel:
                 qops = [schedule.DevOp(kind, qa, qb, pa, pb, coef) for (_, kind, qa, qb, pa, pb, coef) in run]
                 if not keep and final:
@@ -247,24 +259,21 @@ class ShardedPauliEngine(PauliEngine):
                     for q in left:
                         self.pending[q] = None
                 if qops:
-                    chunks.append(schedule.build_passes_relabel(qops, pos, self.nd, max_ops=self.max_ops_per_pass))
+                    # the evictees are parked in the top local slots by trailing swaps of the stretch's
+                    # last pass where its tile has room (folded into the write-back: free)
+                    P, moves = schedule.build_passes_relabel(qops, pos, self.nd, max_ops=self.max_ops_per_pass,
+                                                             final_moves=moves if self.park_in_last_pass else [])
+                    if not self.park_in_last_pass:
+                        moves = [(v, n_loc - m + i) for i, v in enumerate(victims)]
+                    chunks.append(P)
                 devops = []
             else:
                 devops = [schedule.DevOp(kind, pos[qa], pos[qb], pa, pb, coef)
                           for (_, kind, qa, qb, pa, pb, coef) in run]
             queue = keep
             if queue:
-                # evict the local qubits whose next use is farthest away (never-used first)
-                next_use = {}
-                for idx, (_, _, qa, qb, _, _, _) in enumerate(queue):
-                    next_use.setdefault(qa, idx)
-                    next_use.setdefault(qb, idx)
-                local = [q for q in range(self.n) if pos[q] < n_loc]
-                local.sort(key=lambda q: (-next_use.get(q, len(queue) + 1), pos[q]))
-                victims = local[:m]
                 slot_owner = {pos[q]: q for q in range(self.n)}
-                for i, v in enumerate(victims):
-                    target = n_loc - m + i
+                for v, target in moves:
                     if pos[v] != target:
                         other = slot_owner[target]
                         devops.append(schedule.DevOp(capi.OP_SWAP, pos[v], target))

@@ -178,8 +178,14 @@ def _greedy_select(remaining, start_set, cap, max_ops, window, n_qubits):
 
 
 def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_OPS, window=256,
-                         swap_weight=0.0, fuse=None, min_tail=0):
+                         swap_weight=0.0, fuse=None, min_tail=0, final_moves=None):
     """Like ``build_passes`` but with dynamic relabelling of the two low digit positions.
+
+    ``final_moves`` = [(qubit, digit position)]: after the last op, move these qubits to the given
+    positions (the sharded engine parks the qubits it is about to evict in the top local slots).
+    Moves whose two digit positions fit into the last pass's tile ride along as trailing swaps
+    (free: the library folds them into the write-back); the rest are returned for a pass of
+    their own.  The return value is then ``(passes, leftover moves)``.
 
     With ``min_tail`` > 0 scheduling stops as soon as no more than ``min_tail`` ops are left and
     ``(passes, leftover ops)`` is returned: a caller that is still producing ops keeps the tail
@@ -217,6 +223,14 @@ def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max
         remaining = [op for i, op in enumerate(remaining) if i not in chosen_set]
         # tile digit positions: the chosen qubits' positions + positions 0,1 (+ filler)
         tile_d = {pos[q] for q in tile_q} | {0, 1} if n_digits >= 2 else {pos[q] for q in tile_q}
+        moves_here = []
+        if final_moves and not remaining:
+            for q, target in final_moves:
+                if pos[q] == target:
+                    continue
+                if len(tile_d | {pos[q], target}) <= K:
+                    tile_d |= {pos[q], target}
+                    moves_here.append((q, target))
         d = 0
         while len(tile_d) < K:
             if d not in tile_d:
@@ -259,7 +273,20 @@ def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max
                     pos[other] = src
                 else:
                     owner.pop(src, None)
+        for q, target in moves_here:                      # trailing swaps of the last pass
+            src = pos[q]
+            if src == target:
+                continue
+            other = owner.get(target)
+            devops.append(DevOp(capi.OP_SWAP, src, target))
+            owner[target], pos[q] = q, target
+            if other is not None:
+                owner[src], pos[other] = other, src
+            else:
+                owner.pop(src, None)
         plans.append((sorted(tile_d), fuse_swaps(devops) if fuse else devops))
+    if final_moves is not None:
+        return encode_passes(plans), [(q, t) for q, t in final_moves if pos[q] != t]
     if min_tail > 0:
         return encode_passes(plans), remaining
     return encode_passes(plans)
