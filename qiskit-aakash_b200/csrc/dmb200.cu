@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <map>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -322,10 +323,10 @@ static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_p
                             const dmb_remote_src& S = g_no_remote, const dmb_remote_src& D = g_no_remote) {
   const uint64_t n_tiles = 1ull << (n_bits - 2 * K);
   const size_t smem = sizeof(double) << (2 * K);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_done{0};          // one bit per device: the attribute is per device
+  if (!((attr_done.load() >> (ctx->device & 63)) & 1ull)) {
     CU_TRY(cudaFuncSetAttribute(k_tile_pass<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done.fetch_or(1ull << (ctx->device & 63));
   }
   const uint64_t grid = n_tiles < 0x7fffffffull ? n_tiles : 0x7fffffffull;
   k_tile_pass<K><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, P, n_tiles, S, D);
@@ -336,11 +337,11 @@ static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_p
 template <int STAGES, int CTAS, int REMOTE, int STMODE = DMB_ST_PLAIN>
 static int launch_lean(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, const dmb_remote_src& S = g_no_remote) {
   const size_t smem = (size_t)STAGES * DMB_LEAN_TILE_BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_done{0};
+  if (!((attr_done.load() >> (ctx->device & 63)) & 1ull)) {
     CU_TRY(cudaFuncSetAttribute(k_tile_pass6<STAGES, CTAS, REMOTE, STMODE>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done.fetch_or(1ull << (ctx->device & 63));
   }
   uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
   if (grid > L.n_tiles) grid = L.n_tiles;
@@ -352,10 +353,10 @@ static int launch_lean(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, cons
 template <int STAGES, int CTAS>
 static int launch_r3(dmb_ctx* ctx, double* state, const dmb_r3_pass& R) {
   const size_t smem = (size_t)STAGES * DMB_LEAN_TILE_BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_done{0};
+  if (!((attr_done.load() >> (ctx->device & 63)) & 1ull)) {
     CU_TRY(cudaFuncSetAttribute(k_tile_pass_r3<STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done.fetch_or(1ull << (ctx->device & 63));
   }
   uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
   if (grid > R.n_tiles) grid = R.n_tiles;
@@ -366,13 +367,13 @@ static int launch_r3(dmb_ctx* ctx, double* state, const dmb_r3_pass& R) {
 
 static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass& P) {
   if (ctx->tile_variant == 4 || ctx->tile_variant == 5) {
-    static dmb_r3_pass R;
+    static thread_local dmb_r3_pass R;
     if (dmb_make_r3_pass(P, n_bits, R)) {
       ctx->stats.r3_phases += (uint64_t)R.n_phases;
       return ctx->tile_variant == 5 ? launch_r3<1, 4>(ctx, state, R) : launch_r3<2, 3>(ctx, state, R);
     }
   }
-  static dmb_lean_pass L;                 // 6.5 KB: keep it off the stack; single-threaded per ctx
+  static thread_local dmb_lean_pass L;    // 6.5 KB: keep it off the stack; one host thread drives a ctx
   const bool fold = ctx->tile_variant == 0 && dmb_fold_swaps_enabled();
   dmb_make_lean_pass(P, n_bits, L, fold);
   ctx->stats.folded_swaps += (uint64_t)(P.n_ops - L.n_ops);
@@ -523,7 +524,7 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
     // dmb_op.post_swap (a layout remap attached to an op) is executed as an explicit swap op:
     // folding it into the op's store was implemented and measured -- no faster, and the extra
     // registers slowed every other op by 3 % -- so the kernels do not carry that path
-    static dmb_pass expanded[2];
+    static thread_local dmb_pass expanded[2];
     int n_run = 1;
     const dmb_pass* run = &passes[i];
     if (dmb_pass_has_post_swap(passes[i])) {
@@ -560,7 +561,7 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
   if (block_shift + tab_bits != n_bits) return fail("dmb_apply_pass_remote", "block_shift + tab_bits != n_bits");
   CU_TRY(cudaSetDevice(ctx->device));
   if (validate_pass(*pass, n_bits)) return 1;
-  static dmb_pass expanded_r[2];
+  static thread_local dmb_pass expanded_r[2];
   const dmb_pass* pp = pass;
   if (dmb_pass_has_post_swap(*pass)) {
     if (dmb_expand_post_swaps(*pass, expanded_r) != 1) return fail("dmb_apply_pass_remote", "pass too long after expanding remaps");
@@ -581,7 +582,7 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
     case 4: rc = launch_tile_pass<4>(ctx, dst_state, n_bits, P, ld, st); break;
     case 5: rc = launch_tile_pass<5>(ctx, dst_state, n_bits, P, ld, st); break;
     case 6: {
-      static dmb_lean_pass L;
+      static thread_local dmb_lean_pass L;
       dmb_make_lean_pass(P, n_bits, L);
       rc = push ? launch_lean<2, 3, 2>(ctx, dst_state, L, S) : launch_lean<2, 3, 1>(ctx, dst_state, L, S);
       break;
