@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMB_ABI_VERSION 1
+#define DMB_ABI_VERSION 2   /* 2: dmb_stats.folded_swaps */
 #define DMB_MAX_TILE_DIGITS 6   /* a tile holds 4^6 = 4096 doubles = 32 KiB of shared memory */
 #define DMB_MAX_OPS 16          /* fused ops per tile pass */
 #define DMB_MAX_QUBITS 32

@@ -26,6 +26,9 @@ PASS_DTYPE = np.dtype([("n_tile_digits", "<i4"), ("n_ops", "<i4"), ("tile_digit"
                        ("ops", OP_DTYPE, (MAX_OPS,))])
 
 
+ABI_VERSION = 2          # include/dmb200.h DMB_ABI_VERSION
+
+
 class Stats(ctypes.Structure):
     _fields_ = [("tile_pass_launches", ctypes.c_uint64), ("other_launches", ctypes.c_uint64),
                 ("fused_ops", ctypes.c_uint64), ("state_bytes_moved", ctypes.c_uint64),
@@ -88,7 +91,7 @@ def load_library(path=None):
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.dmb_abi_version() != 1:
+    if lib.dmb_abi_version() != ABI_VERSION:
         raise DmbError("ABI version mismatch")
     if lib.dmb_sizeof_op() != OP_DTYPE.itemsize or lib.dmb_sizeof_pass() != PASS_DTYPE.itemsize:
         raise DmbError("struct layout mismatch between capi.py and libdmb200.so")
