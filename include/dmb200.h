@@ -126,7 +126,10 @@ int dmb_init_product(dmb_ctx* ctx, double* state, int n_bits, uint64_t rank_bits
  *      amp_decay :397-425, _add_qasm_measure_X/Y/Z/N :574-704, the projections of
  *      _pauli_string_expectation :553-566, the mask of _add_bell_basis_measure :749-756,
  *      _add_qasm_reset :810-823) -- pre-scheduled into tile passes by the host.
- * `passes` is HOST memory; it is consumed before the call returns (kernel parameters). */
+ * `passes` is HOST memory; it is consumed before the call returns (kernel parameters).
+ * DMB_OP_SWAP ops WITHOUT maps at the end of a pass's op list are not executed in shared
+ * memory: they are realised by the tile's write-back addressing (same result, counted in
+ * dmb_stats.folded_swaps; environment DMB_FOLD_SWAPS=0 disables this).                   */
 int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits,
                      const dmb_pass* passes, size_t n_passes);
 
