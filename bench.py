@@ -235,6 +235,23 @@ def run_ours(args):
         roofline["note"] = ("launches that fuse more than ~3 ops are shared-memory-bandwidth bound (one 64 KiB round "
                             "trip per tile and op), so frac against HBM falls as fusion grows while circuit time "
                             "improves; see staging_only / one_gate_per_launch for the HBM-bound operating points")
+    # second roofline of the same launches: shared-memory traffic of the op phase.  Every op executed in
+    # shared memory reads and writes the whole tile (2 x 8 B per coefficient), staging adds one write
+    # (cp.async) and one read (write-back); peak = 128 B/clk/SM x SMs x the SM clock sampled during the run.
+    try:
+        launches = max(1, counters["tile_pass_launches"])
+        smem_ops = (counters["fused_ops"] - counters.get("folded_swaps", 0)) / launches
+        smem_bytes = (smem_ops + 1.0) * 16.0 * 4 ** n / world
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
+        if mhz:
+            smem_peak = 128.0 * sm_count * mhz * 1e6 / 1e9
+            smem_ach = smem_bytes / (pass_ms * 1e-3) / 1e9
+            roofline["shared_memory"] = {"bound": "smem", "achieved": smem_ach, "peak": smem_peak, "unit": "GB/s",
+                                         "frac": smem_ach / smem_peak, "ops_in_smem_per_launch": smem_ops,
+                                         "peak_source": "128 B/clk/SM x %d SMs x %.0f MHz (sampled)" % (sm_count, mhz)}
+    except Exception:
+        pass
     prof = os.path.join(ROOT, "profiles", "r01_tile_pass_ncu_summary.json")
     if os.path.exists(prof):
         try:
