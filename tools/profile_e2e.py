@@ -14,10 +14,17 @@ def main():
     import bench
     from qiskit_aakash_b200 import BasicAer, assemble, circuits
     n, depth, _ = bench.workload(1)
-    if len(sys.argv) > 1:
-        n, depth = int(sys.argv[1]), int(sys.argv[2])
     opts = dict(circuits.noisy_options(), compute_densitymatrix=False)
-    qobj = assemble(circuits.random_layered(n, depth, 100 * n))
+    if len(sys.argv) > 1 and sys.argv[1] == "grover12":
+        qobj = assemble(circuits.grover(7, "1011001", 1))
+        opts = dict(circuits.grover_options(), compute_densitymatrix=False)
+    elif len(sys.argv) > 1 and sys.argv[1] == "qft8":
+        qobj = assemble(circuits.qft(8))
+        opts = {}
+    else:
+        if len(sys.argv) > 2:
+            n, depth = int(sys.argv[1]), int(sys.argv[2])
+        qobj = assemble(circuits.random_layered(n, depth, 100 * n))
     backend = BasicAer.get_backend("dm_simulator")
     for _ in range(2):
         backend.run(qobj, backend_options=copy.deepcopy(opts)).result()
