@@ -220,3 +220,15 @@ def test_facade_on_cuda_matches_full_reference_stack(name, golden, backend, case
     qc = frontend_cases.CASES[name](api)
     res = execute(qc, backend(), **copy.deepcopy(cases.FRONTEND_CASES[name])).result()
     check_against_golden(golden, "fe_" + name, res["results"][0])
+
+
+def test_relabelling_store_is_an_exact_digit_permutation_on_cuda(backend):
+    """Swap-only passes through libdmb200.so (k_tile_pass6<..., PERM128 / SPLIT64>) == NumPy axis
+    swaps, bit for bit; all swaps folded into the write-back."""
+    import store_cases
+    from qiskit_aakash_b200 import engine
+    folded, total = store_cases.check_relabelling_store(lambda n: engine.PauliEngine(n))
+    assert folded == total
+    folded, total = store_cases.check_relabelling_store(lambda n: engine.PauliEngine(n), n=9,
+                                                        tile_digits=(0, 1, 2, 5, 7, 8))
+    assert folded == total

@@ -364,3 +364,12 @@ def test_split_store_thread_order_is_bank_conflict_free():
         assert {1, 2, 3} <= set(tb[:5]) and len(set(tb)) == 8 and all(1 <= b <= 11 for b in tb)
         checked += 1
     assert checked > 50
+
+
+def test_relabelling_store_is_an_exact_digit_permutation():
+    """Swap-only passes on the emulated kernels == NumPy axis swaps, bit for bit, and every swap
+    was realised by the write-back (none ran as a shared-memory op)."""
+    from emu_backend import emu_engine
+    import store_cases
+    folded, total = store_cases.check_relabelling_store(emu_engine)
+    assert folded == total
