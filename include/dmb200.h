@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMB_ABI_VERSION 2   /* 2: dmb_stats.folded_swaps */
+#define DMB_ABI_VERSION 3   /* 2: dmb_stats.folded_swaps; 3: dmb_schedule */
 #define DMB_MAX_TILE_DIGITS 6   /* a tile holds 4^6 = 4096 doubles = 32 KiB of shared memory */
 #define DMB_MAX_OPS 16          /* fused ops per tile pass */
 #define DMB_MAX_QUBITS 32
@@ -132,6 +132,49 @@ int dmb_init_product(dmb_ctx* ctx, double* state, int n_bits, uint64_t rank_bits
  * dmb_stats.folded_swaps; environment DMB_FOLD_SWAPS=0 disables this).                   */
 int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits,
                      const dmb_pass* passes, size_t n_passes);
+
+/* ---- host-side gate-fusion scheduler (no device work; generalises the reference's per-qubit
+ *      U3 merge, basicaertools.py:251-307 single_gate_merge, from "adjacent single-qubit gates"
+ *      to "every op whose qubits fit one 4^6-coefficient tile") ---------------------------------
+ * Input: the op stream in program order on QUBIT ids -- every single-qubit map (rotations, noise,
+ * projections, resets) has already been multiplied into the pa / pb of the next two-qubit op of
+ * its qubit by the caller.  pos[q] = digit position of qubit q (positions >= n_digits are allowed
+ * for qubits no op touches: the global slots of a sharded state); it is advanced to the layout
+ * after the last emitted pass.  The scheduler packs the stream into tile passes of <= max_tile
+ * digits and <= max_ops ops (greedy list scheduling over the next `window` ops; an op is hoisted
+ * past skipped ops only when it shares no qubit with them, which is exact because ops on disjoint
+ * qubits commute).  Digit positions 0 and 1 belong to every tile (128-byte runs in HBM), so after
+ * each pass it chooses which two qubits of the tile should occupy them next -- the pair whose
+ * greedy next pass runs the most ops -- and appends the DMB_OP_SWAP ops that move them there
+ * (trailing swaps are free: dmb_apply_passes folds them into the write-back).
+ *   min_tail > 0: stop as soon as no more than min_tail ops are left and return their indices in
+ *     left[0..*n_left) (program order) -- a caller that is still producing ops keeps them queued,
+ *     so pass boundaries do not depend on where the stream was cut;
+ *   moves / n_moves (may be NULL): *n_moves pairs (qubit, digit position) to realise after the
+ *     last op (the sharded engine parks the qubits it is about to send away in the top local
+ *     slots).  Moves whose digits fit the last pass's tile ride along as trailing swaps; the rest
+ *     are written back to moves[] and counted in *n_moves.
+ * out must have room for out_cap passes (n_ops always suffices).                                 */
+typedef struct dmb_qop {
+  int32_t kind;      /* DMB_OP_*                                                            */
+  int32_t flags;     /* DMB_HAS_PA | DMB_HAS_PB                                             */
+  int32_t qa, qb;    /* qubit ids; qb = -1: lone single-qubit map (kind DMB_OP_MATS)        */
+  double pa[12];     /* rows 1..3 of the pending map of qubit qa                            */
+  double pb[12];     /* rows 1..3 of the pending map of qubit qb                            */
+  double coef[16];
+} dmb_qop;           /* 336 bytes */
+size_t dmb_sizeof_qop(void);
+/* strategy: how the qubits of a pass's tile are chosen.
+ *   DMB_SCHED_PROGRAM_ORDER  walk the stream in program order and let the first ops that fit claim
+ *                            the tile (list scheduling as it is usually done);
+ *   DMB_SCHED_TILE_SEARCH    grow the tile by the qubits of one ready op at a time, keeping the
+ *                            choice that lets the most ops run: finds time-skewed windows on
+ *                            nearest-neighbour circuits (fewer, fuller passes).                     */
+enum { DMB_SCHED_PROGRAM_ORDER = 0, DMB_SCHED_TILE_SEARCH = 1 };
+int dmb_schedule(const dmb_qop* ops, size_t n_ops, int32_t* pos, int n_qubits, int n_digits,
+                 int max_tile, int max_ops, int window, int strategy, size_t min_tail,
+                 int32_t* moves, int32_t* n_moves,
+                 dmb_pass* out, size_t out_cap, size_t* n_out, int32_t* left, size_t* n_left);
 
 /* ---- multi-GPU: fused exchange + tile pass over NVLink peer memory -----------------------
  * In the pass that follows a global<->local slot swap (qiskit-aakash_b200/distributed.py) the

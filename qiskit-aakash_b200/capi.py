@@ -26,7 +26,10 @@ PASS_DTYPE = np.dtype([("n_tile_digits", "<i4"), ("n_ops", "<i4"), ("tile_digit"
                        ("ops", OP_DTYPE, (MAX_OPS,))])
 
 
-ABI_VERSION = 2          # include/dmb200.h DMB_ABI_VERSION
+QOP_DTYPE = np.dtype([("kind", "<i4"), ("flags", "<i4"), ("qa", "<i4"), ("qb", "<i4"), ("pa", "<f8", (12,)),
+                      ("pb", "<f8", (12,)), ("coef", "<f8", (16,))])
+
+ABI_VERSION = 3          # include/dmb200.h DMB_ABI_VERSION
 
 
 class Stats(ctypes.Structure):
@@ -49,6 +52,8 @@ _SIGNATURES = {
     "dmb_sizeof_op": (_sz, []),
     "dmb_sizeof_pass": (_sz, []),
     "dmb_last_error": (_c.c_char_p, []),
+    "dmb_sizeof_qop": (_sz, []),
+    "dmb_schedule": (_i, [_vp, _sz, _vp, _i, _i, _i, _i, _i, _i, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "dmb_create": (_i, [_i, _c.POINTER(_vp)]),
     "dmb_destroy": (_i, [_vp]),
     "dmb_set_stream": (_i, [_vp, _vp]),
@@ -95,12 +100,46 @@ def load_library(path=None):
         raise DmbError("ABI version mismatch")
     if lib.dmb_sizeof_op() != OP_DTYPE.itemsize or lib.dmb_sizeof_pass() != PASS_DTYPE.itemsize:
         raise DmbError("struct layout mismatch between capi.py and libdmb200.so")
+    if lib.dmb_sizeof_qop() != QOP_DTYPE.itemsize:
+        raise DmbError("struct layout mismatch between capi.py and libdmb200.so (dmb_qop)")
     _LIBRARIES[path] = lib
     return lib
 
 
 def _ptr(arr):
     return arr.ctypes.data_as(ctypes.c_void_p)
+
+
+SCHED_PROGRAM_ORDER, SCHED_TILE_SEARCH = 0, 1
+
+
+def schedule(lib, qops, pos, n_digits, max_tile=MAX_TILE_DIGITS, max_ops=MAX_OPS, window=256, min_tail=0,
+             final_moves=None, strategy=SCHED_PROGRAM_ORDER):
+    """``dmb_schedule``: QOP_DTYPE array (program order, qubit ids) -> (PASS_DTYPE array, indices of
+    the ops left unscheduled, leftover final moves or None).  ``pos`` (list) is advanced in place."""
+    assert qops.dtype == QOP_DTYPE and qops.flags["C_CONTIGUOUS"]
+    n_ops = len(qops)
+    pos_arr = np.ascontiguousarray(pos, dtype=np.int32)
+    out = np.empty(max(n_ops, 1), dtype=PASS_DTYPE)
+    left = np.empty(max(n_ops, 1), dtype=np.int32)
+    n_out, n_left = ctypes.c_size_t(), ctypes.c_size_t()
+    if final_moves is not None:
+        mv = np.ascontiguousarray(list(final_moves) or [(0, 0)], dtype=np.int32).reshape(-1, 2)
+        n_mv = ctypes.c_int32(len(final_moves))
+        mv_p, n_mv_p = _ptr(mv), ctypes.cast(ctypes.byref(n_mv), ctypes.c_void_p)
+    else:
+        mv_p = n_mv_p = None
+    rc = lib.dmb_schedule(_ptr(qops), n_ops, _ptr(pos_arr), len(pos), int(n_digits), int(max_tile), int(max_ops),
+                          int(window), int(strategy), int(min_tail), mv_p, n_mv_p, _ptr(out), len(out),
+                          ctypes.cast(ctypes.byref(n_out), ctypes.c_void_p), _ptr(left),
+                          ctypes.cast(ctypes.byref(n_left), ctypes.c_void_p))
+    if rc != 0:
+        raise DmbError(lib.dmb_last_error().decode("utf-8", "replace"))
+    pos[:] = pos_arr.tolist()
+    moves_left = None
+    if final_moves is not None:
+        moves_left = [(int(q), int(t)) for q, t in mv[:n_mv.value]]
+    return out[:n_out.value], left[:n_left.value], moves_left
 
 
 class Context:

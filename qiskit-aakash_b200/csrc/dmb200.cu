@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "dm_device.h"
+#include "dm_schedule.h"
 
 // ---------------------------------------------------------------------------------------
 // error handling
@@ -427,6 +428,18 @@ int dmb_abi_version(void) { return DMB_ABI_VERSION; }
 size_t dmb_sizeof_op(void) { return sizeof(dmb_op); }
 size_t dmb_sizeof_pass(void) { return sizeof(dmb_pass); }
 const char* dmb_last_error(void) { return g_err.c_str(); }
+
+size_t dmb_sizeof_qop(void) { return sizeof(dmb_qop); }
+int dmb_schedule(const dmb_qop* ops, size_t n_ops, int32_t* pos, int n_qubits, int n_digits, int max_tile,
+                 int max_ops, int window, int strategy, size_t min_tail, int32_t* moves, int32_t* n_moves,
+                 dmb_pass* out, size_t out_cap, size_t* n_out, int32_t* left, size_t* n_left) {
+  if ((!ops && n_ops) || !pos || !out || !n_out) return fail("dmb_schedule", "null argument");
+  std::string err;
+  if (dmb_sched::schedule_impl(ops, n_ops, pos, n_qubits, n_digits, max_tile, max_ops, window, strategy, min_tail, moves,
+                               n_moves, out, out_cap, n_out, left, n_left, err))
+    return fail("dmb_schedule", err.c_str());
+  return 0;
+}
 
 int dmb_create(int device, dmb_ctx** out) {
   if (!out) return fail("dmb_create", "null out pointer");

@@ -165,7 +165,8 @@ class ShardedPauliEngine(PauliEngine):
         self.pos = [self.n - 1 - q for q in range(self.n)]      # qubit -> slot
         self.pending = [None] * self.n
         self.queue = []
-        self.max_ops_per_pass = int(max_ops_per_pass or os.environ.get("DMB_MAX_OPS_PER_PASS", 10))
+        self.max_ops_per_pass = int(max_ops_per_pass or os.environ.get("DMB_MAX_OPS_PER_PASS", capi.MAX_OPS))
+        self.strategy = int(os.environ.get("DMB_SCHED_STRATEGY", capi.SCHED_TILE_SEARCH))
         self.reserve_low = int(reserve_low if reserve_low is not None else os.environ.get("DMB_RESERVE_LOW", 2))
         self.passes_run = 0
         self.h2d_bytes = 0
@@ -261,8 +262,9 @@ class ShardedPauliEngine(PauliEngine):
                 if qops:
                     # the evictees are parked in the top local slots by trailing swaps of the stretch's
                     # last pass where its tile has room (folded into the write-back: free)
-                    P, moves = schedule.build_passes_relabel(qops, pos, self.nd, max_ops=self.max_ops_per_pass,
-                                                             final_moves=moves if self.park_in_last_pass else [])
+                    P, moves = schedule.relabel_passes(self.lib, qops, pos, self.nd, max_ops=self.max_ops_per_pass,
+                                                       final_moves=moves if self.park_in_last_pass else [],
+                                                       strategy=self.strategy)
                     if not self.park_in_last_pass:
                         moves = [(v, n_loc - m + i) for i, v in enumerate(victims)]
                     chunks.append(P)

@@ -176,7 +176,8 @@ class PauliEngine:
         self.pending = [None] * self.n
         self.queue = []
         # scheduling knobs (env overrides are for on-GPU experiments)
-        self.max_ops_per_pass = int(max_ops_per_pass or os.environ.get("DMB_MAX_OPS_PER_PASS", 10))
+        self.max_ops_per_pass = int(max_ops_per_pass or os.environ.get("DMB_MAX_OPS_PER_PASS", capi.MAX_OPS))
+        self.strategy = int(os.environ.get("DMB_SCHED_STRATEGY", capi.SCHED_TILE_SEARCH))
         self.reserve_low = int(reserve_low if reserve_low is not None else os.environ.get("DMB_RESERVE_LOW", 2))
         self.passes_run = 0
         self.h2d_bytes = 0
@@ -280,7 +281,8 @@ class PauliEngine:
                     qops.append(schedule.DevOp(capi.OP_MATS, left[-1], None, self.pending[left[-1]], None))
             if not qops:
                 return np.zeros(0, dtype=capi.PASS_DTYPE)
-            return schedule.build_passes_relabel(qops, self.pos, self.nd, max_ops=self.max_ops_per_pass)
+            return schedule.relabel_passes(self.lib, qops, self.pos, self.nd, max_ops=self.max_ops_per_pass,
+                                           strategy=getattr(self, "strategy", capi.SCHED_PROGRAM_ORDER))
         ops = self.device_ops(final=final)
         if not ops:
             return np.zeros(0, dtype=capi.PASS_DTYPE)
@@ -296,8 +298,8 @@ class PauliEngine:
                 return
             qops = [schedule.DevOp(kind, qa, qb, pa, pb, coef) for (_, kind, qa, qb, pa, pb, coef) in self.queue]
             item_of = {id(op): item for op, item in zip(qops, self.queue)}
-            passes, left = schedule.build_passes_relabel(qops, self.pos, self.nd, max_ops=self.max_ops_per_pass,
-                                                         min_tail=tail)
+            passes, left = schedule.relabel_passes(self.lib, qops, self.pos, self.nd, max_ops=self.max_ops_per_pass,
+                                                   min_tail=tail, strategy=getattr(self, "strategy", 0))
             self.queue = [item_of[id(op)] for op in left]
             self.run_passes(passes)
             return

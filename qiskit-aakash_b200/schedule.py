@@ -177,6 +177,59 @@ def _greedy_select(remaining, start_set, cap, max_ops, window, n_qubits):
     return chosen, tile
 
 
+def pack_qops(qops):
+    """[DevOp on qubit ids] -> ``capi.QOP_DTYPE`` array for ``dmb_schedule`` (vectorised: the
+    matrices are stacked once instead of being copied field by field)."""
+    n = len(qops)
+    arr = np.zeros(n, dtype=capi.QOP_DTYPE)
+    if not n:
+        return arr
+    arr["kind"] = [op.kind for op in qops]
+    arr["qa"] = [op.da for op in qops]
+    arr["qb"] = [-1 if op.db is None else op.db for op in qops]
+    flags = np.zeros(n, dtype=np.int32)
+    for field, bit in (("pa", capi.HAS_PA), ("pb", capi.HAS_PB)):
+        idx = [i for i, op in enumerate(qops) if getattr(op, field) is not None]
+        if idx:
+            mats = np.asarray([getattr(qops[i], field) for i in idx], dtype=np.float64)
+            if mats.shape[1:] != (4, 4):
+                raise ValueError("single-qubit map must be 4x4")
+            if not np.array_equal(mats[:, 0, :], np.broadcast_to([1.0, 0.0, 0.0, 0.0], (len(idx), 4))):
+                raise ValueError("single-qubit map is not trace preserving (row 0 != e0)")
+            arr[field][idx] = mats[:, 1:4, :].reshape(len(idx), 12)
+            flags[idx] |= bit
+    arr["flags"] = flags
+    for i, op in enumerate(qops):
+        if op.coef is not None:
+            c = np.asarray(op.coef, dtype=np.float64).reshape(-1)
+            arr["coef"][i, :c.size] = c
+    return arr
+
+
+#: The native scheduler (``dmb_schedule``, csrc/dm_schedule.h) is the product path; the Python
+#: ``build_passes_relabel`` below is its executable specification (tests compare them byte for
+#: byte) and serves the two experimental knobs the native one does not carry (fuse, swap_weight).
+NATIVE_DEFAULT = bool(int(os.environ.get("DMB_NATIVE_SCHEDULE", "1")))
+
+
+def relabel_passes(lib, qops, pos, n_digits, max_ops=capi.MAX_OPS, min_tail=0, final_moves=None, native=None,
+                   strategy=capi.SCHED_PROGRAM_ORDER):
+    """``build_passes_relabel`` through ``dmb_schedule`` of ``lib``.  Same return convention:
+    passes | (passes, leftover ops) with ``min_tail`` | (passes, leftover moves) with ``final_moves``.
+    ``strategy``: ``capi.SCHED_PROGRAM_ORDER`` (what the Python specification does) or
+    ``capi.SCHED_TILE_SEARCH`` (native only)."""
+    native = NATIVE_DEFAULT if native is None else native
+    if not native or FUSE_SWAPS_DEFAULT:
+        return build_passes_relabel(qops, pos, n_digits, max_ops=max_ops, min_tail=min_tail, final_moves=final_moves)
+    passes, left, moves_left = capi.schedule(lib, pack_qops(qops), pos, n_digits, max_ops=max_ops, min_tail=min_tail,
+                                             final_moves=final_moves, strategy=strategy)
+    if final_moves is not None:
+        return passes, moves_left
+    if min_tail > 0:
+        return passes, [qops[i] for i in left]
+    return passes
+
+
 def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_OPS, window=256,
                          swap_weight=0.0, fuse=None, min_tail=0, final_moves=None):
     """Like ``build_passes`` but with dynamic relabelling of the two low digit positions.

@@ -7,6 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "libdmb200_emu.so")
 SRCS = [os.path.join(HERE, "emu_api.cpp")]
 DEPS = SRCS + [os.path.join(ROOT, "qiskit-aakash_b200", "csrc", "dm_device.h"),
+               os.path.join(ROOT, "qiskit-aakash_b200", "csrc", "dm_schedule.h"),
                os.path.join(ROOT, "include", "dmb200.h")]
 
 
