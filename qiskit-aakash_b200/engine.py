@@ -22,6 +22,7 @@ state has at least two digit positions (the kernels work on digit pairs).
 """
 from __future__ import annotations
 
+import math
 import os
 
 import numpy as np
@@ -51,18 +52,26 @@ def rotation_matrix(axis, angle, err):
 
 def gate_matrix(name, params, rotation_error):
     """u3(theta,phi,lam) = rz(lam), ry(theta), rz(phi) applied in that order; u1(lam) = rz(lam)
-    (``single_gate_dm_matrix``, ``basicaertools.py:69-90``)."""
-    p = list(map(float, params))
-    if name in ("U", "u3"):
-        seq = (("rz", p[2]), ("ry", p[0]), ("rz", p[1]))
-    elif name == "u1":
-        seq = (("rz", p[0]),)
-    else:
+    (``single_gate_dm_matrix``, ``basicaertools.py:69-90``).  The product of the three
+    ``rotation_matrix`` factors is written out (same association as multiplying them one after the
+    other), because building and multiplying 4x4 arrays per gate dominated the lowering time."""
+    p = [float(x) for x in params]
+    rz, dz = rotation_error["rz"]
+    if name == "u1":
+        cl, sl = rz * math.cos(p[0] + dz), rz * math.sin(p[0] + dz)
+        return np.array([[1.0, 0.0, 0.0, 0.0], [0.0, cl, -sl, 0.0], [0.0, sl, cl, 0.0], [0.0, 0.0, 0.0, 1.0]])
+    if name not in ("U", "u3"):
         raise BasicAerError("Gate is not among the valid types: %s" % name)
-    m = np.eye(4)
-    for axis, ang in seq:
-        m = rotation_matrix(axis, ang, rotation_error[axis]) @ m
-    return m
+    ry, dy = rotation_error["ry"]
+    cl, sl = rz * math.cos(p[2] + dz), rz * math.sin(p[2] + dz)      # rz(lam):   X' = cX - sY, Y' = cY + sX
+    ct, st = ry * math.cos(p[0] + dy), ry * math.sin(p[0] + dy)      # ry(theta): Z' = cZ - sX, X' = cX + sZ
+    cp, sp = rz * math.cos(p[1] + dz), rz * math.sin(p[1] + dz)      # rz(phi)
+    ax = (ct * cl, ct * -sl, st)              # rows of ry(theta) @ rz(lam)
+    ay = (sl, cl, 0.0)
+    return np.array([[1.0, 0.0, 0.0, 0.0],
+                     [0.0, cp * ax[0] - sp * ay[0], cp * ax[1] - sp * ay[1], cp * ax[2]],
+                     [0.0, sp * ax[0] + cp * ay[0], sp * ax[1] + cp * ay[1], sp * ax[2]],
+                     [0.0, -st * cl, -st * -sl, ct]])
 
 
 def memory_noise_matrix(f, p, g):
@@ -99,8 +108,21 @@ def reset_matrix():
     return m
 
 
+_CX_COEF_CACHE = {}
+
+
 def cx_coefficients(tsp):
     """(c, s, c2, s2, cs) of ``cx_gate_dm_matrix`` (``basicaertools.py:329-336``)."""
+    key = (float(tsp[0]), float(tsp[1]))
+    hit = _CX_COEF_CACHE.get(key)
+    if hit is None:
+        if len(_CX_COEF_CACHE) > 64:
+            _CX_COEF_CACHE.clear()
+        hit = _CX_COEF_CACHE[key] = _cx_coefficients(key)
+    return hit
+
+
+def _cx_coefficients(tsp):
     cav, e1 = float(tsp[0]), float(tsp[1])
     c2av = 4 * cav - 3
     c = cav * np.cos(e1)
