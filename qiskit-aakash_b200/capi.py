@@ -233,10 +233,14 @@ class Context:
         nv = np.ascontiguousarray(nv, dtype=np.float64)
         self._check(self.lib.dmb_contract_digit(self._h, in_ptr, out_ptr, int(H), int(L), _ptr(nv)))
 
+    READ_CHUNK = 1 << 16         # the library's gather scratch holds 4^8 coefficients per call
+
     def read_coeffs(self, state_ptr, idx):
         idx = np.ascontiguousarray(idx, dtype=np.uint64)
         out = np.empty(len(idx), dtype=np.float64)
-        self._check(self.lib.dmb_read_coeffs(self._h, state_ptr, _ptr(idx), len(idx), _ptr(out)))
+        for lo in range(0, len(idx), self.READ_CHUNK):
+            part, dst = idx[lo:lo + self.READ_CHUNK], out[lo:lo + self.READ_CHUNK]
+            self._check(self.lib.dmb_read_coeffs(self._h, state_ptr, _ptr(part), len(part), _ptr(dst)))
         return out
 
     def to_matrix(self, state_ptr, n_qubits, work_ptr, out_ptr):

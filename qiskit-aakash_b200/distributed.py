@@ -473,26 +473,24 @@ class ShardedPauliEngine(PauliEngine):
         self.ctx.download(self.alloc.ptr(out), host)
         return host
 
-    def read_coefficients(self, digit_tuples):
-        """Coefficients a[p_0..p_{n-1}] of a sharded state: the owning rank reads, one all-reduce
-        (Expect / Bell readouts, ``dm_simulator.py:569-570, 744-760``)."""
-        self._localise_all_pending()
-        mask = (1 << self.n_bits) - 1
-        local_idx, mine = [], []
-        for tup in digit_tuples:
-            g = 0
-            for q, p in enumerate(tup):
-                g |= int(p) << (2 * self.pos[q])
-            mine.append((g >> self.n_bits) == self.rank)
-            local_idx.append(g & mask)
+    def read_flat(self, flat_indices):
+        """Coefficients at flat indices of the current (global) slot layout: the owning rank reads,
+        one all-reduce (Expect / Bell readouts, ``dm_simulator.py:569-570, 744-760``; reduced states)."""
+        self.settle()
+        g = np.asarray(flat_indices, dtype=np.uint64)
+        mine = (g >> np.uint64(self.n_bits)) == np.uint64(self.rank)
+        local_idx = g & np.uint64((1 << self.n_bits) - 1)
         vals = self.ctx.read_coeffs(self.sptr, local_idx)
-        vals = np.where(np.array(mine), vals, 0.0)
+        vals = np.where(mine, vals, 0.0)
         t = self.alloc.empty(len(vals))
         self.ctx.upload(self.alloc.ptr(t), vals)
         self.comm.all_reduce_sum(t)
         out = np.empty(len(vals))
         self.ctx.download(self.alloc.ptr(t), out)
         return out
+
+    def settle(self):
+        self._localise_all_pending()
 
     def to_matrix(self):
         """``_compute_densitymatrix`` of a sharded state: result formatting for registers small

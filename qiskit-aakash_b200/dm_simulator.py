@@ -175,6 +175,9 @@ class DmSimulatorB200:
         self._depolarization_factor = d["depolarization_factor"]
         self._bell_depolarization_factor = d["bell_depolarization_factor"]
         opts = backend_options if backend_options is not None else {}
+        # extension (not in the reference): 'reduced_state': [qubits] adds the partial trace onto those
+        # qubits to the result data ('reduced_coeffmatrix', 'reduced_densitymatrix'); not sticky
+        self._reduced_state_qubits = opts.get("reduced_state")
 
         if "initial_densitymatrix" in opts:
             self._initial_densitymatrix = np.array(opts["initial_densitymatrix"], dtype=float) \
@@ -451,6 +454,9 @@ class DmSimulatorB200:
         t_dl0 = t_dl1 = t_levels
         if self.SHOW_FINAL_STATE:
             matrix = engine.to_matrix() if self._get_den_mat else None   # before the chop (:1261-1263)
+            if getattr(self, "_reduced_state_qubits", None) is not None:
+                data["reduced_coeffmatrix"] = engine.reduced_coefficients(self._reduced_state_qubits)
+                data["reduced_densitymatrix"] = engine.reduced_densitymatrix(self._reduced_state_qubits)
             engine.chop(self._chop_threshold)
             engine.sync()
             t_dl0 = time.time()

@@ -411,14 +411,60 @@ class PauliEngine:
 
     def read_coefficients(self, digit_tuples):
         """Coefficients a[p_0, ..., p_{n-1}] (tuple index = qubit) -> numpy array."""
-        self.flush()
+        self.settle()                                        # scheduling may relabel: settles self.pos
+        pos = self.pos
         idx = []
         for tup in digit_tuples:
             flat = 0
             for q, p in enumerate(tup):
-                flat |= int(p) << (2 * self.pos[q])
+                flat |= int(p) << (2 * pos[q])
             idx.append(flat)
-        return self.ctx.read_coeffs(self.sptr, idx)
+        return self.read_flat(idx)
+
+    def settle(self):
+        """Apply everything outstanding so that the buffer holds the state itself (layout ``self.pos``)."""
+        self.flush()
+
+    def read_flat(self, flat_indices):
+        """Coefficients at flat indices of the CURRENT layout (digit of qubit q at bits 2*pos[q])."""
+        self.settle()
+        return self.ctx.read_coeffs(self.sptr, flat_indices)
+
+    def reduced_coefficients(self, qubits):
+        """Pauli-coefficient vector (4^k real numbers, ``qubits[0]`` = most significant digit, trace
+        normalisation r[0] = 2^-k) of the reduced state Tr_{other qubits}(rho).  In the Pauli basis a
+        partial trace is a gather: every Pauli string with a non-identity letter on a traced-out
+        qubit is traceless, so r[P] = 2^(n-k) * a[P on `qubits`, I elsewhere].  Generalises the
+        reduced two-qubit matrix of ``_add_bell_basis_measure`` (``dm_simulator.py:744-747``) to any
+        subset of qubits; the state is not modified."""
+        qubits = [int(q) for q in qubits]
+        k = len(qubits)
+        if k < 1 or len(set(qubits)) != k or not all(0 <= q < self.n for q in qubits):
+            raise BasicAerError("reduced state: qubit list invalid: %r" % (qubits,))
+        if k > 12:
+            raise BasicAerError("reduced state on %d qubits is too large to gather" % k)
+        self.settle()                                        # scheduling may relabel: settles self.pos
+        j = np.arange(4 ** k, dtype=np.uint64)
+        flat = np.zeros(4 ** k, dtype=np.uint64)
+        for i, q in enumerate(qubits):                       # digit i of j (most significant first) -> qubit q
+            digit = (j >> np.uint64(2 * (k - 1 - i))) & np.uint64(3)
+            flat |= digit << np.uint64(2 * self.pos[q])
+        return self.read_flat(flat) * float(2 ** (self.n - k))
+
+    def reduced_densitymatrix(self, qubits):
+        """2^k x 2^k complex matrix of the reduced state (``qubits[0]`` = most significant bit of the
+        row / column index): ``reduced_coefficients`` + the Pauli->matrix kernels of
+        ``_compute_densitymatrix`` (``:1198-1255``) on the 4^k gathered coefficients."""
+        r = self.reduced_coefficients(qubits)
+        k = len(qubits)
+        src = self.alloc.empty(4 ** k)
+        self.ctx.upload(self.alloc.ptr(src), r)
+        work = self.alloc.empty(2 * 4 ** k)
+        out = self.alloc.empty(2 * 4 ** k)
+        self.ctx.to_matrix(self.alloc.ptr(src), k, self.alloc.ptr(work), self.alloc.ptr(out))
+        host = np.empty(2 * 4 ** k)
+        self.ctx.download(self.alloc.ptr(out), host)
+        return host.view(np.complex128).reshape(2 ** k, 2 ** k)
 
     def _require_reference_layout(self):
         """Bring every qubit q back to digit position n-1-q (SWAP ops in ordinary tile passes)."""

@@ -93,6 +93,8 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
     opts = dict(cases.FULL_NOISE, compute_densitymatrix=False)
     if mode == "matrix":
         opts["compute_densitymatrix"] = True
+    if mode == "reduced":
+        opts["reduced_state"] = [n - 1, 0, 2]            # one global, two local qubits
     if mode == "stored":
         # start from a stored state and compare against stored coefficients (a4, a27) on shards
         os.chdir(out_dir)
@@ -117,10 +119,17 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
     c2.instructions = copy.deepcopy(circ.instructions)
     res = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
     ref = dm_oracle.run_oracle(n, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
+    d_red = 0.0
+    if mode == "reduced":
+        import test_reduced_state as trs
+        full = dm_oracle.run_oracle(n, copy.deepcopy(circ.instructions), dict(copy.deepcopy(opts), compute_densitymatrix=True))
+        want = trs.numpy_partial_trace(np.asarray(full["data"]["densitymatrix"]), n, opts["reduced_state"])
+        d_red = max(float(np.max(np.abs(res["data"].pop("reduced_densitymatrix") - want))),
+                    float(np.max(np.abs(res["data"].pop("reduced_coeffmatrix") - trs.pauli_vector(want, 3)))))
     p_got = np.array(list(res["data"]["ensemble_probability"].values()))
     p_ref = np.array(list(ref["data"]["ensemble_probability"].values()))
     d_p = float(np.max(np.abs(p_got - p_ref)))
-    d_c = float(np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])))
+    d_c = max(d_red, float(np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"]))))
     assert set(res["data"]) == set(ref["data"]), (set(res["data"]), set(ref["data"]))
     for key, val in ref["data"].items():
         if key.startswith(("Pauli_string", "reduced_bell")):
@@ -141,7 +150,7 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
                                                (4, 7, 4, "layered"), (8, 7, 5, "rand"), (8, 7, 6, "layered"),
                                                (2, 5, 7, "expect"), (4, 6, 8, "bell"), (8, 7, 9, "expect"),
                                                (2, 5, 10, "stored"), (8, 7, 11, "stored"),
-                                               (4, 6, 15, "matrix"),
+                                               (4, 6, 15, "matrix"), (2, 5, 16, "reduced"), (8, 7, 17, "reduced"),
                                                (2, 5, 12, "nbasis"), (4, 6, 13, "nbasis"), (8, 7, 14, "nbasis")])
 def test_sharded_backend_matches_oracle(world, n, seed, mode, tmp_path):
     import torch.multiprocessing as mp
