@@ -261,7 +261,9 @@ def run_ours(args):
 
     # end to end through the public API (host buffers; D2H of the coefficient vector inside)
     e2e = None
-    if world == 1:
+    if world == 1 and args.no_e2e:
+        pass
+    elif world == 1:
         backend = BasicAer.get_backend("dm_simulator")
         run_opts = dict(opts, compute_densitymatrix=False)
         qobj = assemble(circuits.random_layered(n, depth, seed))    # the backend never mutates it
@@ -305,6 +307,9 @@ def run_ours(args):
                 "config": workload_config(n, depth, n_gates, {
                            "levels": runner.n_levels, "state_bytes": state_bytes,
                            "passes_per_step": counters["tile_pass_launches"] / args.steps,
+                           "scheduler": "dmb_schedule strategy %d (%s), <= %d ops per pass" % (
+                               runner.engine.strategy, "tile search" if runner.engine.strategy == 1 else "program order",
+                               runner.engine.max_ops_per_pass),
                            "l2": "state (%.1f GiB/GPU) >> 126 MB L2, no flush needed" % (state_bytes / world / 2 ** 30),
                            "parallelism": "1 GPU" if world == 1 else "%d GPUs, high-order Pauli digits sharded" % world}),
                 "circuit_ms": ms_step, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
