@@ -193,6 +193,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sched_desc = "dmb_schedule strategy %d (%s), <= %d ops per pass" % (
+        runner.engine.strategy, "tile search" if runner.engine.strategy == 1 else "program order",
+        runner.engine.max_ops_per_pass)
     for _ in range(args.warmup):
         runner.step()
     barrier()
@@ -307,9 +310,7 @@ def run_ours(args):
                 "config": workload_config(n, depth, n_gates, {
                            "levels": runner.n_levels, "state_bytes": state_bytes,
                            "passes_per_step": counters["tile_pass_launches"] / args.steps,
-                           "scheduler": "dmb_schedule strategy %d (%s), <= %d ops per pass" % (
-                               runner.engine.strategy, "tile search" if runner.engine.strategy == 1 else "program order",
-                               runner.engine.max_ops_per_pass),
+                           "scheduler": sched_desc,
                            "l2": "state (%.1f GiB/GPU) >> 126 MB L2, no flush needed" % (state_bytes / world / 2 ** 30),
                            "parallelism": "1 GPU" if world == 1 else "%d GPUs, high-order Pauli digits sharded" % world}),
                 "circuit_ms": ms_step, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
