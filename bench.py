@@ -255,12 +255,16 @@ def run_ours(args):
                                          "peak_source": "128 B/clk/SM x %d SMs x %.0f MHz (sampled)" % (sm_count, mhz)}
     except Exception:
         pass
-    prof = os.path.join(ROOT, "profiles", "r01_tile_pass_ncu_summary.json")
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+    # DRAM bytes per launch from the latest committed `ncu --set full` capture of this kernel
+    for name in ("r01b_tile_pass_ncu_summary.json", "r01_tile_pass_ncu_summary.json"):
+        prof = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(prof) and world == 1:
+            try:
+                roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+                roofline["traffic_source"] = "profiles/" + name
+                break
+            except Exception:
+                pass
 
     # end to end through the public API (host buffers; D2H of the coefficient vector inside)
     e2e = None
