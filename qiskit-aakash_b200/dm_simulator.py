@@ -165,6 +165,19 @@ class DmSimulatorB200:
         ``custom_densitymatrix`` / ``compute_densitymatrix`` / flags, the leaking rotation
         error default and the ineffective ``bell_depolarization_factor``."""
         d = self.DEFAULT_OPTIONS
+        # extension (SURVEY 8f item 3): 'reference_quirks': False switches the reference's accidental
+        # behaviours off -- options that stick to the backend instance between runs (custom_densitymatrix,
+        # compute_densitymatrix, merge / plot / partition / store / compare flags, rotation errors written
+        # into the shared default), the ignored bell_depolarization_factor (:240), every second measure of
+        # a mixed-basis level being skipped (:1100) and 'Bell ab' acting on qubits n-1-b, n-1-a (:721-777).
+        # Default True: number-for-number the reference.
+        self._quirks = bool((backend_options or {}).get("reference_quirks", True))
+        if not self._quirks:
+            self._custom_densitymatrix = None
+            self._get_den_mat = True
+            self.MERGE, self.PLOTTING, self.SHOW_PARTITION = True, False, False
+            self.STORE_LOCAL, self.COMPARE, self.FILE_EXIST = False, False, False
+            self._default_rotation_error = {k: list(v) for k, v in d["rotation_error"].items()}
         self._initial_densitymatrix = d["initial_densitymatrix"]
         self._chop_threshold = d["chop_threshold"]
         self._rotation_error = self._default_rotation_error
@@ -216,6 +229,8 @@ class DmSimulatorB200:
         if "bell_depolarization_factor" in opts:
             # (:240) lands in an attribute nobody reads: Bell measurements never depolarize
             self.bell_depolarization_factor = opts["bell_depolarization_factor"]
+            if not self._quirks:
+                self._bell_depolarization_factor = opts["bell_depolarization_factor"]
         if "chop_threshold" in opts:
             self._chop_threshold = opts["chop_threshold"]
         elif hasattr(qobj_config, "chop_threshold"):
@@ -356,6 +371,8 @@ class DmSimulatorB200:
         n = self._number_of_qubits
         q_1, q_2 = min(qubit_1, qubit_2), max(qubit_1, qubit_2)
         qi, qj = n - 1 - q_2, n - 1 - q_1            # axes 1 and 3 of the reference's view
+        if not getattr(self, "_quirks", True):
+            qi, qj = q_1, q_2                        # 'Bell ab' on qubits a and b
         tuples = []
         for i in range(4):
             for j in range(4):
@@ -557,7 +574,8 @@ class DmSimulatorB200:
                         data["reduced_bell_densitymatrix" + pair[0] + pair[1]] = reduced
                     else:
                         self._single_measure(engine, qubit, "Z")
-                    level.remove(op)    # (:1100) -> the next measure of this level is skipped
+                    if getattr(self, "_quirks", True):
+                        level.remove(op)    # (:1100) -> the next measure of this level is skipped
                     continue
                 # >= 2 measures of one common basis: partial measurement of all of them at once
                 qubits = [x.qubits[0] for x in level]

@@ -16,7 +16,8 @@ def _line(path):
 
 
 @pytest.mark.parametrize("fname,n_gpus", [("r01_bench_1gpu.json", 1), ("r01_bench_2gpu.json", 2),
-                                          ("r01_bench_4gpu.json", 4), ("r01_bench_8gpu.json", 8)])
+                                          ("r01_bench_4gpu.json", 4), ("r01_bench_8gpu.json", 8),
+                                          ("r01b_bench_1gpu.json", 1), ("r01b_bench_2gpu.json", 2)])
 def test_recorded_bench_lines_follow_the_contract(fname, n_gpus):
     d = _line(os.path.join(RAW, fname))
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
