@@ -181,6 +181,7 @@ class ShardedPauliEngine(PauliEngine):
         if bool(int(os.environ.get("DMB_FUSED_EXCHANGE", "1"))) and callable(getattr(comm, "peer_addresses", None)):
             self.peers = comm.peer_addresses(self.ctx, [self.alloc.ptr(self.state), self.alloc.ptr(self.scratch)])
         self._cur = 0                    # which of the two registered buffers is `state`
+        self._peers_may_read_scratch = False
         self.exchange_mode = os.environ.get("DMB_EXCHANGE", "pull")      # pull | push | nccl
         self.plain_exchange = bool(int(os.environ.get("DMB_EXCHANGE_PLAIN", "0")))   # op-free pull pass
         if self.exchange_mode == "nccl":
@@ -359,6 +360,7 @@ class ShardedPauliEngine(PauliEngine):
             if mode == "pull":
                 self.ctx.sync()
                 self.comm.barrier()          # every rank's old buffer is final
+                self._peers_may_read_scratch = False
                 old = self.peers[self._cur]
                 for d in range(1 << px.block_bits):
                     sr, sb = px.image(self.rank, d)
@@ -374,11 +376,22 @@ class ShardedPauliEngine(PauliEngine):
                 self.comm.barrier()          # all remote stores have landed
             self.passes_run += 1
             self._cur ^= 1
+            self._peers_may_read_scratch = mode == "pull"     # a slower peer may still be pulling from the old buffer
         else:
             self.comm.exchange(px, self.state, self.scratch)
         self.state, self.scratch = self.scratch, self.state
         self.exchanges += 1
         self.nvlink_bytes_sent += px.bytes_sent()
+
+    def _own_scratch(self):
+        """Call before writing the scratch shard outside an exchange.  After a fused pull the
+        scratch shard is the buffer the peers read their new layout from; a rank that finishes its
+        own pull first must not overwrite it until every rank has (a readout that uses the scratch
+        shard as workspace would otherwise corrupt a slower peer's state)."""
+        if self._peers_may_read_scratch:
+            self.ctx.sync()
+            self.comm.barrier()
+            self._peers_may_read_scratch = False
 
     def flush(self):
         saved = list(self.pos)
@@ -426,6 +439,7 @@ class ShardedPauliEngine(PauliEngine):
         n, n_loc = self.n, self.n_loc
         unit = np.asarray(nvec, dtype=float)
         owner = {self.pos[q]: q for q in range(n)}
+        self._own_scratch()
         src = self.sptr
         base = self.alloc.ptr(self.scratch)
         offset, count = 0, self.size
@@ -564,6 +578,7 @@ class ShardedPauliEngine(PauliEngine):
         other_vec = np.ascontiguousarray(other_vec, dtype=np.float64).reshape(-1)
         if other_vec.size != 4 ** self.n:
             raise BasicAerError("stored coefficients have the wrong length")
+        self._own_scratch()
         self.ctx.upload(self.alloc.ptr(self.scratch), self._to_current_layout(other_vec))
         part = self.ctx.dot(self.alloc.ptr(self.scratch), self.sptr, self.size)
         t = self.alloc.empty(1)
