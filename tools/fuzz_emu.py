@@ -120,8 +120,38 @@ def as_arr(v):
     return np.asarray(v, dtype=complex)
 
 
-def one(seed, max_n, min_n=1, max_ops=60):
+KNOBS = ("DMB_MAX_OPS_PER_PASS", "DMB_SCHED_STRATEGY", "DMB_RESERVE_LOW", "DMB_DRAIN_TAIL", "DMB_DRAIN_CHUNK",
+         "DMB_RELABEL", "DMB_FOLD_SWAPS", "DMB_DRAIN_THRESHOLD")
+
+
+def random_knobs(rng):
+    """Scheduler / streaming knobs the engine reads from the environment (engine.PauliEngine.__init__)."""
+    for k in KNOBS:
+        os.environ.pop(k, None)
+    env = {}
+    if rng.random() < 0.7:
+        env["DMB_MAX_OPS_PER_PASS"] = int(rng.integers(1, 17))
+    if rng.random() < 0.5:
+        env["DMB_SCHED_STRATEGY"] = int(rng.integers(0, 2))
+    if rng.random() < 0.3:
+        env["DMB_RESERVE_LOW"] = int(rng.integers(0, 3))
+    if rng.random() < 0.7:
+        env["DMB_DRAIN_TAIL"] = int(rng.integers(1, 12))
+        env["DMB_DRAIN_CHUNK"] = int(rng.integers(1, 8))
+    if rng.random() < 0.2:
+        env["DMB_RELABEL"] = 0
+        env["DMB_DRAIN_THRESHOLD"] = int(rng.integers(1, 10))
+    if rng.random() < 0.3:
+        env["DMB_FOLD_SWAPS"] = 0
+    for k, v in env.items():
+        os.environ[k] = str(v)
+    return env
+
+
+def one(seed, max_n, min_n=1, max_ops=60, knobs=False):
     rng = np.random.default_rng(seed)
+    if knobs:
+        env = random_knobs(np.random.default_rng(seed + 77777))
     n = int(rng.integers(min_n, max_n + 1))
     circ = random_circuit(rng, n, max_ops)
     opts = random_options(rng)
@@ -155,7 +185,7 @@ def one(seed, max_n, min_n=1, max_ops=60):
         if a.size:
             worst = max(worst, float(np.max(np.abs(a - b))))
     if worst > 1e-10:
-        return "FAIL", "max|d| = %.3e" % worst
+        return "FAIL", "n=%d max|d| = %.3e %s" % (n, worst, env if knobs else "")
     return "ok", "%.1e" % worst
 
 
@@ -166,11 +196,12 @@ def main():
     ap.add_argument("--max-n", type=int, default=8)
     ap.add_argument("--min-n", type=int, default=1)
     ap.add_argument("--max-ops", type=int, default=60)
+    ap.add_argument("--knobs", action="store_true", help="randomise the scheduler / streaming knobs too")
     a = ap.parse_args()
     counts = {}
     for seed in range(a.start, a.start + a.seeds):
         try:
-            st, msg = one(seed, a.max_n, a.min_n, a.max_ops)
+            st, msg = one(seed, a.max_n, a.min_n, a.max_ops, a.knobs)
         except Exception:  # noqa: BLE001
             st, msg = "FAIL", traceback.format_exc()
         counts[st] = counts.get(st, 0) + 1
