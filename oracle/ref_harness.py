@@ -122,8 +122,13 @@ def to_reference_instructions(instrs):
             for p in d["params"]:
                 if isinstance(p, str):
                     ps.append(sympy.Symbol(p))
-                elif isinstance(p, (list, tuple)) and len(p) == 2 and isinstance(p[0], str):
-                    ps.append([sympy.Symbol(p[0]), np.array(p[1], dtype=float)])
+                elif isinstance(p, (list, tuple, np.ndarray)) and len(p) == 2 and isinstance(p[0], str):
+                    # Ensemble + 'N': the only form the real front-end lets through is an object
+                    # ndarray ['N', direction] (circuit/instruction.py:142-143 accepts ndarrays,
+                    # rejects lists); dm_simulator.py:1130 then compares its element 0 with 'N'
+                    arr = np.empty(2, dtype=object)
+                    arr[0], arr[1] = str(p[0]), np.array(p[1], dtype=float)
+                    ps.append(arr)
                 elif isinstance(p, (list, tuple, np.ndarray)):
                     ps.append(np.array(p, dtype=float))
                 else:

@@ -144,6 +144,18 @@ def _cases():
     c = C.Circuit(4); c.instructions = list(_rand_circuit(4, 20, 41).instructions)
     c.measure(0, 0, basis="N", add_param=[0.0, 0.6, 0.8]); c.measure(2, 2, basis="N", add_param=[0.0, 0.6, 0.8])
     add("measure_partial_N", c, {"depolarization_factor": 0.95})
+    # Ensemble readout along a direction: the only form the reference's front-end lets through and its
+    # dispatcher accepts is an object ndarray ['N', direction] (circuit/instruction.py:142-143,
+    # dm_simulator.py:1130-1132)
+    c = C.Circuit(4); c.instructions = list(_rand_circuit(4, 20, 41).instructions)
+    c.barrier()
+    for q in range(4):
+        prm = np.empty(2, dtype=object)
+        prm[0], prm[1] = "N", np.array([1.0, -2.0, 0.5])
+        c.instructions.append(C.instr("measure", [q], ["Ensemble", prm], memory=[q]))
+    c.barrier()
+    c.u3(0.3, 0.1, 0.2, 1)
+    add("measure_ensemble_N", c, dict(FULL_NOISE))
     # mixed bases in one level: every second measure is skipped (dm_simulator.py:1100)
     c = C.Circuit(4); c.instructions = list(_rand_circuit(4, 20, 42).instructions)
     c.measure(0, 0, basis="X"); c.measure(1, 1, basis="Y"); c.measure(2, 2, basis="Z"); c.measure(3, 3, basis="X")

@@ -3,6 +3,8 @@ reference's own README / notebooks, against the committed golden fixtures genera
 unmodified reference, against the scheduler known answers of SURVEY.md appendix A, and --
 where /root/reference exists -- against the live reference on fresh random circuits."""
 import copy
+import os
+import sys
 import math
 
 import numpy as np
@@ -154,3 +156,15 @@ def test_oracle_matches_live_reference(seed, case_dir):
         w = got["data"][k]
         b = np.array(list(w.values())) if isinstance(w, dict) else np.asarray(w)
         assert np.max(np.abs(a - b)) <= 1e-14
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_matches_live_reference_on_random_programs():
+    """tools/fuzz_oracle.py: random circuits with every measurement mode (incl. Ensemble along a
+    direction), resets, barriers and random option sets; 3400 seeds agreed to 1e-13 when this
+    slice was committed."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_oracle.py"), "--seeds", "120", "--start", "50000"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0 and "'ok': 120" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
