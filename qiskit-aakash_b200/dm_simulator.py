@@ -26,6 +26,7 @@ import numpy as np
 
 from . import engine as eng
 from . import hostpass
+from . import unitary
 from .exceptions import BasicAerError
 
 logger = logging.getLogger(__name__)
@@ -449,7 +450,12 @@ class DmSimulatorB200:
         self._initialize_densitymatrix(engine)
         self._initialize_errors()
         t_pre2 = time.time()
-        ops = hostpass.merge_single_qubit_gates(experiment.instructions, n, self.MERGE)
+        instructions = experiment.instructions
+        if not getattr(self, "_quirks", True):
+            # 'unitary' is advertised in basis_gates but rejected by the reference's merge pass; without
+            # the quirks it is unrolled the way UnitaryGate._define would (unitary.py)
+            instructions = unitary.expand_unitaries(instructions)
+        ops = hostpass.merge_single_qubit_gates(instructions, n, self.MERGE)
         levels, n_levels = hostpass.partition_levels(ops, n)
         if self.SHOW_PARTITION:
             self._describe_partition(levels)
