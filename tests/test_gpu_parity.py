@@ -232,3 +232,26 @@ def test_relabelling_store_is_an_exact_digit_permutation_on_cuda(backend):
     folded, total = store_cases.check_relabelling_store(lambda n: engine.PauliEngine(n), n=9,
                                                         tile_digits=(0, 1, 2, 5, 7, 8))
     assert folded == total
+
+
+def test_random_programs_vs_oracle_on_cuda(backend):
+    """tools/fuzz_emu.py's generator (every measurement mode, resets, barriers, random option sets and
+    initial states) on the real kernels: 160 programs with n <= 8, 12 long ones at n = 8..10, and 40
+    with randomised scheduler / streaming knobs."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_emu
+    bad = []
+    plan = [(s, 8, 1, 60, False) for s in range(100000, 100160)] + \
+           [(s, 10, 8, 250, False) for s in range(101000, 101012)] + \
+           [(s, 9, 2, 150, True) for s in range(102000, 102040)]
+    try:
+        for seed, max_n, min_n, max_ops, knobs in plan:
+            status, msg = fuzz_emu.one(seed, max_n, min_n, max_ops, knobs, backend=backend)
+            if status == "FAIL":
+                bad.append((seed, msg))
+    finally:
+        for k in fuzz_emu.KNOBS:
+            os.environ.pop(k, None)
+    assert not bad, bad[:5]

@@ -148,7 +148,8 @@ def random_knobs(rng):
     return env
 
 
-def one(seed, max_n, min_n=1, max_ops=60, knobs=False):
+def one(seed, max_n, min_n=1, max_ops=60, knobs=False, backend=None):
+    """``backend``: factory of the backend under test (default: emulated kernels; the -m gpu tests pass the real one)."""
     rng = np.random.default_rng(seed)
     if knobs:
         env = random_knobs(np.random.default_rng(seed + 77777))
@@ -164,7 +165,7 @@ def one(seed, max_n, min_n=1, max_ops=60, knobs=False):
     except Exception as e:  # noqa: BLE001
         ref_exc = e
     try:
-        got = emu_backend().run(assemble(circ), backend_options=copy.deepcopy(opts)).result()["results"][0]
+        got = (backend or emu_backend)().run(assemble(circ), backend_options=copy.deepcopy(opts)).result()["results"][0]
     except Exception as e:  # noqa: BLE001
         got_exc = e
     if ref_exc or got_exc:
