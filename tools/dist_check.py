@@ -65,7 +65,46 @@ def main():
                               "d_coeff": d_c, "exchanges": engines[0].exchanges, "fused_exchange": engines[0].peers is not None,
                               "nvlink_bytes_sent_per_rank": engines[0].nvlink_bytes_sent}))
         dist.barrier()
+    # random programs (tools/fuzz_emu.py's generator: every measurement mode mid-circuit, resets, random
+    # options) -- includes the pattern that exposed the scratch-shard race after a fused pull (a readout
+    # that uses the scratch shard as workspace right after an exchange)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import contextlib
+    import io
+    import fuzz_emu
+    lo = {2: 3, 4: 4, 8: 6}.get(world, 6)
+    n_fuzz, bad = int(os.environ.get("DIST_CHECK_FUZZ", "40")), []
+    for seed in range(n_fuzz):
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(lo, 10))
+        circ = fuzz_emu.random_circuit(rng, n, 80)
+        if seed % 4 == 0:                       # the minimal trigger: global cx, then an N-basis partial readout
+            circ = C.Circuit(n)
+            circ.cx(0, 1)
+            circ.measure([1, n - 1], [1, n - 1], basis="N", add_param=np.array([0.67, -0.43, -0.57]))
+            circ.cx(1, 0)
+            circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="Y")
+        opts = fuzz_emu.random_options(rng)
+        fuzz_emu.random_init(rng, n, opts)
+        be = DmSimulatorB200(_engine_factory=lambda nq: distributed.ShardedPauliEngine(nq, comm, device=local))
+        c2 = C.Circuit(n)
+        c2.instructions = copy.deepcopy(circ.instructions)
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
+            ref = dm_oracle.run_oracle(n, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
+        d = 0.0
+        for k, v in ref["data"].items():
+            d = max(d, float(np.max(np.abs(fuzz_emu.as_arr(v) - fuzz_emu.as_arr(res["data"][k])))))
+        if set(ref["data"]) != set(res["data"]) or d > 1e-10:
+            bad.append((seed, n, d))
+        worst = max(worst, d)
+        dist.barrier()
+    flag = torch.tensor([len(bad)], device="cuda")
+    dist.all_reduce(flag)
     if rank == 0:
+        print(json.dumps({"check": "random_programs", "world": world, "programs": n_fuzz, "failed_on_any_rank": int(flag.item()),
+                          "bad_rank0": bad[:5]}))
+        assert int(flag.item()) == 0
         assert worst <= 1e-10, worst
         print("DIST_CHECK_OK world=%d worst=%.3e" % (world, worst))
     dist.destroy_process_group()
