@@ -457,9 +457,15 @@ int dmb_create(int device, dmb_ctx** out) {
   ctx->tile_variant = 0;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->scratch_elems = kScratchElems;
-  CU_TRY(cudaMalloc(&ctx->d_scratch, kScratchElems * sizeof(double)));
-  CU_TRY(cudaMalloc(&ctx->d_idx, kScratchElems * sizeof(uint64_t)));
-  CU_TRY(cudaMallocHost(&ctx->h_scratch, kScratchElems * sizeof(double)));
+  cudaError_t e = cudaMalloc(&ctx->d_scratch, kScratchElems * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_idx, kScratchElems * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_scratch, kScratchElems * sizeof(double));
+  if (e != cudaSuccess) {                  // do not leak a half-built context
+    cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_idx);
+    delete ctx;
+    return fail("dmb_create: scratch allocation", cudaGetErrorString(e));
+  }
   *out = ctx;
   return 0;
 }
@@ -544,7 +550,7 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
       n_run = dmb_expand_post_swaps(passes[i], expanded);
       run = expanded;
     }
-   for (int r = 0; r < n_run; ++r) {
+    for (int r = 0; r < n_run; ++r) {
     const dmb_pass& P = run[r];
     int rc = 0;
     switch (P.n_tile_digits) {
@@ -562,7 +568,7 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
     ctx->stats.tile_pass_launches++;
     ctx->stats.fused_ops += (uint64_t)P.n_ops;
     ctx->stats.state_bytes_moved += 16ull << n_bits;
-   }
+    }
   }
   return 0;
 }
