@@ -178,6 +178,47 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
 }
 
 // ---------------------------------------------------------------------------------------
+// tile pass, K = 6, HALF-CTA variant (dmb_set_tile_variant 8 / 9): 128 threads per tile, every
+// thread plays the two virtual threads t and t + 128 of k_tile_pass6 one after the other, one
+// 32 KiB stage per CTA and CTAS = 6 (5) CTAs per SM.  Same warps per SM (24) and registers as the
+// default, but six independent barrier domains of four warps instead of three of eight: more
+// phase mixing between CTAs on the shared-memory / FP64 pipes and cheaper barriers; the HBM
+// latency of a CTA's own tile load is hidden by the other CTAs instead of a prefetch stage.
+// ---------------------------------------------------------------------------------------
+#define DMB_HALF_THREADS 128
+template <int CTAS, int STMODE>
+__global__ void __launch_bounds__(DMB_HALF_THREADS, CTAS)
+k_tile_pass6_half(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L) {
+  extern __shared__ __align__(128) unsigned char lean_smem[];
+  dmb_smem_mem mem;
+  mem.base = (uint32_t)__cvta_generic_to_shared(lean_smem);
+  dmb_lean_thread T0, T1;
+  dmb_lean_thread_init(threadIdx.x, L, T0);
+  dmb_lean_thread_init(threadIdx.x + DMB_HALF_THREADS, L, T1);
+  dmb_remote_src none;
+  none.enabled = 0;
+  for (uint64_t tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x) {
+    const uint64_t tb = dmb_tile_base(tile, L.td, DMB_LEAN_K);
+#pragma unroll
+    for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
+      cp_async16s(mem.base + (T0.soff ^ L.pair_soff[i]), state + tb + (T0.goff | L.pair_goff[i]));
+      cp_async16s(mem.base + (T1.soff ^ L.pair_soff[i]), state + tb + (T1.goff | L.pair_goff[i]));
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int i = 0; i < L.n_ops; ++i) {
+      dmb_lean_op_dispatch(T0, L.ops[i], mem);
+      dmb_lean_op_dispatch(T1, L.ops[i], mem);
+      __syncthreads();
+    }
+    dmb_lean_store_thread<false, STMODE>(T0, L, state, tb, none, mem);
+    dmb_lean_store_thread<false, STMODE>(T1, L, state, tb, none, mem);
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // tile pass, K = 6, three digits per thread (R3): 64 threads per tile, each phase keeps a
 // digit triple's 64 coefficients in registers and runs all ops inside the triple back to
 // back -- roughly half the shared-memory traffic per fused op of k_tile_pass6.
@@ -351,6 +392,28 @@ static int launch_lean(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, cons
   return 0;
 }
 
+template <int CTAS, int STMODE>
+static int launch_half(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
+  const size_t smem = DMB_LEAN_TILE_BYTES;
+  static std::atomic<uint64_t> attr_done{0};
+  if (!((attr_done.load() >> (ctx->device & 63)) & 1ull)) {
+    CU_TRY(cudaFuncSetAttribute(k_tile_pass6_half<CTAS, STMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done.fetch_or(1ull << (ctx->device & 63));
+  }
+  uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
+  if (grid > L.n_tiles) grid = L.n_tiles;
+  k_tile_pass6_half<CTAS, STMODE><<<(unsigned)grid, DMB_HALF_THREADS, smem, ctx->stream>>>(state, L);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+template <int CTAS>
+static int launch_half_any(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
+  if (L.st_mode == DMB_ST_PERM128) return launch_half<CTAS, DMB_ST_PERM128>(ctx, state, L);
+  if (L.st_mode == DMB_ST_SPLIT64) return launch_half<CTAS, DMB_ST_SPLIT64>(ctx, state, L);
+  return launch_half<CTAS, DMB_ST_PLAIN>(ctx, state, L);
+}
+
 template <int STAGES, int CTAS>
 static int launch_r3(dmb_ctx* ctx, double* state, const dmb_r3_pass& R) {
   const size_t smem = (size_t)STAGES * DMB_LEAN_TILE_BYTES;
@@ -375,7 +438,7 @@ static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_
     }
   }
   static thread_local dmb_lean_pass L;    // 6.5 KB: keep it off the stack; one host thread drives a ctx
-  const bool fold = ctx->tile_variant == 0 && dmb_fold_swaps_enabled();
+  const bool fold = (ctx->tile_variant == 0 || ctx->tile_variant >= 8) && dmb_fold_swaps_enabled();
   dmb_make_lean_pass(P, n_bits, L, fold);
   ctx->stats.folded_swaps += (uint64_t)(P.n_ops - L.n_ops);
   switch (ctx->tile_variant) {
@@ -383,6 +446,8 @@ static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_
     case 3: return launch_lean<2, 2, 0>(ctx, state, L);
     case 6: return launch_lean<1, 4, 0>(ctx, state, L);
     case 7: return launch_lean<1, 5, 0>(ctx, state, L);
+    case 8: return launch_half_any<6>(ctx, state, L);
+    case 9: return launch_half_any<5>(ctx, state, L);
     default:
       if (L.st_mode == DMB_ST_PERM128) return launch_lean<2, 3, 0, DMB_ST_PERM128>(ctx, state, L);
       if (L.st_mode == DMB_ST_SPLIT64) return launch_lean<2, 3, 0, DMB_ST_SPLIT64>(ctx, state, L);
@@ -506,7 +571,7 @@ int dmb_reset_stats(dmb_ctx* ctx) {
 
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant) {
   if (!ctx) return fail("dmb_set_tile_variant", "null context");
-  if (variant < 0 || variant > 7) return fail("dmb_set_tile_variant", "variant must be 0..7");
+  if (variant < 0 || variant > 9) return fail("dmb_set_tile_variant", "variant must be 0..9");
   ctx->tile_variant = variant;
   return 0;
 }

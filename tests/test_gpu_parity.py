@@ -255,3 +255,30 @@ def test_random_programs_vs_oracle_on_cuda(backend):
         for k in fuzz_emu.KNOBS:
             os.environ.pop(k, None)
     assert not bad, bad[:5]
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("DMB_TEST_TILE_VARIANT"),
+                    reason="experimental tile-kernel variants are checked on request (tools/gpu_half_variants.sh)")
+def test_experimental_tile_variant_parity(backend, golden, case_dir, monkeypatch):
+    """Parity of an opt-in tile-kernel variant (DMB_TEST_TILE_VARIANT=8|9: half-CTA kernel) before it is
+    timed: the golden cases that reach the K = 6 kernel, 60 random programs with n >= 6, and the n = 14
+    round trip.  Not part of the default run: the default kernel is what the other tests cover."""
+    import os
+    import sys
+    monkeypatch.setenv("DMB_TILE_VARIANT", os.environ["DMB_TEST_TILE_VARIANT"])
+    try:
+        for name in cases.CASES:
+            case = cases.get(name)
+            if case["n"] >= 6:
+                cases.write_files(case, ".")
+                check_against_golden(golden, name, _run(backend, case["n"], case["instrs"], case["options"], name))
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+        import fuzz_emu
+        bad = [(s, m) for s in range(103000, 103060) for st, m in [fuzz_emu.one(s, 10, 6, 200, False, backend=backend)]
+               if st == "FAIL"]
+        assert not bad, bad[:5]
+        test_n14_unitary_round_trip(backend)
+    finally:
+        from qiskit_aakash_b200 import engine
+        for ctx in engine._CONTEXTS.values():          # contexts are shared: put the default kernel back
+            ctx.set_tile_variant(0)
