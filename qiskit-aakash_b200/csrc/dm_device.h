@@ -290,7 +290,7 @@ DMB_HD void dmb_tile_op_thread(int t, const dmb_op& op, double* smem, int K) {
 #define DMB_LEAN_TILE_BYTES (DMB_LEAN_TILE * 8u)        // 32 KiB
 #define DMB_LEAN_PAIRS 8                                 // 16-byte pairs per thread per tile
 enum { DMB_MODE_A = 0, DMB_MODE_PAIR_A = 1, DMB_MODE_PAIR_B = 2 };
-enum { DMB_PA_COL0 = 4, DMB_PB_COL0 = 8, DMB_TSP_ZERO_MEAN = 16 };   // extra flag bits (library-internal)
+enum { DMB_PA_COL0 = 4, DMB_PB_COL0 = 8, DMB_TSP_ZERO_MEAN = 16, DMB_PAIRABLE = 32 };   // extra flag bits (library-internal)
 
 struct alignas(16) dmb_lean_op {
   uint32_t sa[4];      // swizzled BYTE offset of digit-a value i
@@ -450,6 +450,8 @@ inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, 
     const int ma = !(q.flags & DMB_HAS_PA) ? 0 : ((q.flags & DMB_PA_COL0) ? 2 : 1);
     const int mb = !(q.flags & DMB_HAS_PB) ? 0 : ((q.flags & DMB_PB_COL0) ? 2 : 1);
     q.variant = dmb_variant_is_specialised(kx, ma, mb) ? dmb_variant_id(kx, ma, mb, q.mode) : -1;
+    // thread digit 0 sits on tile digit 0: virtual threads 2u and 2u+1 own the two halves of every 16-byte pair
+    if (q.mode == DMB_MODE_A && o.fd[0] == 0) q.flags |= DMB_PAIRABLE;
   }
 }
 
@@ -585,6 +587,64 @@ DMB_HD void dmb_lean_op_thread(const dmb_lean_thread& T, const dmb_lean_op& op, 
   }
 }
 
+// arithmetic of a compile-time specialised op on one 16-block (same statements as in dmb_lean_op_spec)
+template <int KINDX, int MA, int MB>
+DMB_HD void dmb_spec_math(const dmb_lean_op& op, double (&v)[4][4]) {
+  if constexpr (MA == 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dmb_mat3_nocol0(op.pa, v[1][j], v[2][j], v[3][j]);
+  } else if constexpr (MA == 2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dmb_mat3(op.pa, v[0][j], v[1][j], v[2][j], v[3][j]);
+  }
+  if constexpr (MB == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dmb_mat3_nocol0(op.pb, v[i][1], v[i][2], v[i][3]);
+  } else if constexpr (MB == 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dmb_mat3(op.pb, v[i][0], v[i][1], v[i][2], v[i][3]);
+  }
+  if constexpr (KINDX == DMB_OP_CX) dmb_cx_ideal(v);
+  else if constexpr (KINDX == DMB_KIND_TSP0) dmb_cx_tsp0(v, op.coef[0], op.coef[2], op.coef[3]);
+  else if constexpr (KINDX == DMB_OP_CX_TSP) dmb_cx_tsp(v, op.coef[0], op.coef[1], op.coef[2], op.coef[3], op.coef[4]);
+  else if constexpr (KINDX == DMB_OP_SWAP) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = i + 1; j < 4; ++j) { const double tmp = v[i][j]; v[i][j] = v[j][i]; v[j][i] = tmp; }
+  }
+}
+
+// PAIRED op body (tile variants 10/11): one real thread plays the virtual threads 2u and 2u+1 of an op in
+// access mode A (tile digit 0 free).  Their 16-blocks differ only in the low bit of digit 0, i.e. they are
+// the two halves of the same sixteen 16-byte pairs: 16 LDS.128 + 16 STS.128 move both blocks (instead of
+// 2 x 16 LDS.64 + 2 x 16 STS.64), with one address computation per pair.  T is the EVEN virtual thread.
+// Bank conflicts: a quarter-warp of real lanes is a half-warp of virtual lanes, whose 16 8-byte slots are 8
+// distinct 16-byte chunks (tests/test_host_logic.py::test_lane_order_is_bank_conflict_free).
+template <int KINDX, int MA, int MB, class Mem>
+DMB_HD void dmb_lean_op_pair(const dmb_lean_thread& T, const dmb_lean_op& op, const Mem& mem) {
+  const uint32_t bl = (T.tq[0] << op.sh[0]) | (T.tq[1] << op.sh[1]) | (T.tq[2] << op.sh[2]) | (T.tq[3] << op.sh[3]);
+  const uint32_t sb = dmb_swz(bl) << 3;
+  double v0[4][4], v1[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const dmb_d2 p = mem.ld128(sb ^ op.sa[i] ^ op.sj[j]);
+      v0[i][j] = p.x; v1[i][j] = p.y;
+    }
+  dmb_spec_math<KINDX, MA, MB>(op, v0);
+  dmb_spec_math<KINDX, MA, MB>(op, v1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dmb_d2 p;
+      p.x = v0[i][j]; p.y = v1[i][j];
+      mem.st128(sb ^ op.sa[i] ^ op.sj[j], p);
+    }
+}
+
 // Compile-time specialised op body: KINDX in {MATS, CX, CX_TSP, SWAP, DMB_KIND_TSP0},
 // MA/MB: 0 = no map, 1 = map without column 0, 2 = full map; MODE as in dmb_lean_op.mode.
 template <int KINDX, int MA, int MB, int MODE, class Mem>
@@ -682,6 +742,41 @@ DMB_HD void dmb_lean_op_dispatch(const dmb_lean_thread& T, const dmb_lean_op& op
     DMB_SPEC_MODES(DMB_OP_SWAP, 0, 0)
     default: dmb_lean_op_thread(T, op, mem); break;
   }
+}
+
+#define DMB_PAIR_CASE(K, A, B) \
+  case ((K * 3 + A) * 3 + B) * 3 + 0: dmb_lean_op_pair<K, A, B>(P0, op, mem); return;
+
+// Dispatch for a real thread u of the paired kernel.  Ops in access mode A run the paired body as virtual
+// threads 2u / 2u + 1 (P0 = thread struct of 2u); every other op runs the ordinary body twice, as virtual
+// threads u and u + 128 (S0, S1), so that consecutive lanes stay consecutive virtual threads -- the
+// arrangement the bank-conflict analysis of the 128-bit modes was made for.  Either way all 256 virtual
+// threads of the tile run exactly once per op.
+template <class Mem>
+DMB_HD void dmb_lean_op_dispatch_pair(const dmb_lean_thread& P0, const dmb_lean_thread& S0, const dmb_lean_thread& S1,
+                                      const dmb_lean_op& op, const Mem& mem) {
+  if (op.flags & DMB_PAIRABLE) {
+    switch (op.variant) {
+      DMB_PAIR_CASE(DMB_OP_MATS, 1, 1)
+      DMB_PAIR_CASE(DMB_OP_MATS, 2, 2)
+      DMB_PAIR_CASE(DMB_OP_CX, 1, 1)
+      DMB_PAIR_CASE(DMB_OP_CX, 2, 2)
+      DMB_PAIR_CASE(DMB_OP_CX, 0, 0)
+      DMB_PAIR_CASE(DMB_OP_CX_TSP, 1, 1)
+      DMB_PAIR_CASE(DMB_OP_CX_TSP, 2, 2)
+      DMB_PAIR_CASE(DMB_KIND_TSP0, 1, 1)
+      DMB_PAIR_CASE(DMB_KIND_TSP0, 2, 2)
+      DMB_PAIR_CASE(DMB_OP_SWAP, 0, 0)
+      default: break;
+    }
+  }
+  dmb_lean_op_dispatch(S0, op, mem);
+  dmb_lean_op_dispatch(S1, op, mem);
+}
+
+// true when dmb_lean_op_dispatch_pair takes the paired body for this op
+DMB_HD bool dmb_lean_op_is_paired(const dmb_lean_op& op) {
+  return (op.flags & DMB_PAIRABLE) && op.variant >= 0 && (op.variant % 3) == 0;
 }
 
 // load / store of one tile (the CUDA kernel replaces the load by cp.async.cg of the same

@@ -186,34 +186,46 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
 // latency of a CTA's own tile load is hidden by the other CTAs instead of a prefetch stage.
 // ---------------------------------------------------------------------------------------
 #define DMB_HALF_THREADS 128
-template <int CTAS, int STMODE>
+// PAIRED (variants 10 / 11): the two virtual threads are 2u and 2u + 1 instead of u and u + 128, and ops in
+// access mode A run the paired body (dmb_lean_op_pair: 128-bit shared-memory accesses for both blocks).
+template <int CTAS, int STMODE, bool PAIRED>
 __global__ void __launch_bounds__(DMB_HALF_THREADS, CTAS)
 k_tile_pass6_half(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L) {
   extern __shared__ __align__(128) unsigned char lean_smem[];
   dmb_smem_mem mem;
   mem.base = (uint32_t)__cvta_generic_to_shared(lean_smem);
-  dmb_lean_thread T0, T1;
-  dmb_lean_thread_init(threadIdx.x, L, T0);
-  dmb_lean_thread_init(threadIdx.x + DMB_HALF_THREADS, L, T1);
+  // staging (tile load / write-back) always walks the tile as virtual threads u and u + 128: consecutive
+  // lanes touch consecutive 16-byte chunks (conflict-free, whole 128-byte lines per quarter-warp)
+  dmb_lean_thread S0, S1;
+  dmb_lean_thread_init(threadIdx.x, L, S0);
+  dmb_lean_thread_init(threadIdx.x + DMB_HALF_THREADS, L, S1);
+  // op phase: the same two virtual threads; PAIRED: mode-A ops run as virtual threads 2u / 2u + 1 instead
+  // (dmb_lean_op_dispatch_pair) -- only P0's index digits are used
+  dmb_lean_thread P0;
+  dmb_lean_thread_init(2 * threadIdx.x, L, P0);
   dmb_remote_src none;
   none.enabled = 0;
   for (uint64_t tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x) {
     const uint64_t tb = dmb_tile_base(tile, L.td, DMB_LEAN_K);
 #pragma unroll
     for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
-      cp_async16s(mem.base + (T0.soff ^ L.pair_soff[i]), state + tb + (T0.goff | L.pair_goff[i]));
-      cp_async16s(mem.base + (T1.soff ^ L.pair_soff[i]), state + tb + (T1.goff | L.pair_goff[i]));
+      cp_async16s(mem.base + (S0.soff ^ L.pair_soff[i]), state + tb + (S0.goff | L.pair_goff[i]));
+      cp_async16s(mem.base + (S1.soff ^ L.pair_soff[i]), state + tb + (S1.goff | L.pair_goff[i]));
     }
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
     for (int i = 0; i < L.n_ops; ++i) {
-      dmb_lean_op_dispatch(T0, L.ops[i], mem);
-      dmb_lean_op_dispatch(T1, L.ops[i], mem);
+      if constexpr (PAIRED) {
+        dmb_lean_op_dispatch_pair(P0, S0, S1, L.ops[i], mem);
+      } else {
+        dmb_lean_op_dispatch(S0, L.ops[i], mem);
+        dmb_lean_op_dispatch(S1, L.ops[i], mem);
+      }
       __syncthreads();
     }
-    dmb_lean_store_thread<false, STMODE>(T0, L, state, tb, none, mem);
-    dmb_lean_store_thread<false, STMODE>(T1, L, state, tb, none, mem);
+    dmb_lean_store_thread<false, STMODE>(S0, L, state, tb, none, mem);
+    dmb_lean_store_thread<false, STMODE>(S1, L, state, tb, none, mem);
     __syncthreads();
   }
 }
@@ -392,26 +404,26 @@ static int launch_lean(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, cons
   return 0;
 }
 
-template <int CTAS, int STMODE>
+template <int CTAS, int STMODE, bool PAIRED>
 static int launch_half(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
   const size_t smem = DMB_LEAN_TILE_BYTES;
   static std::atomic<uint64_t> attr_done{0};
   if (!((attr_done.load() >> (ctx->device & 63)) & 1ull)) {
-    CU_TRY(cudaFuncSetAttribute(k_tile_pass6_half<CTAS, STMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_tile_pass6_half<CTAS, STMODE, PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done.fetch_or(1ull << (ctx->device & 63));
   }
   uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
   if (grid > L.n_tiles) grid = L.n_tiles;
-  k_tile_pass6_half<CTAS, STMODE><<<(unsigned)grid, DMB_HALF_THREADS, smem, ctx->stream>>>(state, L);
+  k_tile_pass6_half<CTAS, STMODE, PAIRED><<<(unsigned)grid, DMB_HALF_THREADS, smem, ctx->stream>>>(state, L);
   CU_TRY(cudaGetLastError());
   return 0;
 }
 
-template <int CTAS>
+template <int CTAS, bool PAIRED>
 static int launch_half_any(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
-  if (L.st_mode == DMB_ST_PERM128) return launch_half<CTAS, DMB_ST_PERM128>(ctx, state, L);
-  if (L.st_mode == DMB_ST_SPLIT64) return launch_half<CTAS, DMB_ST_SPLIT64>(ctx, state, L);
-  return launch_half<CTAS, DMB_ST_PLAIN>(ctx, state, L);
+  if (L.st_mode == DMB_ST_PERM128) return launch_half<CTAS, DMB_ST_PERM128, PAIRED>(ctx, state, L);
+  if (L.st_mode == DMB_ST_SPLIT64) return launch_half<CTAS, DMB_ST_SPLIT64, PAIRED>(ctx, state, L);
+  return launch_half<CTAS, DMB_ST_PLAIN, PAIRED>(ctx, state, L);
 }
 
 template <int STAGES, int CTAS>
@@ -446,8 +458,10 @@ static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_
     case 3: return launch_lean<2, 2, 0>(ctx, state, L);
     case 6: return launch_lean<1, 4, 0>(ctx, state, L);
     case 7: return launch_lean<1, 5, 0>(ctx, state, L);
-    case 8: return launch_half_any<6>(ctx, state, L);
-    case 9: return launch_half_any<5>(ctx, state, L);
+    case 8: return launch_half_any<6, false>(ctx, state, L);
+    case 9: return launch_half_any<5, false>(ctx, state, L);
+    case 10: return launch_half_any<4, true>(ctx, state, L);
+    case 11: return launch_half_any<5, true>(ctx, state, L);
     default:
       if (L.st_mode == DMB_ST_PERM128) return launch_lean<2, 3, 0, DMB_ST_PERM128>(ctx, state, L);
       if (L.st_mode == DMB_ST_SPLIT64) return launch_lean<2, 3, 0, DMB_ST_SPLIT64>(ctx, state, L);
@@ -571,7 +585,7 @@ int dmb_reset_stats(dmb_ctx* ctx) {
 
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant) {
   if (!ctx) return fail("dmb_set_tile_variant", "null context");
-  if (variant < 0 || variant > 9) return fail("dmb_set_tile_variant", "variant must be 0..9");
+  if (variant < 0 || variant > 11) return fail("dmb_set_tile_variant", "variant must be 0..11");
   ctx->tile_variant = variant;
   return 0;
 }

@@ -78,6 +78,8 @@ static void run_tile_pass(double* state, int n_bits, const dmb_pass& P, const dm
 // lean K = 6 path: same per-thread bodies as k_tile_pass6, tiles processed one after another
 static int g_variant = 0;
 static thread_local long g_folded_swaps = 0;
+static long g_paired_ops = 0;     // thread-ops that went through dmb_lean_op_pair (test hook)
+extern "C" long dmb_emu_paired_ops(void) { return g_paired_ops; }
 static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const dmb_remote_src& S = g_no_remote,
                            const dmb_remote_src& D = g_no_remote) {
   static thread_local dmb_lean_pass L;
@@ -91,8 +93,16 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const d
   for (uint64_t tile = 0; tile < L.n_tiles; ++tile) {
     const uint64_t tbase = dmb_tile_base(tile, L.td, DMB_LEAN_K);
     for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, state, tbase, S, mem);
-    for (int i = 0; i < L.n_ops; ++i)
-      for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_dispatch(T[t], L.ops[i], mem);
+    for (int i = 0; i < L.n_ops; ++i) {
+      if (g_variant == 10 || g_variant == 11) {        // paired kernel: real thread u plays virtual threads 2u, 2u + 1
+        for (int u = 0; u < DMB_TILE_THREADS / 2; ++u) {
+          if (dmb_lean_op_is_paired(L.ops[i])) ++g_paired_ops;
+          dmb_lean_op_dispatch_pair(T[2 * u], T[u], T[u + DMB_TILE_THREADS / 2], L.ops[i], mem);
+        }
+      } else {
+        for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_dispatch(T[t], L.ops[i], mem);
+      }
+    }
     for (int t = 0; t < DMB_TILE_THREADS; ++t) {
       if (D.enabled) dmb_lean_store_thread<true, DMB_ST_PLAIN>(T[t], L, state, tbase, D, mem);
       else if (L.st_mode == DMB_ST_PERM128) dmb_lean_store_thread<false, DMB_ST_PERM128>(T[t], L, state, tbase, D, mem);
@@ -175,7 +185,7 @@ int dmb_sync(dmb_ctx*) { return 0; }
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out) { *out = ctx->stats; return 0; }
 int dmb_reset_stats(dmb_ctx* ctx) { memset(&ctx->stats, 0, sizeof(dmb_stats)); return 0; }
 int dmb_set_tile_variant(dmb_ctx*, int variant) {
-  if (variant < 0 || variant > 9) return fail("dmb_set_tile_variant", "variant must be 0..9");
+  if (variant < 0 || variant > 11) return fail("dmb_set_tile_variant", "variant must be 0..11");
   g_variant = variant;
   return 0;
 }

@@ -111,3 +111,25 @@ def test_trailing_swaps_are_folded_into_the_store(golden, case_dir, monkeypatch)
     assert results["1"]["folded"] > 0 and results["0"]["folded"] == 0
     for key in ("sum", "dot", "sample"):
         assert results["1"][key] == results["0"][key]
+
+
+@pytest.mark.parametrize("variant", [8, 10])
+def test_half_cta_and_paired_kernel_bodies_match_golden(variant, golden, case_dir):
+    """Opt-in tile-kernel variants 8/9 (half-CTA) and 10/11 (paired: one thread plays virtual threads 2u and
+    2u + 1, mode-A ops move both 16-blocks with 128-bit accesses -- dmb_lean_op_pair) run the same per-thread
+    bodies here as on the GPU; the default kernel stays variant 0."""
+    import ctypes
+    from emu_backend import emu_engine, emu_lib
+    lib = emu_lib()
+    hook = lib.dmb_emu_paired_ops
+    hook.restype = ctypes.c_long
+    before = hook()
+    ctx = emu_engine(6).ctx
+    ctx.set_tile_variant(variant)
+    try:
+        for name in ("layered_n8_d6_noisy", "layered_n9_d4_memnoise", "rand_n7_fullnoise", "qft8_binary", "rand_n6_clean"):
+            if name in cases.CASES:
+                check_against_golden(golden, name, run_case(name))
+    finally:
+        ctx.set_tile_variant(0)
+    assert (hook() > before) == (variant == 10)

@@ -187,6 +187,31 @@ def test_lane_order_is_bank_conflict_free(a, b):
                     assert len(slots) == 16
 
 
+@pytest.mark.parametrize("a,b", [(a, b) for a in range(1, 6) for b in range(1, 6) if a != b])
+def test_paired_kernel_mode_a_is_bank_conflict_free(a, b):
+    """Paired tile kernel (variants 10/11, dmb_lean_op_pair): real lane u plays virtual threads 2u / 2u + 1 and
+    moves both blocks with one 128-bit access per (i, j).  lane_order puts tile digit 0 first, so the pair
+    (2u, 2u + 1) is one 16-byte chunk, and a quarter-warp of real lanes must hit 8 distinct chunks."""
+    K = 6
+    fd = schedule.lane_order(K, a, b)
+    assert fd[0] == 0                                 # the DMB_PAIRABLE condition (dm_device.h)
+    for warp in range(4):                             # 128 real threads
+        for i, j in itertools.product(range(4), repeat=2):
+            chunk_of_lane = []
+            for lane in range(32):
+                u = warp * 32 + lane
+                addrs = []
+                for t in (2 * u, 2 * u + 1):
+                    bl = 0
+                    for m in range(K - 2):
+                        bl |= ((t >> (2 * m)) & 3) << (2 * fd[m])
+                    addrs.append(_swz(bl | (i << (2 * a)) | (j << (2 * b))))
+                assert addrs[1] == addrs[0] + 1 and addrs[0] % 2 == 0      # the two halves of one aligned pair
+                chunk_of_lane.append((addrs[0] >> 1) & 7)
+            for quarter in range(4):
+                assert len(set(chunk_of_lane[8 * quarter: 8 * quarter + 8])) == 8
+
+
 # ---- pass scheduler ------------------------------------------------------------------------
 
 def _random_devops(rng, n_digits, count):
