@@ -744,17 +744,29 @@ DMB_HD void dmb_lean_op_dispatch(const dmb_lean_thread& T, const dmb_lean_op& op
   }
 }
 
+// virtual threads u and u + 128 one after the other (u + 128 = same index digits with tq[3] + 2); a real loop,
+// not unrolled, so that the specialised bodies exist once in the instruction stream
+template <class Mem>
+DMB_HD void dmb_lean_op_dispatch_twice(const dmb_lean_thread& S0, const dmb_lean_op& op, const Mem& mem) {
+  dmb_lean_thread T = S0;
+#pragma unroll 1
+  for (uint32_t h = 0; h < 2; ++h) {
+    T.tq[3] = S0.tq[3] + 2u * h;
+    dmb_lean_op_dispatch(T, op, mem);
+  }
+}
+
 #define DMB_PAIR_CASE(K, A, B) \
   case ((K * 3 + A) * 3 + B) * 3 + 0: dmb_lean_op_pair<K, A, B>(P0, op, mem); return;
 
 // Dispatch for a real thread u of the paired kernel.  Ops in access mode A run the paired body as virtual
 // threads 2u / 2u + 1 (P0 = thread struct of 2u); every other op runs the ordinary body twice, as virtual
-// threads u and u + 128 (S0, S1), so that consecutive lanes stay consecutive virtual threads -- the
+// threads u and u + 128 (from S0), so that consecutive lanes stay consecutive virtual threads -- the
 // arrangement the bank-conflict analysis of the 128-bit modes was made for.  Either way all 256 virtual
 // threads of the tile run exactly once per op.
 template <class Mem>
-DMB_HD void dmb_lean_op_dispatch_pair(const dmb_lean_thread& P0, const dmb_lean_thread& S0, const dmb_lean_thread& S1,
-                                      const dmb_lean_op& op, const Mem& mem) {
+DMB_HD void dmb_lean_op_dispatch_pair(const dmb_lean_thread& P0, const dmb_lean_thread& S0, const dmb_lean_op& op,
+                                      const Mem& mem) {
   if (op.flags & DMB_PAIRABLE) {
     switch (op.variant) {
       DMB_PAIR_CASE(DMB_OP_MATS, 1, 1)
@@ -770,8 +782,7 @@ DMB_HD void dmb_lean_op_dispatch_pair(const dmb_lean_thread& P0, const dmb_lean_
       default: break;
     }
   }
-  dmb_lean_op_dispatch(S0, op, mem);
-  dmb_lean_op_dispatch(S1, op, mem);
+  dmb_lean_op_dispatch_twice(S0, op, mem);
 }
 
 // true when dmb_lean_op_dispatch_pair takes the paired body for this op

@@ -216,12 +216,8 @@ k_tile_pass6_half(double* __restrict__ state, const __grid_constant__ dmb_lean_p
     cp_async_wait<0>();
     __syncthreads();
     for (int i = 0; i < L.n_ops; ++i) {
-      if constexpr (PAIRED) {
-        dmb_lean_op_dispatch_pair(P0, S0, S1, L.ops[i], mem);
-      } else {
-        dmb_lean_op_dispatch(S0, L.ops[i], mem);
-        dmb_lean_op_dispatch(S1, L.ops[i], mem);
-      }
+      if constexpr (PAIRED) dmb_lean_op_dispatch_pair(P0, S0, L.ops[i], mem);
+      else dmb_lean_op_dispatch_twice(S0, L.ops[i], mem);
       __syncthreads();
     }
     dmb_lean_store_thread<false, STMODE>(S0, L, state, tb, none, mem);

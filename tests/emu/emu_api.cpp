@@ -97,8 +97,10 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const d
       if (g_variant == 10 || g_variant == 11) {        // paired kernel: real thread u plays virtual threads 2u, 2u + 1
         for (int u = 0; u < DMB_TILE_THREADS / 2; ++u) {
           if (dmb_lean_op_is_paired(L.ops[i])) ++g_paired_ops;
-          dmb_lean_op_dispatch_pair(T[2 * u], T[u], T[u + DMB_TILE_THREADS / 2], L.ops[i], mem);
+          dmb_lean_op_dispatch_pair(T[2 * u], T[u], L.ops[i], mem);
         }
+      } else if (g_variant == 8 || g_variant == 9) {   // half-CTA kernel: real thread u plays u and u + 128
+        for (int u = 0; u < DMB_TILE_THREADS / 2; ++u) dmb_lean_op_dispatch_twice(T[u], L.ops[i], mem);
       } else {
         for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_dispatch(T[t], L.ops[i], mem);
       }
