@@ -188,12 +188,13 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
 #define DMB_HALF_THREADS 128
 // PAIRED (variants 10 / 11): the two virtual threads are 2u and 2u + 1 instead of u and u + 128, and ops in
 // access mode A run the paired body (dmb_lean_op_pair: 128-bit shared-memory accesses for both blocks).
-template <int CTAS, int STMODE, bool PAIRED>
+// STAGES = 1: load, wait, ops, store per tile (the other CTAs of the SM hide the latency); STAGES = 2: the next
+// tile of this CTA streams in during the op phase like in k_tile_pass6 (64 KiB per CTA -> 3 CTAs per SM).
+template <int CTAS, int STMODE, bool PAIRED, int STAGES = 1>
 __global__ void __launch_bounds__(DMB_HALF_THREADS, CTAS)
 k_tile_pass6_half(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L) {
   extern __shared__ __align__(128) unsigned char lean_smem[];
-  dmb_smem_mem mem;
-  mem.base = (uint32_t)__cvta_generic_to_shared(lean_smem);
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
   // staging (tile load / write-back) always walks the tile as virtual threads u and u + 128: consecutive
   // lanes touch consecutive 16-byte chunks (conflict-free, whole 128-byte lines per quarter-warp)
   dmb_lean_thread S0, S1;
@@ -205,24 +206,45 @@ k_tile_pass6_half(double* __restrict__ state, const __grid_constant__ dmb_lean_p
   dmb_lean_thread_init(2 * threadIdx.x, L, P0);
   dmb_remote_src none;
   none.enabled = 0;
-  for (uint64_t tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x) {
+  auto fetch = [&](uint64_t tile, uint32_t stage) {
     const uint64_t tb = dmb_tile_base(tile, L.td, DMB_LEAN_K);
+    const uint32_t dst = smem0 + stage * DMB_LEAN_TILE_BYTES;
 #pragma unroll
     for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
-      cp_async16s(mem.base + (S0.soff ^ L.pair_soff[i]), state + tb + (S0.goff | L.pair_goff[i]));
-      cp_async16s(mem.base + (S1.soff ^ L.pair_soff[i]), state + tb + (S1.goff | L.pair_goff[i]));
+      cp_async16s(dst + (S0.soff ^ L.pair_soff[i]), state + tb + (S0.goff | L.pair_goff[i]));
+      cp_async16s(dst + (S1.soff ^ L.pair_soff[i]), state + tb + (S1.goff | L.pair_goff[i]));
     }
+  };
+  const uint64_t first = blockIdx.x, stride = gridDim.x;
+  if (first >= L.n_tiles) return;
+  if constexpr (STAGES == 2) {
+    fetch(first, 0);
     cp_async_commit();
-    cp_async_wait<0>();
+  }
+  uint32_t cur = 0;
+  for (uint64_t tile = first; tile < L.n_tiles; tile += stride) {
+    if constexpr (STAGES == 2) {
+      if (tile + stride < L.n_tiles) fetch(tile + stride, cur ^ 1u);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      fetch(tile, 0);
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
     __syncthreads();
+    dmb_smem_mem mem;
+    mem.base = smem0 + cur * DMB_LEAN_TILE_BYTES;
     for (int i = 0; i < L.n_ops; ++i) {
       if constexpr (PAIRED) dmb_lean_op_dispatch_pair(P0, S0, L.ops[i], mem);
       else dmb_lean_op_dispatch_twice(S0, L.ops[i], mem);
       __syncthreads();
     }
+    const uint64_t tb = dmb_tile_base(tile, L.td, DMB_LEAN_K);
     dmb_lean_store_thread<false, STMODE>(S0, L, state, tb, none, mem);
     dmb_lean_store_thread<false, STMODE>(S1, L, state, tb, none, mem);
     __syncthreads();
+    if constexpr (STAGES == 2) cur ^= 1u;
   }
 }
 
@@ -400,26 +422,26 @@ static int launch_lean(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, cons
   return 0;
 }
 
-template <int CTAS, int STMODE, bool PAIRED>
+template <int CTAS, int STMODE, bool PAIRED, int STAGES>
 static int launch_half(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
-  const size_t smem = DMB_LEAN_TILE_BYTES;
+  const size_t smem = (size_t)STAGES * DMB_LEAN_TILE_BYTES;
   static std::atomic<uint64_t> attr_done{0};
   if (!((attr_done.load() >> (ctx->device & 63)) & 1ull)) {
-    CU_TRY(cudaFuncSetAttribute(k_tile_pass6_half<CTAS, STMODE, PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_tile_pass6_half<CTAS, STMODE, PAIRED, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done.fetch_or(1ull << (ctx->device & 63));
   }
   uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
   if (grid > L.n_tiles) grid = L.n_tiles;
-  k_tile_pass6_half<CTAS, STMODE, PAIRED><<<(unsigned)grid, DMB_HALF_THREADS, smem, ctx->stream>>>(state, L);
+  k_tile_pass6_half<CTAS, STMODE, PAIRED, STAGES><<<(unsigned)grid, DMB_HALF_THREADS, smem, ctx->stream>>>(state, L);
   CU_TRY(cudaGetLastError());
   return 0;
 }
 
-template <int CTAS, bool PAIRED>
+template <int CTAS, bool PAIRED, int STAGES = 1>
 static int launch_half_any(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
-  if (L.st_mode == DMB_ST_PERM128) return launch_half<CTAS, DMB_ST_PERM128, PAIRED>(ctx, state, L);
-  if (L.st_mode == DMB_ST_SPLIT64) return launch_half<CTAS, DMB_ST_SPLIT64, PAIRED>(ctx, state, L);
-  return launch_half<CTAS, DMB_ST_PLAIN, PAIRED>(ctx, state, L);
+  if (L.st_mode == DMB_ST_PERM128) return launch_half<CTAS, DMB_ST_PERM128, PAIRED, STAGES>(ctx, state, L);
+  if (L.st_mode == DMB_ST_SPLIT64) return launch_half<CTAS, DMB_ST_SPLIT64, PAIRED, STAGES>(ctx, state, L);
+  return launch_half<CTAS, DMB_ST_PLAIN, PAIRED, STAGES>(ctx, state, L);
 }
 
 template <int STAGES, int CTAS>
@@ -458,6 +480,7 @@ static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_
     case 9: return launch_half_any<5, false>(ctx, state, L);
     case 10: return launch_half_any<4, true>(ctx, state, L);
     case 11: return launch_half_any<5, true>(ctx, state, L);
+    case 12: return launch_half_any<3, true, 2>(ctx, state, L);
     default:
       if (L.st_mode == DMB_ST_PERM128) return launch_lean<2, 3, 0, DMB_ST_PERM128>(ctx, state, L);
       if (L.st_mode == DMB_ST_SPLIT64) return launch_lean<2, 3, 0, DMB_ST_SPLIT64>(ctx, state, L);
@@ -581,7 +604,7 @@ int dmb_reset_stats(dmb_ctx* ctx) {
 
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant) {
   if (!ctx) return fail("dmb_set_tile_variant", "null context");
-  if (variant < 0 || variant > 11) return fail("dmb_set_tile_variant", "variant must be 0..11");
+  if (variant < 0 || variant > 12) return fail("dmb_set_tile_variant", "variant must be 0..12");
   ctx->tile_variant = variant;
   return 0;
 }

@@ -94,7 +94,7 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const d
     const uint64_t tbase = dmb_tile_base(tile, L.td, DMB_LEAN_K);
     for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, state, tbase, S, mem);
     for (int i = 0; i < L.n_ops; ++i) {
-      if (g_variant == 10 || g_variant == 11) {        // paired kernel: real thread u plays virtual threads 2u, 2u + 1
+      if (g_variant >= 10) {        // paired kernel: real thread u plays virtual threads 2u, 2u + 1
         for (int u = 0; u < DMB_TILE_THREADS / 2; ++u) {
           if (dmb_lean_op_is_paired(L.ops[i])) ++g_paired_ops;
           dmb_lean_op_dispatch_pair(T[2 * u], T[u], L.ops[i], mem);
@@ -187,7 +187,7 @@ int dmb_sync(dmb_ctx*) { return 0; }
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out) { *out = ctx->stats; return 0; }
 int dmb_reset_stats(dmb_ctx* ctx) { memset(&ctx->stats, 0, sizeof(dmb_stats)); return 0; }
 int dmb_set_tile_variant(dmb_ctx*, int variant) {
-  if (variant < 0 || variant > 11) return fail("dmb_set_tile_variant", "variant must be 0..11");
+  if (variant < 0 || variant > 12) return fail("dmb_set_tile_variant", "variant must be 0..12");
   g_variant = variant;
   return 0;
 }
