@@ -186,8 +186,9 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
 // latency of a CTA's own tile load is hidden by the other CTAs instead of a prefetch stage.
 // ---------------------------------------------------------------------------------------
 #define DMB_HALF_THREADS 128
-// PAIRED (variants 10 / 11): the two virtual threads are 2u and 2u + 1 instead of u and u + 128, and ops in
-// access mode A run the paired body (dmb_lean_op_pair: 128-bit shared-memory accesses for both blocks).
+// PAIRED (variants 10 / 11 / 12): ops in access mode A (tile digit 0 free) run the paired body -- the thread plays
+// virtual threads 2u and 2u + 1, whose blocks are the two halves of the same 16-byte pairs (dmb_lean_op_pair:
+// 128-bit shared-memory accesses for both blocks); all other ops and the staging keep u / u + 128.
 // STAGES = 1: load, wait, ops, store per tile (the other CTAs of the SM hide the latency); STAGES = 2: the next
 // tile of this CTA streams in during the op phase like in k_tile_pass6 (64 KiB per CTA -> 3 CTAs per SM).
 template <int CTAS, int STMODE, bool PAIRED, int STAGES = 1>
