@@ -34,6 +34,8 @@ def main():
     from qiskit_aakash_b200 import circuits as C
     from qiskit_aakash_b200.dm_simulator import assemble
     dm, _ = ref_harness.load()
+    import tempfile
+    base_dir = tempfile.mkdtemp(prefix="dmb_fuzz_sessions_")
     counts = {}
     jobs = {'compared': 0, 'both-raise': 0}
     for seed in range(a.start, a.start + a.seeds):
@@ -43,6 +45,9 @@ def main():
         cls.DEFAULT_OPTIONS["rotation_error"] = {"rx": [1., 0.], "ry": [1., 0.], "rz": [1., 0.]}
         sim = cls()
         be = emu_backend()
+        dirs = [os.path.join(base_dir, "ref_%d" % seed), os.path.join(base_dir, "own_%d" % seed)]   # one cwd per side:
+        for d in dirs:                                                                            # each keeps its own
+            os.makedirs(d)                                                                        # stored_coefficients.npy
         st, msg = "ok", ""
         for job in range(int(rng.integers(2, 6))):
             n = int(rng.integers(1, 6))
@@ -51,9 +56,19 @@ def main():
             fuzz_emu.random_init(rng, n, opts)
             if rng.random() < 0.3:
                 opts["compute_densitymatrix"] = bool(rng.random() < 0.5)
+            # store / compare / stored initial state go through stored_density_matrix.npy in the working directory
+            # (dm_simulator.py:476-480, 1271-1282); both sides write and read the same file name
+            r = rng.random()
+            if r < 0.15:
+                opts["store_densitymatrix"] = True
+            elif r < 0.3:
+                opts["compare"] = True
+            elif r < 0.4:
+                opts["custom_densitymatrix"] = "stored_density_matrix"      # np.load("stored_density_matrix.npy"): absent -> both raise
             ref = got = e_ref = e_got = None
             with contextlib.redirect_stdout(io.StringIO()):
                 try:
+                    os.chdir(dirs[0])
                     sim._set_options(qobj_config=NS(n_qubits=n), backend_options=copy.deepcopy(opts))
                     worker = copy.deepcopy(sim)
                     exp = NS(config=NS(n_qubits=n, memory_slots=n),
@@ -63,6 +78,7 @@ def main():
                 except Exception as e:  # noqa: BLE001
                     e_ref = e
                 try:
+                    os.chdir(dirs[1])
                     c2 = C.Circuit(n)
                     c2.instructions = copy.deepcopy(circ.instructions)
                     got = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
