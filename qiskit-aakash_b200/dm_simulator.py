@@ -416,6 +416,10 @@ class DmSimulatorB200:
     def _run_job(self, job_id, qobj):
         """``_run_job`` (``:921-948``)."""
         self._validate(qobj)
+        # The reference runs a job in a forked worker (basicaerjob.py:51-54): what run_experiment writes to the
+        # simulator object -- the fidelity of a 'compare' -- never reaches the parent, so every job starts
+        # without one (it does carry over between the experiments of one job, :1184-1185).
+        self._fidelity = None
         start = time.time()
         # lowering a deep circuit allocates ~10^5 small host objects; a generational GC pass over the
         # whole heap in the middle of it stalls kernel submission by 100+ ms, so collection is

@@ -142,3 +142,21 @@ def test_store_and_compare_round_trip(case_dir):
     assert stored.shape == (64,) and abs(stored[0] * 8 - 1) < 1e-15
     d = _run(emu_backend(), c, compare=True)["results"][0]["data"]
     assert abs(d["fidelity"] - 1.0) < 1e-12
+
+
+def test_fidelity_of_a_compare_job_does_not_leak_into_the_next_job(tmp_path, monkeypatch):
+    """The reference runs each job in a forked worker, so the fidelity computed by a 'compare' job is gone when
+    the next job starts (found by tools/fuzz_sessions.py against the live reference)."""
+    from emu_backend import emu_backend
+    from qiskit_aakash_b200 import assemble, circuits as C
+    monkeypatch.chdir(tmp_path)
+    be = emu_backend()
+    c = C.ghz(3)
+    c.measure([0, 1, 2], [0, 1, 2], basis="Ensemble", add_param="Z")
+    be.run(assemble(c), backend_options={"store_densitymatrix": True}).result()
+    second = be.run(assemble(c), backend_options={"compare": True, "store_densitymatrix": False}).result()["results"][0]["data"]
+    assert abs(second["fidelity"] - 1.0) <= 1e-12
+    plain = C.Circuit(3)
+    plain.h(0)                                   # no ensemble readout -> no comparison in this job
+    third = be.run(assemble(plain), backend_options={}).result()["results"][0]["data"]
+    assert "fidelity" not in third
