@@ -51,7 +51,8 @@ def main():
         st, msg = "ok", ""
         for job in range(int(rng.integers(2, 6))):
             n = int(rng.integers(1, 6))
-            circ = fuzz_emu.random_circuit(rng, n, 30)
+            n_exp = 1 if rng.random() < 0.6 else int(rng.integers(2, 4))      # experiments of this job (same register size)
+            circs = [fuzz_emu.random_circuit(rng, n, 30) for _ in range(n_exp)]
             opts = fuzz_emu.random_options(rng)
             fuzz_emu.random_init(rng, n, opts)
             if rng.random() < 0.3:
@@ -71,17 +72,22 @@ def main():
                     os.chdir(dirs[0])
                     sim._set_options(qobj_config=NS(n_qubits=n), backend_options=copy.deepcopy(opts))
                     worker = copy.deepcopy(sim)
-                    exp = NS(config=NS(n_qubits=n, memory_slots=n),
-                             instructions=ref_harness.to_reference_instructions(copy.deepcopy(circ.instructions)),
-                             header=NS(name="fuzz", as_dict=lambda: {"name": "fuzz"}))
-                    ref = worker.run_experiment(exp)
+                    ref = []
+                    for circ in circs:              # one worker runs all experiments of the job (dm_simulator.py:934-935)
+                        exp = NS(config=NS(n_qubits=n, memory_slots=n),
+                                 instructions=ref_harness.to_reference_instructions(copy.deepcopy(circ.instructions)),
+                                 header=NS(name="fuzz", as_dict=lambda: {"name": "fuzz"}))
+                        ref.append(worker.run_experiment(exp))
                 except Exception as e:  # noqa: BLE001
                     e_ref = e
                 try:
                     os.chdir(dirs[1])
-                    c2 = C.Circuit(n)
-                    c2.instructions = copy.deepcopy(circ.instructions)
-                    got = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
+                    mine = []
+                    for circ in circs:
+                        c2 = C.Circuit(n)
+                        c2.instructions = copy.deepcopy(circ.instructions)
+                        mine.append(c2)
+                    got = be.run(assemble(mine), backend_options=copy.deepcopy(opts)).result()["results"]
                 except Exception as e:  # noqa: BLE001
                     e_got = e
             if e_ref or e_got:
@@ -91,15 +97,20 @@ def main():
                 jobs['both-raise'] += 1
                 continue
             jobs['compared'] += 1
-            if ref["number_of_clock_cycles"] != got["number_of_clock_cycles"] or set(ref["data"]) != set(got["data"]):
-                st, msg = "FAIL", "job %d: levels/keys %s vs %s (opts %r)" % (job, sorted(ref["data"]), sorted(got["data"]), opts)
-                break
-            for k, v in ref["data"].items():
-                x, y = fuzz_emu.as_arr(v), fuzz_emu.as_arr(got["data"][k])
-                if x.shape != y.shape or (x.size and float(np.max(np.abs(x - y))) > 1e-10):
-                    st, msg = "FAIL", "job %d n=%d %s differs (opts %r)" % (job, n, k, opts)
+            for e, (r_e, g_e) in enumerate(zip(ref, got)):
+                if r_e["number_of_clock_cycles"] != g_e["number_of_clock_cycles"] or set(r_e["data"]) != set(g_e["data"]):
+                    st, msg = "FAIL", "job %d exp %d: levels/keys %s vs %s (opts %r)" % (job, e, sorted(r_e["data"]),
+                                                                                        sorted(g_e["data"]), opts)
                     break
-            if st != "ok":
+                for k, v in r_e["data"].items():
+                    x, y = fuzz_emu.as_arr(v), fuzz_emu.as_arr(g_e["data"][k])
+                    if x.shape != y.shape or (x.size and float(np.max(np.abs(x - y))) > 1e-10):
+                        st, msg = "FAIL", "job %d exp %d n=%d %s differs (opts %r)" % (job, e, n, k, opts)
+                        break
+                if st != "ok":
+                    break
+            if st != "ok" or len(ref) != len(got):
+                st = "FAIL"
                 break
         counts[st] = counts.get(st, 0) + 1
         if st == "FAIL":
