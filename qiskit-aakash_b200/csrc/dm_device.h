@@ -825,6 +825,72 @@ DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass&
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Body of the half-CTA / paired tile kernel (k_tile_pass6_half in dmb200.cu, tile variants 8-12), written
+// against an execution-context policy so that the SAME control flow -- tile loop, stage ring, asynchronous
+// staging, barriers -- runs on the GPU and, with real host threads, in the CPU tests (tests/emu).
+//   Ctx: tid() / block() / grid()       thread index in the CTA (0..127), CTA index, number of CTAs
+//        copy16(stage byte offset, src) asynchronous 16-byte copy global -> stage memory (cp.async)
+//        commit() / wait<N>()           close the current copy group / wait for all but the N newest groups
+//        sync()                         CTA barrier
+//        mem(stage byte offset)         accessor (ld64 / ld128 / st64 / st128) of a stage
+// STAGES = 1: load, wait, ops, store per tile (the other CTAs of the SM hide the latency); STAGES = 2: the
+// next tile of this CTA streams in during the op phase.
+// ---------------------------------------------------------------------------------------
+#define DMB_HALF_THREADS 128
+template <int STMODE, bool PAIRED, int STAGES, class Ctx>
+DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L) {
+  // staging (tile load / write-back) walks the tile as virtual threads u and u + 128: consecutive lanes touch
+  // consecutive 16-byte chunks (conflict-free, whole 128-byte lines per quarter-warp)
+  dmb_lean_thread S0, S1;
+  dmb_lean_thread_init(cx.tid(), L, S0);
+  dmb_lean_thread_init(cx.tid() + DMB_HALF_THREADS, L, S1);
+  // op phase: the same two virtual threads; PAIRED: mode-A ops run as virtual threads 2u / 2u + 1 instead
+  // (dmb_lean_op_dispatch_pair) -- only P0's index digits are used
+  dmb_lean_thread P0;
+  dmb_lean_thread_init(2 * cx.tid(), L, P0);
+  dmb_remote_src none;
+  none.enabled = 0;
+  const uint64_t first = cx.block(), stride = cx.grid();
+  if (first >= L.n_tiles) return;
+  if (STAGES == 2) {
+    const uint64_t tb = dmb_tile_base(first, L.td, DMB_LEAN_K);
+#pragma unroll
+    for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
+      cx.copy16(S0.soff ^ L.pair_soff[i], state + tb + (S0.goff | L.pair_goff[i]));
+      cx.copy16(S1.soff ^ L.pair_soff[i], state + tb + (S1.goff | L.pair_goff[i]));
+    }
+    cx.commit();
+  }
+  uint32_t cur = 0;
+  for (uint64_t tile = first; tile < L.n_tiles; tile += stride) {
+    const uint64_t fetch_tile = STAGES == 2 ? tile + stride : tile;
+    if (fetch_tile < L.n_tiles) {
+      const uint64_t tb = dmb_tile_base(fetch_tile, L.td, DMB_LEAN_K);
+      const uint32_t dst = (STAGES == 2 ? (cur ^ 1u) : 0u) * DMB_LEAN_TILE_BYTES;
+#pragma unroll
+      for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
+        cx.copy16(dst + (S0.soff ^ L.pair_soff[i]), state + tb + (S0.goff | L.pair_goff[i]));
+        cx.copy16(dst + (S1.soff ^ L.pair_soff[i]), state + tb + (S1.goff | L.pair_goff[i]));
+      }
+    }
+    cx.commit();
+    cx.template wait<STAGES - 1>();
+    cx.sync();
+    const auto mem = cx.mem(cur * DMB_LEAN_TILE_BYTES);
+    for (int i = 0; i < L.n_ops; ++i) {
+      if (PAIRED) dmb_lean_op_dispatch_pair(P0, S0, L.ops[i], mem);
+      else dmb_lean_op_dispatch_twice(S0, L.ops[i], mem);
+      cx.sync();
+    }
+    const uint64_t tb = dmb_tile_base(tile, L.td, DMB_LEAN_K);
+    dmb_lean_store_thread<false, STMODE>(S0, L, state, tb, none, mem);
+    dmb_lean_store_thread<false, STMODE>(S1, L, state, tb, none, mem);
+    cx.sync();
+    if (STAGES == 2) cur ^= 1u;
+  }
+}
+
 // A pass whose ops carry post_swap is run by materialising the remap as explicit DMB_OP_SWAP ops.  Returns the number of
 // passes written to out[0..1] (the expanded op list can exceed DMB_MAX_OPS).
 inline int dmb_expand_post_swaps(const dmb_pass& P, dmb_pass* out) {

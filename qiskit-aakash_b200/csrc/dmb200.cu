@@ -185,68 +185,35 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
 // phase mixing between CTAs on the shared-memory / FP64 pipes and cheaper barriers; the HBM
 // latency of a CTA's own tile load is hidden by the other CTAs instead of a prefetch stage.
 // ---------------------------------------------------------------------------------------
-#define DMB_HALF_THREADS 128
 // PAIRED (variants 10 / 11 / 12): ops in access mode A (tile digit 0 free) run the paired body -- the thread plays
 // virtual threads 2u and 2u + 1, whose blocks are the two halves of the same 16-byte pairs (dmb_lean_op_pair:
 // 128-bit shared-memory accesses for both blocks); all other ops and the staging keep u / u + 128.
-// STAGES = 1: load, wait, ops, store per tile (the other CTAs of the SM hide the latency); STAGES = 2: the next
-// tile of this CTA streams in during the op phase like in k_tile_pass6 (64 KiB per CTA -> 3 CTAs per SM).
+// The control flow lives in dm_device.h (dmb_half_kernel_body) so that the CPU tests run it with real threads;
+// this is its CUDA execution context.
+struct dmb_cuda_cta {
+  uint32_t smem0;
+  __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
+  __device__ __forceinline__ uint64_t block() const { return blockIdx.x; }
+  __device__ __forceinline__ uint64_t grid() const { return gridDim.x; }
+  __device__ __forceinline__ void copy16(uint32_t off, const double* src) const { cp_async16s(smem0 + off, src); }
+  __device__ __forceinline__ void commit() const { cp_async_commit(); }
+  template <int N>
+  __device__ __forceinline__ void wait() const { cp_async_wait<N>(); }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  __device__ __forceinline__ dmb_smem_mem mem(uint32_t off) const {
+    dmb_smem_mem m;
+    m.base = smem0 + off;
+    return m;
+  }
+};
+
 template <int CTAS, int STMODE, bool PAIRED, int STAGES = 1>
 __global__ void __launch_bounds__(DMB_HALF_THREADS, CTAS)
 k_tile_pass6_half(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L) {
   extern __shared__ __align__(128) unsigned char lean_smem[];
-  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
-  // staging (tile load / write-back) always walks the tile as virtual threads u and u + 128: consecutive
-  // lanes touch consecutive 16-byte chunks (conflict-free, whole 128-byte lines per quarter-warp)
-  dmb_lean_thread S0, S1;
-  dmb_lean_thread_init(threadIdx.x, L, S0);
-  dmb_lean_thread_init(threadIdx.x + DMB_HALF_THREADS, L, S1);
-  // op phase: the same two virtual threads; PAIRED: mode-A ops run as virtual threads 2u / 2u + 1 instead
-  // (dmb_lean_op_dispatch_pair) -- only P0's index digits are used
-  dmb_lean_thread P0;
-  dmb_lean_thread_init(2 * threadIdx.x, L, P0);
-  dmb_remote_src none;
-  none.enabled = 0;
-  auto fetch = [&](uint64_t tile, uint32_t stage) {
-    const uint64_t tb = dmb_tile_base(tile, L.td, DMB_LEAN_K);
-    const uint32_t dst = smem0 + stage * DMB_LEAN_TILE_BYTES;
-#pragma unroll
-    for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
-      cp_async16s(dst + (S0.soff ^ L.pair_soff[i]), state + tb + (S0.goff | L.pair_goff[i]));
-      cp_async16s(dst + (S1.soff ^ L.pair_soff[i]), state + tb + (S1.goff | L.pair_goff[i]));
-    }
-  };
-  const uint64_t first = blockIdx.x, stride = gridDim.x;
-  if (first >= L.n_tiles) return;
-  if constexpr (STAGES == 2) {
-    fetch(first, 0);
-    cp_async_commit();
-  }
-  uint32_t cur = 0;
-  for (uint64_t tile = first; tile < L.n_tiles; tile += stride) {
-    if constexpr (STAGES == 2) {
-      if (tile + stride < L.n_tiles) fetch(tile + stride, cur ^ 1u);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      fetch(tile, 0);
-      cp_async_commit();
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    dmb_smem_mem mem;
-    mem.base = smem0 + cur * DMB_LEAN_TILE_BYTES;
-    for (int i = 0; i < L.n_ops; ++i) {
-      if constexpr (PAIRED) dmb_lean_op_dispatch_pair(P0, S0, L.ops[i], mem);
-      else dmb_lean_op_dispatch_twice(S0, L.ops[i], mem);
-      __syncthreads();
-    }
-    const uint64_t tb = dmb_tile_base(tile, L.td, DMB_LEAN_K);
-    dmb_lean_store_thread<false, STMODE>(S0, L, state, tb, none, mem);
-    dmb_lean_store_thread<false, STMODE>(S1, L, state, tb, none, mem);
-    __syncthreads();
-    if constexpr (STAGES == 2) cur ^= 1u;
-  }
+  dmb_cuda_cta cx;
+  cx.smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
+  dmb_half_kernel_body<STMODE, PAIRED, STAGES>(cx, state, L);
 }
 
 // ---------------------------------------------------------------------------------------

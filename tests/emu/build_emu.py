@@ -15,7 +15,7 @@ def build(force=False):
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
         return OUT
     cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "include"),
-           "-I" + os.path.join(ROOT, "qiskit-aakash_b200", "csrc")] + SRCS + ["-o", OUT]
+           "-I" + os.path.join(ROOT, "qiskit-aakash_b200", "csrc")] + SRCS + ["-o", OUT, "-pthread"]
     subprocess.check_call(cmd)
     return OUT
 

@@ -8,6 +8,9 @@
 // into tests/emu/libdmb200_emu.so by tests/emu/build_emu.py and loaded only by the
 // `-m "not gpu"` tests through an explicit injection hook; the product never loads it.
 #include <math.h>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
@@ -112,6 +115,92 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const d
       else dmb_lean_store_thread<false, DMB_ST_PLAIN>(T[t], L, state, tbase, D, mem);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// The half-CTA / paired kernel's REAL control flow (dmb_half_kernel_body, the function the CUDA kernel
+// k_tile_pass6_half wraps) on host threads: 128 std::threads per CTA, a CTA barrier, and cp.async emulated as
+// deferred copies that only land at wait<N>() -- so a read before the wait, a missing barrier or a wrong stage
+// index shows up as a wrong result here, without a GPU.
+// ---------------------------------------------------------------------------------------
+struct emu_barrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int count = 0, generation = 0, parties;
+  explicit emu_barrier(int n) : parties(n) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    const int gen = generation;
+    if (++count == parties) { count = 0; ++generation; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != generation; });
+  }
+};
+
+struct emu_cta_thread {
+  int tid_;
+  uint64_t block_, grid_;
+  unsigned char* stages;                    // STAGES x 32 KiB, shared by the CTA's threads
+  emu_barrier* bar;
+  std::vector<std::vector<std::pair<uint32_t, const double*>>> groups;   // open group = groups.back()
+  emu_cta_thread() { groups.emplace_back(); }
+  int tid() const { return tid_; }
+  uint64_t block() const { return block_; }
+  uint64_t grid() const { return grid_; }
+  void copy16(uint32_t off, const double* src) { groups.back().emplace_back(off, src); }
+  void commit() { groups.emplace_back(); }
+  template <int N>
+  void wait() {                             // all but the N most recently committed groups complete
+    while ((int)groups.size() - 1 > N) {
+      for (auto& c : groups.front()) memcpy(stages + c.first, c.second, 16);
+      groups.erase(groups.begin());
+    }
+  }
+  void sync() { bar->wait(); }
+  dmb_host_mem mem(uint32_t off) const {
+    dmb_host_mem m;
+    m.base = stages + off;
+    return m;
+  }
+};
+
+template <int STMODE, bool PAIRED, int STAGES>
+static void run_half_kernel_cta(double* state, const dmb_lean_pass& L, uint64_t block, uint64_t grid) {
+  std::vector<unsigned char> stages((size_t)STAGES * DMB_LEAN_TILE_BYTES + 128);
+  unsigned char* base = stages.data() + (128 - (reinterpret_cast<uintptr_t>(stages.data()) & 127)) % 128;
+  emu_barrier bar(DMB_HALF_THREADS);
+  std::vector<std::thread> threads;
+  for (int t = 0; t < DMB_HALF_THREADS; ++t)
+    threads.emplace_back([&, t] {
+      emu_cta_thread cx;
+      cx.tid_ = t; cx.block_ = block; cx.grid_ = grid; cx.stages = base; cx.bar = &bar;
+      dmb_half_kernel_body<STMODE, PAIRED, STAGES>(cx, state, L);
+    });
+  for (auto& th : threads) th.join();
+}
+
+template <bool PAIRED, int STAGES>
+static void run_half_kernel(double* state, const dmb_lean_pass& L, uint64_t grid) {
+  for (uint64_t block = 0; block < grid; ++block) {
+    if (L.st_mode == DMB_ST_PERM128) run_half_kernel_cta<DMB_ST_PERM128, PAIRED, STAGES>(state, L, block, grid);
+    else if (L.st_mode == DMB_ST_SPLIT64) run_half_kernel_cta<DMB_ST_SPLIT64, PAIRED, STAGES>(state, L, block, grid);
+    else run_half_kernel_cta<DMB_ST_PLAIN, PAIRED, STAGES>(state, L, block, grid);
+  }
+}
+
+// test hook: run `n_passes` K = 6 passes through the threaded kernel body (paired: 0/1, stages: 1/2, grid CTAs)
+extern "C" int dmb_emu_run_half_kernel(double* state, int n_bits, const dmb_pass* passes, size_t n_passes, int paired,
+                                       int stages, int grid) {
+  static thread_local dmb_lean_pass L;
+  for (size_t i = 0; i < n_passes; ++i) {
+    if (passes[i].n_tile_digits != DMB_LEAN_K || dmb_pass_has_post_swap(passes[i])) return 1;
+    dmb_make_lean_pass(passes[i], n_bits, L, dmb_fold_swaps_enabled());
+    uint64_t g = (uint64_t)grid < L.n_tiles ? (uint64_t)grid : L.n_tiles;
+    if (paired && stages == 2) run_half_kernel<true, 2>(state, L, g);
+    else if (paired) run_half_kernel<true, 1>(state, L, g);
+    else if (stages == 2) run_half_kernel<false, 2>(state, L, g);
+    else run_half_kernel<false, 1>(state, L, g);
+  }
+  return 0;
 }
 
 // R3 path (three digits per thread), same bodies as k_tile_pass_r3
