@@ -437,7 +437,7 @@ static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_
   }
   static thread_local dmb_lean_pass L;    // 6.5 KB: keep it off the stack; one host thread drives a ctx
   const bool fold = (ctx->tile_variant == 0 || ctx->tile_variant >= 8) && dmb_fold_swaps_enabled();
-  dmb_make_lean_pass(P, n_bits, L, fold);
+  dmb_make_lean_pass(P, n_bits, L, fold, ctx->tile_variant == 13);
   ctx->stats.folded_swaps += (uint64_t)(P.n_ops - L.n_ops);
   switch (ctx->tile_variant) {
     case 2: return launch_lean<3, 2, 0>(ctx, state, L);
@@ -449,6 +449,7 @@ static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_
     case 10: return launch_half_any<4, true>(ctx, state, L);
     case 11: return launch_half_any<5, true>(ctx, state, L);
     case 12: return launch_half_any<3, true, 2>(ctx, state, L);
+    case 13: return launch_half_any<4, true>(ctx, state, L);      // 10 + TSP0 factor folded into the control map
     default:
       if (L.st_mode == DMB_ST_PERM128) return launch_lean<2, 3, 0, DMB_ST_PERM128>(ctx, state, L);
       if (L.st_mode == DMB_ST_SPLIT64) return launch_lean<2, 3, 0, DMB_ST_SPLIT64>(ctx, state, L);
@@ -572,7 +573,7 @@ int dmb_reset_stats(dmb_ctx* ctx) {
 
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant) {
   if (!ctx) return fail("dmb_set_tile_variant", "null context");
-  if (variant < 0 || variant > 12) return fail("dmb_set_tile_variant", "variant must be 0..12");
+  if (variant < 0 || variant > 13) return fail("dmb_set_tile_variant", "variant must be 0..13");
   ctx->tile_variant = variant;
   return 0;
 }

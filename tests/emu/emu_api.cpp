@@ -86,7 +86,8 @@ extern "C" long dmb_emu_paired_ops(void) { return g_paired_ops; }
 static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const dmb_remote_src& S = g_no_remote,
                            const dmb_remote_src& D = g_no_remote) {
   static thread_local dmb_lean_pass L;
-  dmb_make_lean_pass(P, n_bits, L, (g_variant == 0 || g_variant >= 8) && dmb_fold_swaps_enabled() && !S.enabled && !D.enabled);
+  dmb_make_lean_pass(P, n_bits, L, (g_variant == 0 || g_variant >= 8) && dmb_fold_swaps_enabled() && !S.enabled && !D.enabled,
+                     g_variant == 13);
   g_folded_swaps += P.n_ops - L.n_ops;
   alignas(128) static thread_local unsigned char stage[DMB_LEAN_TILE_BYTES];
   static thread_local dmb_lean_thread T[DMB_TILE_THREADS];
@@ -276,7 +277,7 @@ int dmb_sync(dmb_ctx*) { return 0; }
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out) { *out = ctx->stats; return 0; }
 int dmb_reset_stats(dmb_ctx* ctx) { memset(&ctx->stats, 0, sizeof(dmb_stats)); return 0; }
 int dmb_set_tile_variant(dmb_ctx*, int variant) {
-  if (variant < 0 || variant > 12) return fail("dmb_set_tile_variant", "variant must be 0..12");
+  if (variant < 0 || variant > 13) return fail("dmb_set_tile_variant", "variant must be 0..13");
   g_variant = variant;
   return 0;
 }

@@ -113,11 +113,12 @@ def test_trailing_swaps_are_folded_into_the_store(golden, case_dir, monkeypatch)
         assert results["1"][key] == results["0"][key]
 
 
-@pytest.mark.parametrize("variant", [8, 10])
+@pytest.mark.parametrize("variant", [8, 10, 13])
 def test_half_cta_and_paired_kernel_bodies_match_golden(variant, golden, case_dir):
     """Opt-in tile-kernel variants 8/9 (half-CTA) and 10/11 (paired: one thread plays virtual threads 2u and
     2u + 1, mode-A ops move both 16-blocks with 128-bit accesses -- dmb_lean_op_pair) run the same per-thread
-    bodies here as on the GPU; the default kernel stays variant 0."""
+    bodies here as on the GPU (13 = 10 with the zero-mean TSP factor folded into the control map on the host); the default
+    kernel stays variant 0."""
     import ctypes
     from emu_backend import emu_engine, emu_lib
     lib = emu_lib()
@@ -132,4 +133,4 @@ def test_half_cta_and_paired_kernel_bodies_match_golden(variant, golden, case_di
                 check_against_golden(golden, name, run_case(name))
     finally:
         ctx.set_tile_variant(0)
-    assert (hook() > before) == (variant == 10)
+    assert (hook() > before) == (variant >= 10)
