@@ -328,7 +328,12 @@ class DmSimulatorB200:
             probs = engine.marginal_probabilities(basis, err_param)
         prob = dict(zip(self._keys(n), probs))
         if self.STORE_LOCAL:
-            np.save("stored_coefficients", engine.download())
+            vec = engine.download()
+            comm = getattr(engine, "comm", None)
+            if comm is None or comm.rank == 0:               # sharded: one writer, the others wait for the file
+                np.save("stored_coefficients", vec)
+            if comm is not None:
+                comm.barrier()
         if self.COMPARE and self.FILE_EXIST:
             self._fidelity = engine.overlap_with(self._density_matrix_stored) * 2 ** n
         return prob
