@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N tools/dist_check.py : sharded engine on real GPUs vs the oracle."""
+"""torchrun --nproc-per-node N tests/harness/dist_check.py : sharded engine on real GPUs vs the oracle."""
 import copy
 import json
 import os
@@ -8,7 +8,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -65,10 +65,10 @@ def main():
                               "d_coeff": d_c, "exchanges": engines[0].exchanges, "fused_exchange": engines[0].peers is not None,
                               "nvlink_bytes_sent_per_rank": engines[0].nvlink_bytes_sent}))
         dist.barrier()
-    # random programs (tools/fuzz_emu.py's generator: every measurement mode mid-circuit, resets, random
+    # random programs (tests/harness/fuzz_emu.py's generator: every measurement mode mid-circuit, resets, random
     # options) -- includes the pattern that exposed the scratch-shard race after a fused pull (a readout
     # that uses the scratch shard as workspace right after an exchange)
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "harness"))
     import contextlib
     import io
     import fuzz_emu

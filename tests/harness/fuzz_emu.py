@@ -3,7 +3,7 @@ mode, resets, barriers and random option sets are run through the backend bound 
 kernels (tests/emu) and through the oracle; any difference > 1e-10, any key mismatch and any
 exception raised by only one side is reported with the seed that reproduces it.
 
-    python tools/fuzz_emu.py [--seeds 200] [--start 0] [--min-n 1] [--max-n 8] [--max-ops 60]
+    python tests/harness/fuzz_emu.py [--seeds 200] [--start 0] [--min-n 1] [--max-n 8] [--max-ops 60]
 """
 import argparse
 import copy
@@ -13,7 +13,7 @@ import traceback
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

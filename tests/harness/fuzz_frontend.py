@@ -4,7 +4,7 @@ qiskit_aakash_b200.frontend and through the reference's QuantumCircuit (oracle/f
 and the instruction lists both hand to the simulator must be identical record by record
 (names, order, qubit / clbit indices, parameter bits).
 
-    python tools/fuzz_frontend.py [--seeds 300] [--start 0]
+    python tests/harness/fuzz_frontend.py [--seeds 300] [--start 0]
 """
 import argparse
 import os
@@ -14,7 +14,7 @@ from types import SimpleNamespace
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

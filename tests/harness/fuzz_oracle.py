@@ -1,9 +1,9 @@
 """Randomised pinning of the ORACLE against the LIVE reference simulator (TEST TOOL; needs
-/root/reference, build container only): tools/fuzz_emu.py's random circuits and option sets are
+/root/reference, build container only): tests/harness/fuzz_emu.py's random circuits and option sets are
 run through the unmodified ``DmSimulatorPy.run_experiment`` (oracle/ref_harness.py) and through
 oracle/dm_oracle.py; every result key must agree to 1e-13 and both must raise on the same inputs.
 
-    python tools/fuzz_oracle.py [--seeds 300] [--start 0] [--max-n 6]
+    python tests/harness/fuzz_oracle.py [--seeds 300] [--start 0] [--max-n 6]
 """
 import argparse
 import contextlib
@@ -14,10 +14,10 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "harness"))
 
 
 def main():

@@ -5,7 +5,7 @@ mirror must reproduce that number for number.  A session = several jobs with ran
 on ONE reference ``DmSimulatorPy`` (``_set_options`` in the parent, ``run_experiment`` on a copy,
 like the forked worker of basicaerjob.py:51-54) and on ONE emulated-kernel backend.
 
-    python tools/fuzz_sessions.py [--seeds 100] [--start 0]
+    python tests/harness/fuzz_sessions.py [--seeds 100] [--start 0]
 """
 import argparse
 import contextlib
@@ -17,10 +17,10 @@ from types import SimpleNamespace as NS
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "harness"))
 
 
 def main():

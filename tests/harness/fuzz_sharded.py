@@ -1,8 +1,8 @@
 """Randomised parity hunt for the SHARDED engine (TEST TOOL, CPU only): the ranks are threads of
 one process (tests/test_fused_exchange_cpu.py's ThreadCluster), kernels are the emulated ones, the
-circuits / option sets are tools/fuzz_emu.py's (every measurement mode, resets, barriers).
+circuits / option sets are tests/harness/fuzz_emu.py's (every measurement mode, resets, barriers).
 
-    python tools/fuzz_sharded.py [--seeds 100] [--start 0] [--worlds 2,4,8] [--modes pull,push,nccl]
+    python tests/harness/fuzz_sharded.py [--seeds 100] [--start 0] [--worlds 2,4,8] [--modes pull,push,nccl]
 """
 import argparse
 import copy
@@ -12,10 +12,10 @@ import traceback
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "harness"))
 
 import fuzz_emu  # noqa: E402
 from oracle import dm_oracle  # noqa: E402

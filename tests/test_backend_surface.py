@@ -146,7 +146,7 @@ def test_store_and_compare_round_trip(case_dir):
 
 def test_fidelity_of_a_compare_job_does_not_leak_into_the_next_job(tmp_path, monkeypatch):
     """The reference runs each job in a forked worker, so the fidelity computed by a 'compare' job is gone when
-    the next job starts (found by tools/fuzz_sessions.py against the live reference)."""
+    the next job starts (found by tests/harness/fuzz_sessions.py against the live reference)."""
     from emu_backend import emu_backend
     from qiskit_aakash_b200 import assemble, circuits as C
     monkeypatch.chdir(tmp_path)

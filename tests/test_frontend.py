@@ -255,10 +255,10 @@ def test_text_views_and_circuit_arithmetic():
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/qiskit"), reason="live reference front-end only in the build container")
 def test_random_programs_against_the_live_reference_front_end():
-    """tools/fuzz_frontend.py (own process: the harness claims the ``qiskit`` module name); 2800
+    """tests/harness/fuzz_frontend.py (own process: the harness claims the ``qiskit`` module name); 2800
     seeds were identical when this slice was committed."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_frontend.py"), "--seeds", "60", "--start", "7000"],
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "harness", "fuzz_frontend.py"), "--seeds", "60", "--start", "7000"],
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0 and "'ok': 60" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

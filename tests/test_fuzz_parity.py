@@ -1,6 +1,6 @@
 """Randomised parity (CPU): random instruction lists with every measurement mode, resets,
 barriers and random option sets through the backend on the emulated kernels vs the oracle
-(tools/fuzz_emu.py is the long-running form of the same hunt; 1700 seeds were clean when this
+(tests/harness/fuzz_emu.py is the long-running form of the same hunt; 1700 seeds were clean when this
 slice was committed).  A case where the reference itself crashes must raise here too."""
 import os
 import sys
@@ -8,7 +8,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "harness"))
 
 import fuzz_emu  # noqa: E402
 
@@ -28,7 +28,7 @@ def test_random_long_circuit_matches_oracle(seed):
 @pytest.mark.parametrize("world,mode,seed", [(2, "pull", 1), (4, "pull", 1), (8, "pull", 9), (4, "pull", 123), (8, "pull", 67),
                                              (2, "push", 5), (4, "nccl", 6), (8, "push", 7), (8, "nccl", 8)])
 def test_random_circuit_on_the_sharded_engine_matches_oracle(world, mode, seed):
-    """Thread cluster + emulated kernels (tools/fuzz_sharded.py; 3000+ clean runs).  The pull seeds are
+    """Thread cluster + emulated kernels (tests/harness/fuzz_sharded.py; 3000+ clean runs).  The pull seeds are
     the ones that exposed the scratch-shard race: a rank that finished its fused pull used the
     scratch shard as N-basis readout workspace while a slower peer was still pulling from it
     (fixed by ShardedPauliEngine._own_scratch)."""

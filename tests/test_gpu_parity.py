@@ -235,12 +235,12 @@ def test_relabelling_store_is_an_exact_digit_permutation_on_cuda(backend):
 
 
 def test_random_programs_vs_oracle_on_cuda(backend):
-    """tools/fuzz_emu.py's generator (every measurement mode, resets, barriers, random option sets and
+    """tests/harness/fuzz_emu.py's generator (every measurement mode, resets, barriers, random option sets and
     initial states) on the real kernels: 160 programs with n <= 8, 12 long ones at n = 8..10, and 40
     with randomised scheduler / streaming knobs."""
     import os
     import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "harness"))
     import fuzz_emu
     bad = []
     plan = [(s, 8, 1, 60, False) for s in range(100000, 100160)] + \
@@ -272,7 +272,7 @@ def test_experimental_tile_variant_parity(backend, golden, case_dir, monkeypatch
             if case["n"] >= 6:
                 cases.write_files(case, ".")
                 check_against_golden(golden, name, _run(backend, case["n"], case["instrs"], case["options"], name))
-        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "harness"))
         import fuzz_emu
         bad = [(s, m) for s in range(103000, 103060) for st, m in [fuzz_emu.one(s, 10, 6, 200, False, backend=backend)]
                if st == "FAIL"]

@@ -160,11 +160,11 @@ def test_oracle_matches_live_reference(seed, case_dir):
 
 @pytest.mark.skipif(not R.available(), reason="/root/reference not present (GPU box)")
 def test_oracle_matches_live_reference_on_random_programs():
-    """tools/fuzz_oracle.py: random circuits with every measurement mode (incl. Ensemble along a
+    """tests/harness/fuzz_oracle.py: random circuits with every measurement mode (incl. Ensemble along a
     direction), resets, barriers and random option sets; 3400 seeds agreed to 1e-13 when this
     slice was committed."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_oracle.py"), "--seeds", "120", "--start", "50000"],
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "harness", "fuzz_oracle.py"), "--seeds", "120", "--start", "50000"],
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0 and "'ok': 120" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
