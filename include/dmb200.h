@@ -114,8 +114,9 @@ int dmb_reset_stats(dmb_ctx* ctx);
  *   10 / 11 / 12 = paired kernel: as 8, and ops that leave tile digit 0 free move two 16-blocks per thread with
  *           128-bit shared-memory accesses; 1 stage x 4 / 5 CTAs/SM, 2 stages x 3 CTAs/SM
  *   13 = 10, and the <cos a> factor of a zero-mean TSP CNOT is folded into the control digit's map on the host
- *           (8-13: written in round 1 after the GPU budget ran out -- parity-checked on emulated kernels only,
+ *           (8-14: written in round 1 after the GPU budget ran out -- parity-checked on emulated kernels only,
  *            not yet timed; tools/gpu_half_variants.sh)
+ *   14 = variant 0's algorithm compiled from the policy body the CPU tests run (dm_device.h: dmb_tile_kernel_body)
  *   1 = the generic register-staged kernel (one tile per CTA), kept as A/B baseline. */
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant);
 

@@ -851,6 +851,59 @@ DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass&
 }
 
 // ---------------------------------------------------------------------------------------
+// The default tile kernel's control flow (k_tile_pass6 in dmb200.cu: 256 threads per tile, a ring of STAGES
+// 32 KiB stages per CTA, tiles k+1 .. k+STAGES-1 streaming in while the op run executes on tile k) restated
+// against the execution-context policy of dmb_half_kernel_body below, so that it can run with real host threads
+// in tests/test_kernel_control_flow.py.  On the GPU it is tile variant 14 (k_tile_pass6_policy), NOT the default:
+// it compiles to equivalent but not byte-identical SASS (+0.5 % instructions, other register allocation) and has
+// not been timed; once it has, the hand-written copy in dmb200.cu can go.
+// ---------------------------------------------------------------------------------------
+template <int STAGES, int STMODE, class Ctx>
+DMB_HD void dmb_tile_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L) {
+  dmb_lean_thread T;
+  dmb_lean_thread_init(cx.tid(), L, T);
+  dmb_remote_src none;
+  none.enabled = 0;
+  const uint64_t first = cx.block();
+  if (first >= L.n_tiles) return;
+  const uint64_t stride = cx.grid();
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {          // prologue: tiles 0 .. STAGES-2 of this CTA
+    const uint64_t tl = first + (uint64_t)s * stride;
+    if (tl < L.n_tiles) {
+      const uint64_t tb = dmb_tile_base(tl, L.td, DMB_LEAN_K);
+#pragma unroll
+      for (int i = 0; i < DMB_LEAN_PAIRS; ++i)
+        cx.copy16((uint32_t)s * DMB_LEAN_TILE_BYTES + (T.soff ^ L.pair_soff[i]), state + tb + (T.goff | L.pair_goff[i]));
+    }
+    cx.commit();
+  }
+  uint32_t cur = 0;                       // stage of the tile being processed
+  uint32_t fill = STAGES - 1;             // stage the next prefetch goes to
+  for (uint64_t tile = first; tile < L.n_tiles; tile += stride) {
+    const uint64_t ahead = tile + (uint64_t)(STAGES - 1) * stride;
+    if (ahead < L.n_tiles) {
+      const uint64_t tb = dmb_tile_base(ahead, L.td, DMB_LEAN_K);
+#pragma unroll
+      for (int i = 0; i < DMB_LEAN_PAIRS; ++i)
+        cx.copy16(fill * DMB_LEAN_TILE_BYTES + (T.soff ^ L.pair_soff[i]), state + tb + (T.goff | L.pair_goff[i]));
+    }
+    cx.commit();
+    cx.template wait<STAGES - 1>();
+    cx.sync();
+    const auto mem = cx.mem(cur * DMB_LEAN_TILE_BYTES);
+    for (int i = 0; i < L.n_ops; ++i) {
+      dmb_lean_op_dispatch(T, L.ops[i], mem);
+      cx.sync();
+    }
+    dmb_lean_store_thread<false, STMODE>(T, L, state, dmb_tile_base(tile, L.td, DMB_LEAN_K), none, mem);
+    cx.sync();
+    cur = (cur + 1 == STAGES) ? 0 : cur + 1;
+    fill = (fill + 1 == STAGES) ? 0 : fill + 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Body of the half-CTA / paired tile kernel (k_tile_pass6_half in dmb200.cu, tile variants 8-12), written
 // against an execution-context policy so that the SAME control flow -- tile loop, stage ring, asynchronous
 // staging, barriers -- runs on the GPU and, with real host threads, in the CPU tests (tests/emu).

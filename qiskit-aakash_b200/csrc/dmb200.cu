@@ -216,6 +216,17 @@ k_tile_pass6_half(double* __restrict__ state, const __grid_constant__ dmb_lean_p
   dmb_half_kernel_body<STMODE, PAIRED, STAGES>(cx, state, L);
 }
 
+// Tile variant 14: the default kernel's control flow through the policy body (dm_device.h), for an A/B against
+// the hand-written k_tile_pass6 above -- same algorithm, compiled from the function the CPU tests run.
+template <int STAGES, int CTAS, int STMODE>
+__global__ void __launch_bounds__(DMB_TILE_THREADS, CTAS)
+k_tile_pass6_policy(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L) {
+  extern __shared__ __align__(128) unsigned char lean_smem[];
+  dmb_cuda_cta cx;
+  cx.smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
+  dmb_tile_kernel_body<STAGES, STMODE>(cx, state, L);
+}
+
 // ---------------------------------------------------------------------------------------
 // tile pass, K = 6, three digits per thread (R3): 64 threads per tile, each phase keeps a
 // digit triple's 64 coefficients in registers and runs all ops inside the triple back to
@@ -405,6 +416,21 @@ static int launch_half(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
   return 0;
 }
 
+template <int STMODE>
+static int launch_policy(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
+  const size_t smem = 2 * DMB_LEAN_TILE_BYTES;
+  static std::atomic<uint64_t> attr_done{0};
+  if (!((attr_done.load() >> (ctx->device & 63)) & 1ull)) {
+    CU_TRY(cudaFuncSetAttribute(k_tile_pass6_policy<2, 3, STMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done.fetch_or(1ull << (ctx->device & 63));
+  }
+  uint64_t grid = (uint64_t)ctx->sm_count * 3;
+  if (grid > L.n_tiles) grid = L.n_tiles;
+  k_tile_pass6_policy<2, 3, STMODE><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, L);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
 template <int CTAS, bool PAIRED, int STAGES = 1>
 static int launch_half_any(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
   if (L.st_mode == DMB_ST_PERM128) return launch_half<CTAS, DMB_ST_PERM128, PAIRED, STAGES>(ctx, state, L);
@@ -449,6 +475,10 @@ static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_
     case 10: return launch_half_any<4, true>(ctx, state, L);
     case 11: return launch_half_any<5, true>(ctx, state, L);
     case 12: return launch_half_any<3, true, 2>(ctx, state, L);
+    case 14:
+      if (L.st_mode == DMB_ST_PERM128) return launch_policy<DMB_ST_PERM128>(ctx, state, L);
+      if (L.st_mode == DMB_ST_SPLIT64) return launch_policy<DMB_ST_SPLIT64>(ctx, state, L);
+      return launch_policy<DMB_ST_PLAIN>(ctx, state, L);
     case 13: return launch_half_any<4, true>(ctx, state, L);      // 10 + TSP0 factor folded into the control map
     default:
       if (L.st_mode == DMB_ST_PERM128) return launch_lean<2, 3, 0, DMB_ST_PERM128>(ctx, state, L);
@@ -573,7 +603,7 @@ int dmb_reset_stats(dmb_ctx* ctx) {
 
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant) {
   if (!ctx) return fail("dmb_set_tile_variant", "null context");
-  if (variant < 0 || variant > 13) return fail("dmb_set_tile_variant", "variant must be 0..13");
+  if (variant < 0 || variant > 14) return fail("dmb_set_tile_variant", "variant must be 0..14");
   ctx->tile_variant = variant;
   return 0;
 }

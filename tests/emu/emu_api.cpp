@@ -164,6 +164,44 @@ struct emu_cta_thread {
   }
 };
 
+template <int STMODE, int STAGES>
+static void run_default_kernel_cta(double* state, const dmb_lean_pass& L, uint64_t block, uint64_t grid) {
+  std::vector<unsigned char> stages((size_t)STAGES * DMB_LEAN_TILE_BYTES + 128);
+  unsigned char* base = stages.data() + (128 - (reinterpret_cast<uintptr_t>(stages.data()) & 127)) % 128;
+  emu_barrier bar(DMB_TILE_THREADS);
+  std::vector<std::thread> threads;
+  for (int t = 0; t < DMB_TILE_THREADS; ++t)
+    threads.emplace_back([&, t] {
+      emu_cta_thread cx;
+      cx.tid_ = t; cx.block_ = block; cx.grid_ = grid; cx.stages = base; cx.bar = &bar;
+      dmb_tile_kernel_body<STAGES, STMODE>(cx, state, L);
+    });
+  for (auto& th : threads) th.join();
+}
+
+// test hook: the default kernel's control flow (256 threads per CTA, STAGES-deep ring) on host threads
+extern "C" int dmb_emu_run_default_kernel(double* state, int n_bits, const dmb_pass* passes, size_t n_passes, int stages,
+                                          int grid) {
+  static thread_local dmb_lean_pass L;
+  for (size_t i = 0; i < n_passes; ++i) {
+    if (passes[i].n_tile_digits != DMB_LEAN_K || dmb_pass_has_post_swap(passes[i])) return 1;
+    dmb_make_lean_pass(passes[i], n_bits, L, dmb_fold_swaps_enabled());
+    const uint64_t g = (uint64_t)grid < L.n_tiles ? (uint64_t)grid : L.n_tiles;
+    for (uint64_t block = 0; block < g; ++block) {
+      if (stages == 3) {
+        if (L.st_mode == DMB_ST_PERM128) run_default_kernel_cta<DMB_ST_PERM128, 3>(state, L, block, g);
+        else if (L.st_mode == DMB_ST_SPLIT64) run_default_kernel_cta<DMB_ST_SPLIT64, 3>(state, L, block, g);
+        else run_default_kernel_cta<DMB_ST_PLAIN, 3>(state, L, block, g);
+      } else {
+        if (L.st_mode == DMB_ST_PERM128) run_default_kernel_cta<DMB_ST_PERM128, 2>(state, L, block, g);
+        else if (L.st_mode == DMB_ST_SPLIT64) run_default_kernel_cta<DMB_ST_SPLIT64, 2>(state, L, block, g);
+        else run_default_kernel_cta<DMB_ST_PLAIN, 2>(state, L, block, g);
+      }
+    }
+  }
+  return 0;
+}
+
 template <int STMODE, bool PAIRED, int STAGES>
 static void run_half_kernel_cta(double* state, const dmb_lean_pass& L, uint64_t block, uint64_t grid) {
   std::vector<unsigned char> stages((size_t)STAGES * DMB_LEAN_TILE_BYTES + 128);
@@ -277,7 +315,7 @@ int dmb_sync(dmb_ctx*) { return 0; }
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out) { *out = ctx->stats; return 0; }
 int dmb_reset_stats(dmb_ctx* ctx) { memset(&ctx->stats, 0, sizeof(dmb_stats)); return 0; }
 int dmb_set_tile_variant(dmb_ctx*, int variant) {
-  if (variant < 0 || variant > 13) return fail("dmb_set_tile_variant", "variant must be 0..13");
+  if (variant < 0 || variant > 14) return fail("dmb_set_tile_variant", "variant must be 0..14");
   g_variant = variant;
   return 0;
 }

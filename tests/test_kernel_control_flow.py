@@ -50,3 +50,23 @@ def test_threaded_kernel_body_equals_sequential_emulation(paired, stages, grid):
     assert rc == 0
     assert np.array_equal(got, want)
     assert not np.array_equal(got, start)
+
+
+@pytest.mark.parametrize("stages,grid", [(2, 3), (2, 1), (3, 2), (2, 7)])
+def test_default_kernel_control_flow_on_host_threads(stages, grid):
+    """``dmb_tile_kernel_body``: the default kernel's tile loop / STAGES-deep prefetch ring / barriers, 256 host threads
+    per CTA (on the GPU this body is tile variant 14; the shipped default is its hand-written twin in dmb200.cu)."""
+    n = 8
+    P = _passes(n, 6, 90 + stages, 8)
+    lib = emu_lib()
+    raw = ctypes.CDLL(lib._name)
+    start = np.random.default_rng(11).standard_normal(4 ** n)
+    want = start.copy()
+    ctx = capi.Context(lib, 0)
+    ctx.set_tile_variant(0)
+    ctx.apply_passes(want.ctypes.data, 2 * n, P)
+    got = start.copy()
+    rc = raw.dmb_emu_run_default_kernel(ctypes.c_void_p(got.ctypes.data), ctypes.c_int(2 * n), P.ctypes.data_as(ctypes.c_void_p),
+                                        ctypes.c_size_t(len(P)), ctypes.c_int(stages), ctypes.c_int(grid))
+    assert rc == 0
+    assert np.array_equal(got, want)

@@ -5,13 +5,13 @@
 # 2. bench A/B in one session: default (0) vs 8 / 9 (half-CTA, 6 / 5 CTAs x 128 threads) vs 10 / 11 / 12 (paired bodies: 4 / 5 CTAs x 1 stage, 3 CTAs x 2 stages; 13 = 10 + TSP factor folded into the control map)
 mkdir -p gpurun_out
 T0=$SECONDS
-for v in 8 10 12 13; do
+for v in 8 10 12 13 14; do
   echo "== parity, variant $v"
   DMB_TEST_TILE_VARIANT=$v timeout 200 python -m pytest tests/test_gpu_parity.py -x -q -k "experimental_tile_variant" > gpurun_out/half_parity_$v.log 2>&1
   echo "rc=$? t=$((SECONDS-T0))"; tail -2 gpurun_out/half_parity_$v.log
 done
 : > gpurun_out/half_variants.jsonl
-for v in 0 8 9 10 11 12 13 0 8 10 13; do
+for v in 0 14 8 9 10 11 12 13 0 14 8 10 13; do
   DMB_TILE_VARIANT=$v timeout 90 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2> gpurun_out/half_variant_$v.err | \
     python -c "import sys, json; d = json.loads(sys.stdin.read()); print(json.dumps({'variant': $v, 'ms_per_step': d['ms_per_step'], 'avg_launch_ms': d['roofline']['avg_launch_ms'], 'passes': d['config']['passes_per_step'], 'clocks': d['clocks']}))" >> gpurun_out/half_variants.jsonl
   tail -1 gpurun_out/half_variants.jsonl
