@@ -346,6 +346,7 @@ def run_ours(args):
                            "levels": runner.n_levels, "state_bytes": state_bytes,
                            "passes_per_step": counters["tile_pass_launches"] / args.steps,
                            "scheduler": sched_desc,
+                           "tile_variant": int(os.environ.get("DMB_TILE_VARIANT", "0") or 0),
                            "l2": "state (%.1f GiB/GPU) >> 126 MB L2, no flush needed" % (state_bytes / world / 2 ** 30),
                            "parallelism": "1 GPU" if world == 1 else "%d GPUs, high-order Pauli digits sharded" % world}),
                 "circuit_ms": ms_step, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
