@@ -240,3 +240,12 @@ def test_sharded_final_moves_with_tile_search():
                                            native=True, strategy=capi.SCHED_TILE_SEARCH)
     _replay(passes, qops, pos0, pos, n_loc)
     assert [tuple(x) for x in left] == [(q, t) for q, t in moves if pos[q] != t]
+
+
+def test_random_streams_caps_and_cut_points_give_valid_schedules():
+    """Slice of tests/harness/fuzz_schedule.py (5 000 cases clean): n up to 20, both strategies, streamed or one-shot."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "harness"))
+    import fuzz_schedule
+    assert fuzz_schedule.run(9000, 9150) == 0
