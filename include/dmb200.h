@@ -27,7 +27,9 @@
 extern "C" {
 #endif
 
-#define DMB_ABI_VERSION 3   /* 2: dmb_stats.folded_swaps; 3: dmb_schedule */
+#define DMB_ABI_VERSION 4   /* 2: dmb_stats.folded_swaps; 3: dmb_schedule; 4: dmb_op.post_swap and
+                               dmb_stats.r3_phases removed (measured slower, round 2), dmb_ipc_close,
+                               dmb_graph_*, dmb_tile_ring */
 #define DMB_MAX_TILE_DIGITS 6   /* a tile holds 4^6 = 4096 doubles = 32 KiB of shared memory */
 #define DMB_MAX_OPS 16          /* fused ops per tile pass */
 #define DMB_MAX_QUBITS 32
@@ -62,10 +64,7 @@ typedef struct dmb_op {
   int8_t a, b;      /* tile-local digit indices (indices into dmb_pass.tile_digit), a != b */
   int8_t fd[4];     /* the other tile-local digits, in the order thread-index bit pairs are
                        dealt to them (chosen by the host for conflict-free shared memory)  */
-  int8_t post_swap; /* 0 none; after the op exchange tile digit `post_swap_with` with digit a (1)
-                       or digit b (2), or exchange a and b (3): a layout remap attached to the
-                       op (executed by the library as a DMB_OP_SWAP right after it)          */
-  int8_t post_swap_with;
+  int8_t reserved_[2]; /* must be 0 */
   double pa[12];    /* rows 1..3 of the matrix on digit a, row-major [3][4]                */
   double pb[12];    /* rows 1..3 of the matrix on digit b                                  */
   double coef[16];
@@ -87,7 +86,6 @@ typedef struct dmb_stats {
   uint64_t other_launches;       /* every other kernel of this library                     */
   uint64_t fused_ops;            /* dmb_op entries executed                                */
   uint64_t state_bytes_moved;    /* algorithmic HBM bytes of tile passes: 16 B x elements  */
-  uint64_t r3_phases;            /* register phases executed by the 3-digits-per-thread kernel */
   uint64_t folded_swaps;         /* trailing SWAP ops realised by the relabelling write-back instead */
 } dmb_stats;
 
@@ -104,20 +102,11 @@ int dmb_set_stream(dmb_ctx* ctx, void* cuda_stream);
 int dmb_sync(dmb_ctx* ctx);                                   /* synchronous */
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out);
 int dmb_reset_stats(dmb_ctx* ctx);
-/* Tile-kernel variant for 4^6-coefficient tiles:
- *   0 = two digits per thread, persistent cp.async kernel, 2 stages x 3 CTAs/SM
- *   2 / 3 = same with 3 stages x 2 CTAs/SM / 2 stages x 2 CTAs/SM
- *   4 / 5 = three digits per thread (ops grouped into register phases), 2 stages x 3 CTAs/SM /
- *           1 stage x 4 CTAs/SM
- *   6 / 7 = two digits per thread without prefetch ring, 1 stage x 4 / 5 CTAs/SM
- *   8 / 9 = half-CTA kernel: 128 threads per tile (each plays two of variant 0's threads), 1 stage x 6 / 5 CTAs/SM
- *   10 / 11 / 12 = paired kernel: as 8, and ops that leave tile digit 0 free move two 16-blocks per thread with
- *           128-bit shared-memory accesses; 1 stage x 4 / 5 CTAs/SM, 2 stages x 3 CTAs/SM
- *   13 = 10, and the <cos a> factor of a zero-mean TSP CNOT is folded into the control digit's map on the host
- *           (8-14: written in round 1 after the GPU budget ran out -- parity-checked on emulated kernels only,
- *            not yet timed; tools/gpu_half_variants.sh)
- *   14 = variant 0's algorithm compiled from the policy body the CPU tests run (dm_device.h: dmb_tile_kernel_body)
- *   1 = the generic register-staged kernel (one tile per CTA), kept as A/B baseline. */
+/* Tile-kernel variant for 4^6-coefficient tiles (A/B switch for measurements, not a feature):
+ *   0 = the shipped kernel k_tile_pass6: 128 threads per tile, one 32 KiB cp.async stage per CTA, 5 CTAs per SM;
+ *       ops that leave tile digit 0 free move two 16-blocks per thread with 128-bit shared-memory accesses
+ *   1 = the generic register-staged kernel k_tile_pass<6> (one tile per CTA iteration), the A/B baseline
+ *   2 / 3 = variant 0 with 4 / 6 CTAs per SM. */
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant);
 
 /* ---- state initialisation (replaces DmSimulatorPy._initialize_densitymatrix,
@@ -192,7 +181,8 @@ int dmb_schedule(const dmb_qop* ops, size_t n_ops, int32_t* pos, int n_qubits, i
  * with n_ops == 0 is a pure exchange.  All ranks must have finished writing their old buffers
  * (host barrier) before the call, and must not overwrite them until every rank has finished.
  * dmb_ipc_export / dmb_ipc_open turn a device pointer of one process into a mapped pointer of
- * another (cudaIpcGetMemHandle / cudaIpcOpenMemHandle; mappings live until process exit).
+ * another (cudaIpcGetMemHandle / cudaIpcOpenMemHandle).  Mappings are reference counted per handle:
+ * every dmb_ipc_open is paired with one dmb_ipc_close, the last close unmaps the peer allocation.
  * push != 0 selects the mirror image: the pass runs in place on `dst_state` (this rank's
  * current buffer, old layout) and STORES every tile to  (double*)src_tab[idx >> block_shift] + idx,
  * i.e. into the buffers of the ranks that own the data after the swap (remote stores). */
@@ -200,6 +190,7 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
                           const uint64_t* src_tab, int tab_bits, int block_shift, int push);
 int dmb_ipc_export(dmb_ctx* ctx, const void* dev_ptr, unsigned char* handle64, uint64_t* offset);
 int dmb_ipc_open(dmb_ctx* ctx, const unsigned char* handle64, uint64_t offset, void** out_ptr);
+int dmb_ipc_close(dmb_ctx* ctx, const unsigned char* handle64);
 
 /* ---- readout ------------------------------------------------------------------------
  * I/B-marginal of _add_ensemble_measure (:427-481) for basis X/Y/Z: for c in [0,2^n_qubits)

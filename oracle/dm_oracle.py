@@ -53,7 +53,24 @@ def as_instruction(ins):
     for key in ("memory", "register"):
         if key in d:
             setattr(ns, key, list(d[key]))
+    if d.get("conditional") is not None:
+        ns.conditional = copy.deepcopy(d["conditional"])
     return ns
+
+
+def conditional_skips(op):
+    """``dm_simulator.py:1020-1034``: an instruction with an int ``conditional`` runs only when that bit of the
+    classical register is set, one with a mask / val ``conditional`` only when the masked classical memory equals
+    val.  Neither is ever written on this path (measurements do not record outcomes, and the ``bfunc`` that would
+    set a register bit cannot pass the partitioner, ``basicaertools.py:549``), so both stay 0: an int conditional
+    always skips, a mask conditional skips unless val == 0."""
+    cond = getattr(op, "conditional", None)
+    if isinstance(cond, int):
+        return True
+    if cond is not None:
+        if int(cond.mask, 16) > 0 and int(cond.val, 16) != 0:
+            return True
+    return False
 
 
 # --------------------------------------------------------------------------------------
@@ -612,6 +629,8 @@ class OracleSim:
                         continue
             it = iter(_LiveIter(level))
             for op in it:
+                if conditional_skips(op):
+                    continue
                 if op.name in ("u1", "u3"):
                     self.single_gate(op.name, op.params, op.qubits[0])
                 elif op.name == "cx":

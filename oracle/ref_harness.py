@@ -138,6 +138,8 @@ def to_reference_instructions(instrs):
             ns.memory = list(d["memory"])
         if "register" in d:
             ns.register = list(d["register"])
+        if d.get("conditional") is not None:
+            ns.conditional = copy.deepcopy(d["conditional"])
         out.append(ns)
     return out
 

@@ -20,7 +20,7 @@ OP_MATS, OP_CX, OP_CX_TSP, OP_DIAG2, OP_SWAP = 0, 1, 2, 3, 4
 HAS_PA, HAS_PB = 1, 2
 
 OP_DTYPE = np.dtype([("kind", "<i4"), ("flags", "<i4"), ("a", "i1"), ("b", "i1"), ("fd", "i1", (4,)),
-                     ("post_swap", "i1"), ("post_swap_with", "i1"), ("pa", "<f8", (12,)), ("pb", "<f8", (12,)),
+                     ("reserved_", "i1", (2,)), ("pa", "<f8", (12,)), ("pb", "<f8", (12,)),
                      ("coef", "<f8", (16,))])
 PASS_DTYPE = np.dtype([("n_tile_digits", "<i4"), ("n_ops", "<i4"), ("tile_digit", "<i4", (MAX_TILE_DIGITS,)),
                        ("ops", OP_DTYPE, (MAX_OPS,))])
@@ -29,13 +29,13 @@ PASS_DTYPE = np.dtype([("n_tile_digits", "<i4"), ("n_ops", "<i4"), ("tile_digit"
 QOP_DTYPE = np.dtype([("kind", "<i4"), ("flags", "<i4"), ("qa", "<i4"), ("qb", "<i4"), ("pa", "<f8", (12,)),
                       ("pb", "<f8", (12,)), ("coef", "<f8", (16,))])
 
-ABI_VERSION = 3          # include/dmb200.h DMB_ABI_VERSION
+ABI_VERSION = 4          # include/dmb200.h DMB_ABI_VERSION
 
 
 class Stats(ctypes.Structure):
     _fields_ = [("tile_pass_launches", ctypes.c_uint64), ("other_launches", ctypes.c_uint64),
                 ("fused_ops", ctypes.c_uint64), ("state_bytes_moved", ctypes.c_uint64),
-                ("r3_phases", ctypes.c_uint64), ("folded_swaps", ctypes.c_uint64)]
+                ("folded_swaps", ctypes.c_uint64)]
 
 
 class DmbError(RuntimeError):
@@ -66,6 +66,7 @@ _SIGNATURES = {
     "dmb_apply_pass_remote": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i]),
     "dmb_ipc_export": (_i, [_vp, _vp, _vp, _vp]),
     "dmb_ipc_open": (_i, [_vp, _vp, _u64, _vp]),
+    "dmb_ipc_close": (_i, [_vp, _vp]),
     "dmb_marginal": (_i, [_vp, _vp, _i, _u64, _i, _vp, _vp, _vp, _vp]),
     "dmb_fwht": (_i, [_vp, _vp, _i]),
     "dmb_contract_digit": (_i, [_vp, _vp, _vp, _u64, _u64, _vp]),
@@ -218,6 +219,10 @@ class Context:
         out = ctypes.c_void_p()
         self._check(self.lib.dmb_ipc_open(self._h, buf, int(offset), ctypes.byref(out)))
         return int(out.value)
+
+    def ipc_close(self, handle):
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self.lib.dmb_ipc_close(self._h, buf))
 
     def marginal(self, state_ptr, n_bits, rank_bits, hi, lo, wt, out_ptr):
         hi = np.ascontiguousarray(hi, dtype=np.int32)

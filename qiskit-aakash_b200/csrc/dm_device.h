@@ -346,7 +346,7 @@ DMB_HD uint32_t dmb_st_source(uint32_t l2, const int32_t* perm) {
 // code (no flag branches, no register moves at control-flow merges: 302 -> ~190 issued
 // instructions per op); everything else runs the generic body.
 #define DMB_KIND_TSP0 5
-#define DMB_KIND_TSP0F 6      // TSP0 whose <cos a> factor was folded into rows 1-2 of the control digit's map (paired kernel only)
+#define DMB_KIND_TSP0F 6      // TSP0 whose <cos a> factor was folded into rows 1-2 of the control digit's map (paired body only)
 DMB_HD int dmb_variant_id(int kindx, int ma, int mb, int mode) { return ((kindx * 3 + ma) * 3 + mb) * 3 + mode; }
 inline bool dmb_variant_is_specialised(int kindx, int ma, int mb) {
   if (ma == mb && (ma == 1 || ma == 2))
@@ -420,8 +420,7 @@ inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, 
   for (int j = 0; j < DMB_LEAN_K; ++j) dest[j] = j;
   if (fold_swaps) {
     int first = P.n_ops;
-    while (first > 0 && P.ops[first - 1].kind == DMB_OP_SWAP && (P.ops[first - 1].flags & (DMB_HAS_PA | DMB_HAS_PB)) == 0 &&
-           P.ops[first - 1].post_swap == 0)
+    while (first > 0 && P.ops[first - 1].kind == DMB_OP_SWAP && (P.ops[first - 1].flags & (DMB_HAS_PA | DMB_HAS_PB)) == 0)
       --first;
     for (int k = first; k < P.n_ops; ++k) {
       const int a = P.ops[k].a, b = P.ops[k].b;
@@ -467,9 +466,9 @@ inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, 
     q.variant = dmb_variant_is_specialised(kx, ma, mb) ? dmb_variant_id(kx, ma, mb, q.mode) : -1;
     // thread digit 0 sits on tile digit 0: virtual threads 2u and 2u+1 own the two halves of every 16-byte pair
     if (q.mode == DMB_MODE_A && o.fd[0] == 0) q.flags |= DMB_PAIRABLE;
-    // Tile variant 13: the zero-mean TSP CNOT scales the eight X/Y-on-control entries by <cos a> after permuting
-    // them among themselves, so the factor moves into rows 1-2 of the control digit's map (8 FP64 fewer per
-    // block).  Only for ops the paired body runs -- no other kernel knows the folded kind.
+    // The zero-mean TSP CNOT scales the eight X/Y-on-control entries by <cos a> after permuting them among
+    // themselves, so the factor moves into rows 1-2 of the control digit's map (8 FP64 fewer per block, exact up
+    // to one rounding).  Only for ops the paired body runs -- no other body knows the folded kind.
     if (fold_tsp0 && kx == DMB_KIND_TSP0 && (q.flags & DMB_PAIRABLE) && ma == mb && ma != 0) {
       for (int i = 0; i < 8; ++i) q.pa[i] *= q.coef[0];
       q.variant = dmb_variant_id(DMB_KIND_TSP0F, ma, mb, q.mode);
@@ -638,7 +637,7 @@ DMB_HD void dmb_spec_math(const dmb_lean_op& op, double (&v)[4][4]) {
   }
 }
 
-// PAIRED op body (tile variants 10/11): one real thread plays the virtual threads 2u and 2u+1 of an op in
+// PAIRED op body: one real thread plays the virtual threads 2u and 2u+1 of an op in
 // access mode A (tile digit 0 free).  Their 16-blocks differ only in the low bit of digit 0, i.e. they are
 // the two halves of the same sixteen 16-byte pairs: 16 LDS.128 + 16 STS.128 move both blocks (instead of
 // 2 x 16 LDS.64 + 2 x 16 STS.64), with one address computation per pair.  T is the EVEN virtual thread.
@@ -851,92 +850,43 @@ DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass&
 }
 
 // ---------------------------------------------------------------------------------------
-// The default tile kernel's control flow (k_tile_pass6 in dmb200.cu: 256 threads per tile, a ring of STAGES
-// 32 KiB stages per CTA, tiles k+1 .. k+STAGES-1 streaming in while the op run executes on tile k) restated
-// against the execution-context policy of dmb_half_kernel_body below, so that it can run with real host threads
-// in tests/test_kernel_control_flow.py.  On the GPU it is tile variant 14 (k_tile_pass6_policy), NOT the default:
-// it compiles to equivalent but not byte-identical SASS (+0.5 % instructions, other register allocation) and has
-// not been timed; once it has, the hand-written copy in dmb200.cu can go.
-// ---------------------------------------------------------------------------------------
-template <int STAGES, int STMODE, class Ctx>
-DMB_HD void dmb_tile_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L) {
-  dmb_lean_thread T;
-  dmb_lean_thread_init(cx.tid(), L, T);
-  dmb_remote_src none;
-  none.enabled = 0;
-  const uint64_t first = cx.block();
-  if (first >= L.n_tiles) return;
-  const uint64_t stride = cx.grid();
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {          // prologue: tiles 0 .. STAGES-2 of this CTA
-    const uint64_t tl = first + (uint64_t)s * stride;
-    if (tl < L.n_tiles) {
-      const uint64_t tb = dmb_tile_base(tl, L.td, DMB_LEAN_K);
-#pragma unroll
-      for (int i = 0; i < DMB_LEAN_PAIRS; ++i)
-        cx.copy16((uint32_t)s * DMB_LEAN_TILE_BYTES + (T.soff ^ L.pair_soff[i]), state + tb + (T.goff | L.pair_goff[i]));
-    }
-    cx.commit();
-  }
-  uint32_t cur = 0;                       // stage of the tile being processed
-  uint32_t fill = STAGES - 1;             // stage the next prefetch goes to
-  for (uint64_t tile = first; tile < L.n_tiles; tile += stride) {
-    const uint64_t ahead = tile + (uint64_t)(STAGES - 1) * stride;
-    if (ahead < L.n_tiles) {
-      const uint64_t tb = dmb_tile_base(ahead, L.td, DMB_LEAN_K);
-#pragma unroll
-      for (int i = 0; i < DMB_LEAN_PAIRS; ++i)
-        cx.copy16(fill * DMB_LEAN_TILE_BYTES + (T.soff ^ L.pair_soff[i]), state + tb + (T.goff | L.pair_goff[i]));
-    }
-    cx.commit();
-    cx.template wait<STAGES - 1>();
-    cx.sync();
-    const auto mem = cx.mem(cur * DMB_LEAN_TILE_BYTES);
-    for (int i = 0; i < L.n_ops; ++i) {
-      dmb_lean_op_dispatch(T, L.ops[i], mem);
-      cx.sync();
-    }
-    dmb_lean_store_thread<false, STMODE>(T, L, state, dmb_tile_base(tile, L.td, DMB_LEAN_K), none, mem);
-    cx.sync();
-    cur = (cur + 1 == STAGES) ? 0 : cur + 1;
-    fill = (fill + 1 == STAGES) ? 0 : fill + 1;
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// Body of the half-CTA / paired tile kernel (k_tile_pass6_half in dmb200.cu, tile variants 8-12), written
-// against an execution-context policy so that the SAME control flow -- tile loop, stage ring, asynchronous
-// staging, barriers -- runs on the GPU and, with real host threads, in the CPU tests (tests/emu).
+// Body of the tile kernel (k_tile_pass6 in dmb200.cu), written against an execution-context policy so that the
+// SAME control flow -- tile loop, stage ring, asynchronous staging, barriers -- runs on the GPU and, with real host
+// threads, in the CPU tests (tests/emu).
 //   Ctx: tid() / block() / grid()       thread index in the CTA (0..127), CTA index, number of CTAs
 //        copy16(stage byte offset, src) asynchronous 16-byte copy global -> stage memory (cp.async)
 //        commit() / wait<N>()           close the current copy group / wait for all but the N newest groups
 //        sync()                         CTA barrier
 //        mem(stage byte offset)         accessor (ld64 / ld128 / st64 / st128) of a stage
-// STAGES = 1: load, wait, ops, store per tile (the other CTAs of the SM hide the latency); STAGES = 2: the
-// next tile of this CTA streams in during the op phase.
+// 128 threads per 4096-coefficient tile.  Staging (tile load / write-back) and ops that touch tile digit 0 walk the
+// tile as virtual threads u and u + 128; ops that leave tile digit 0 free (PAIRED) run as virtual threads 2u / 2u + 1,
+// whose two 16-blocks are the halves of the same sixteen 16-byte pairs (dmb_lean_op_pair).
+// STAGES = 1: load, wait, ops, store per tile (the other CTAs of the SM hide the latency; what ships: 5 CTAs per
+// SM); STAGES = 2: the next tile of this CTA streams in during the op phase (measured slower on B200, kept for the
+// CPU control-flow test of the ring).
+// REMOTE (fused exchange, distributed.py): 0 in place; 1 "pull": pair idx of the tile is loaded from the peer buffer
+// R.tab[idx >> R.shift] that holds it in the old layout; 2 "push": the write-back goes to the peer that owns idx.
 // ---------------------------------------------------------------------------------------
 #define DMB_HALF_THREADS 128
-template <int STMODE, bool PAIRED, int STAGES, class Ctx>
-DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L) {
-  // staging (tile load / write-back) walks the tile as virtual threads u and u + 128: consecutive lanes touch
-  // consecutive 16-byte chunks (conflict-free, whole 128-byte lines per quarter-warp)
+template <int STMODE, bool PAIRED, int STAGES, int REMOTE, class Ctx>
+DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L, const dmb_remote_src& R) {
   dmb_lean_thread S0, S1;
   dmb_lean_thread_init(cx.tid(), L, S0);
   dmb_lean_thread_init(cx.tid() + DMB_HALF_THREADS, L, S1);
-  // op phase: the same two virtual threads; PAIRED: mode-A ops run as virtual threads 2u / 2u + 1 instead
-  // (dmb_lean_op_dispatch_pair) -- only P0's index digits are used
-  dmb_lean_thread P0;
+  dmb_lean_thread P0;                                   // PAIRED: virtual thread 2u (only its index digits are used)
   dmb_lean_thread_init(2 * cx.tid(), L, P0);
-  dmb_remote_src none;
-  none.enabled = 0;
   const uint64_t first = cx.block(), stride = cx.grid();
   if (first >= L.n_tiles) return;
+  auto src_of = [&](uint64_t idx) -> const double* {
+    if (REMOTE == 1) return reinterpret_cast<const double*>(R.tab[idx >> R.shift]) + idx;
+    return state + idx;
+  };
   if (STAGES == 2) {
     const uint64_t tb = dmb_tile_base(first, L.td, DMB_LEAN_K);
 #pragma unroll
     for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
-      cx.copy16(S0.soff ^ L.pair_soff[i], state + tb + (S0.goff | L.pair_goff[i]));
-      cx.copy16(S1.soff ^ L.pair_soff[i], state + tb + (S1.goff | L.pair_goff[i]));
+      cx.copy16(S0.soff ^ L.pair_soff[i], src_of(tb + (S0.goff | L.pair_goff[i])));
+      cx.copy16(S1.soff ^ L.pair_soff[i], src_of(tb + (S1.goff | L.pair_goff[i])));
     }
     cx.commit();
   }
@@ -948,8 +898,8 @@ DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L)
       const uint32_t dst = (STAGES == 2 ? (cur ^ 1u) : 0u) * DMB_LEAN_TILE_BYTES;
 #pragma unroll
       for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
-        cx.copy16(dst + (S0.soff ^ L.pair_soff[i]), state + tb + (S0.goff | L.pair_goff[i]));
-        cx.copy16(dst + (S1.soff ^ L.pair_soff[i]), state + tb + (S1.goff | L.pair_goff[i]));
+        cx.copy16(dst + (S0.soff ^ L.pair_soff[i]), src_of(tb + (S0.goff | L.pair_goff[i])));
+        cx.copy16(dst + (S1.soff ^ L.pair_soff[i]), src_of(tb + (S1.goff | L.pair_goff[i])));
       }
     }
     cx.commit();
@@ -962,377 +912,11 @@ DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L)
       cx.sync();
     }
     const uint64_t tb = dmb_tile_base(tile, L.td, DMB_LEAN_K);
-    dmb_lean_store_thread<false, STMODE>(S0, L, state, tb, none, mem);
-    dmb_lean_store_thread<false, STMODE>(S1, L, state, tb, none, mem);
+    dmb_lean_store_thread<REMOTE == 2, STMODE>(S0, L, state, tb, R, mem);
+    dmb_lean_store_thread<REMOTE == 2, STMODE>(S1, L, state, tb, R, mem);
     cx.sync();
     if (STAGES == 2) cur ^= 1u;
   }
-}
-
-// A pass whose ops carry post_swap is run by materialising the remap as explicit DMB_OP_SWAP ops.  Returns the number of
-// passes written to out[0..1] (the expanded op list can exceed DMB_MAX_OPS).
-inline int dmb_expand_post_swaps(const dmb_pass& P, dmb_pass* out) {
-  dmb_op list[2 * DMB_MAX_OPS];
-  int n = 0;
-  const int K = P.n_tile_digits;
-  for (int k = 0; k < P.n_ops; ++k) {
-    list[n] = P.ops[k];
-    list[n].post_swap = 0;
-    list[n].post_swap_with = 0;
-    ++n;
-    const int ps = P.ops[k].post_swap;
-    if (ps == 0) continue;
-    dmb_op sw;
-    memset(&sw, 0, sizeof(sw));
-    sw.kind = DMB_OP_SWAP;
-    sw.a = (ps == 2) ? P.ops[k].b : P.ops[k].a;
-    sw.b = (ps == 3) ? P.ops[k].b : P.ops[k].post_swap_with;
-    int w = 0;
-    for (int d = 0; d < K; ++d) if (d != sw.a && d != sw.b && w < 4) sw.fd[w++] = (int8_t)d;
-    list[n++] = sw;
-  }
-  int n_out = 0;
-  for (int start = 0; start < n || n_out == 0; start += DMB_MAX_OPS) {
-    dmb_pass& Q = out[n_out++];
-    Q = P;
-    Q.n_ops = (n - start) < DMB_MAX_OPS ? (n - start) : DMB_MAX_OPS;
-    if (Q.n_ops < 0) Q.n_ops = 0;
-    for (int k = 0; k < Q.n_ops; ++k) Q.ops[k] = list[start + k];
-    if (start + DMB_MAX_OPS >= n) break;
-  }
-  return n_out;
-}
-
-inline bool dmb_pass_has_post_swap(const dmb_pass& P) {
-  for (int k = 0; k < P.n_ops; ++k) if (P.ops[k].post_swap) return true;
-  return false;
-}
-
-// ---------------------------------------------------------------------------------------
-// R3 path: three digits per thread (k_tile_pass_r3 in dmb200.cu)
-// ---------------------------------------------------------------------------------------
-// With two digits per thread every fused op costs one shared-memory round trip of the whole
-// tile (64 KiB at 128 B/clk/SM = 512 clk per tile and op) -- measured: a pure permutation op
-// costs 0.13 ms at n = 14, the op phase is shared-memory-bandwidth bound.  Here a thread owns
-// the 64 coefficients spanned by a digit TRIPLE, so all ops whose digits lie inside the triple
-// run back to back in registers ("phase") between one load and one store of the tile.  The
-// library groups the ops of a pass into phases on the host (dmb_make_r3_pass: dependency-aware
-// greedy over the 20 triples of the 6 tile digits) and flattens them into micro-ops:
-//   MAT(dim, m)      rows 1..3 of a single-qubit map along one of the thread's three dims
-//   CX / TSP0 / TSP / DIAG2 / SWAP (dimP, dimQ)   the two-digit kernels on an ordered dim pair
-// 64 threads per tile (2 warps); same swizzled layout and staging as the lean path.
-#define DMB_R3_THREADS 64
-#define DMB_R3_MAX_MICRO 48
-#define DMB_R3_MAX_PHASES 16
-#define DMB_R3_PAIRS 32                                   // 16-byte pairs per thread per tile
-enum { DMB_M_MAT = 0, DMB_M_CX = 6, DMB_M_TSP0 = 12, DMB_M_TSP = 18, DMB_M_DIAG2 = 24, DMB_M_SWAP = 30 };
-
-struct alignas(16) dmb_r3_micro {
-  int32_t code;
-  int32_t pad_[3];
-  double m[16];
-};
-
-struct alignas(16) dmb_r3_phase {
-  uint32_t sx[4], sy[4], sz[4];      // swizzled BYTE offsets of the three triple digits' values
-  uint32_t sh[3];                    // shifts placing the thread's three index digits
-  int32_t mode;                      // 0: 64-bit accesses, 1: 128-bit pairs along x (x = tile digit 0)
-  int32_t micro_begin, micro_count;
-  int32_t pad_[2];
-};
-
-struct alignas(16) dmb_r3_pass {
-  uint64_t n_tiles;
-  int32_t n_phases;
-  int32_t td[DMB_LEAN_K];
-  int32_t pad_;
-  uint64_t pair_goff[DMB_R3_PAIRS];  // element offset of the uniform part of pair i (i << 7)
-  uint32_t pair_soff[DMB_R3_PAIRS];
-  dmb_r3_phase phases[DMB_R3_MAX_PHASES];
-  dmb_r3_micro micro[DMB_R3_MAX_MICRO];
-};
-
-inline int dmb_r3_pair_index(int p, int q) {   // ordered dim pair -> 0..5
-  static const int tab[3][3] = {{-1, 0, 2}, {1, -1, 4}, {3, 5, -1}};
-  return tab[p][q];
-}
-
-// host-side: group the ops of a pass into triple phases and flatten them into micro-ops.
-// Returns false if the pass does not fit the fixed-size tables (caller falls back to lean).
-inline bool dmb_make_r3_pass(const dmb_pass& P, int n_bits, dmb_r3_pass& R) {
-  const int K = DMB_LEAN_K;
-  R.n_tiles = 1ull << (n_bits - 2 * K);
-  R.pad_ = 0;
-  for (int j = 0; j < K; ++j) R.td[j] = P.tile_digit[j];
-  for (int i = 0; i < DMB_R3_PAIRS; ++i) {
-    const uint32_t l = (uint32_t)i << 7;                 // thread part: 2t, t < 64 -> bits 0..6
-    R.pair_goff[i] = dmb_tile_off(l, P.tile_digit, K);
-    R.pair_soff[i] = dmb_swz(l) << 3;
-  }
-  const int n = P.n_ops;
-  bool done[DMB_MAX_OPS];
-  for (int k = 0; k < n; ++k) done[k] = false;
-  int n_done = 0, n_ph = 0, n_mi = 0;
-  while (n_done < n) {
-    int best_cnt = -1, best_t[3] = {0, 1, 2};
-    bool best_mask[DMB_MAX_OPS];
-    for (int x = 0; x < K; ++x)
-      for (int y = x + 1; y < K; ++y)
-        for (int z = y + 1; z < K; ++z) {
-          bool tmp[DMB_MAX_OPS], take[DMB_MAX_OPS];
-          int cnt = 0;
-          for (int k = 0; k < n; ++k) { tmp[k] = done[k]; take[k] = false; }
-          for (int k = 0; k < n; ++k) {
-            if (tmp[k]) continue;
-            const int a = P.ops[k].a, b = P.ops[k].b;
-            const bool lone = P.ops[k].kind == DMB_OP_MATS && !(P.ops[k].flags & DMB_HAS_PB);
-            const bool in_a = (a == x || a == y || a == z), in_b = (b == x || b == y || b == z);
-            if (!in_a || (!lone && !in_b)) continue;
-            bool ok = true;
-            for (int e = 0; e < k && ok; ++e) {
-              if (tmp[e]) continue;
-              const int ea = P.ops[e].a, eb = P.ops[e].b;
-              const bool elone = P.ops[e].kind == DMB_OP_MATS && !(P.ops[e].flags & DMB_HAS_PB);
-              if (ea == a || (!lone && ea == b) || (!elone && (eb == a || (!lone && eb == b)))) ok = false;
-            }
-            if (ok) { tmp[k] = true; take[k] = true; ++cnt; }
-          }
-          // prefer more ops; on ties prefer triples containing tile digit 0 (128-bit accesses)
-          const int score = cnt * 2 + (x == 0 ? 1 : 0);
-          if (cnt > 0 && score > best_cnt) {
-            best_cnt = score;
-            best_t[0] = x; best_t[1] = y; best_t[2] = z;
-            for (int k = 0; k < n; ++k) best_mask[k] = take[k];
-          }
-        }
-    if (best_cnt < 0 || n_ph >= DMB_R3_MAX_PHASES) return false;
-    dmb_r3_phase& ph = R.phases[n_ph++];
-    const int x = best_t[0], y = best_t[1], z = best_t[2];
-    for (int i = 0; i < 4; ++i) {
-      ph.sx[i] = dmb_swz((uint32_t)i << (2 * x)) << 3;
-      ph.sy[i] = dmb_swz((uint32_t)i << (2 * y)) << 3;
-      ph.sz[i] = dmb_swz((uint32_t)i << (2 * z)) << 3;
-    }
-    ph.mode = (x == 0) ? 1 : 0;
-    // lane order of the three free digits (same rules as schedule.lane_order)
-    int free_d[3], nf = 0;
-    for (int d = 0; d < K; ++d) if (d != x && d != y && d != z) free_d[nf++] = d;
-    int order[3] = {free_d[0], free_d[1], free_d[2]};
-    auto has = [&](int d) { return free_d[0] == d || free_d[1] == d || free_d[2] == d; };
-    if (ph.mode == 0) {               // digit 0 is free: it goes first
-      order[0] = 0;
-      int w = 1;
-      for (int i = 0; i < 3; ++i) if (free_d[i] != 0) order[w++] = free_d[i];
-    } else {
-      const int o1 = has(1) ? 1 : (has(2) ? 2 : (has(4) ? 4 : free_d[0]));
-      int o2 = -1;
-      if (has(3) && o1 != 3) o2 = 3; else if (has(5) && o1 != 5) o2 = 5;
-      if (o2 < 0) for (int i = 0; i < 3; ++i) if (free_d[i] != o1) { o2 = free_d[i]; break; }
-      order[0] = o1; order[1] = o2;
-      for (int i = 0; i < 3; ++i) if (free_d[i] != o1 && free_d[i] != o2) order[2] = free_d[i];
-    }
-    for (int i = 0; i < 3; ++i) ph.sh[i] = (uint32_t)(2 * order[i]);
-    ph.micro_begin = n_mi;
-    ph.pad_[0] = ph.pad_[1] = 0;
-    auto dim_of = [&](int d) { return d == x ? 0 : (d == y ? 1 : 2); };
-    for (int k = 0; k < n; ++k) {
-      if (!best_mask[k]) continue;
-      const dmb_op& o = P.ops[k];
-      done[k] = true;
-      ++n_done;
-      const int da = dim_of(o.a);
-      const bool lone = o.kind == DMB_OP_MATS && !(o.flags & DMB_HAS_PB);
-      const int db = lone ? (da == 0 ? 1 : 0) : dim_of(o.b);
-      if (n_mi + 3 > DMB_R3_MAX_MICRO) return false;
-      if (o.flags & DMB_HAS_PA) {
-        dmb_r3_micro& mi = R.micro[n_mi++];
-        const bool c0 = o.pa[0] != 0.0 || o.pa[4] != 0.0 || o.pa[8] != 0.0;
-        mi.code = DMB_M_MAT + da * 2 + (c0 ? 1 : 0);
-        for (int i = 0; i < 12; ++i) mi.m[i] = o.pa[i];
-      }
-      if (o.flags & DMB_HAS_PB) {
-        dmb_r3_micro& mi = R.micro[n_mi++];
-        const bool c0 = o.pb[0] != 0.0 || o.pb[4] != 0.0 || o.pb[8] != 0.0;
-        mi.code = DMB_M_MAT + db * 2 + (c0 ? 1 : 0);
-        for (int i = 0; i < 12; ++i) mi.m[i] = o.pb[i];
-      }
-      if (o.kind != DMB_OP_MATS) {
-        dmb_r3_micro& mi = R.micro[n_mi++];
-        const int pi = dmb_r3_pair_index(da, db);
-        if (o.kind == DMB_OP_CX) mi.code = DMB_M_CX + pi;
-        else if (o.kind == DMB_OP_CX_TSP) mi.code = ((o.coef[1] == 0.0 && o.coef[4] == 0.0) ? DMB_M_TSP0 : DMB_M_TSP) + pi;
-        else if (o.kind == DMB_OP_DIAG2) mi.code = DMB_M_DIAG2 + pi;
-        else mi.code = DMB_M_SWAP + (da + db - 1);      // unordered pairs (0,1),(0,2),(1,2) -> 0,1,2
-        for (int i = 0; i < 16; ++i) mi.m[i] = o.coef[i];
-      }
-    }
-    ph.micro_count = n_mi - ph.micro_begin;
-  }
-  R.n_phases = n_ph;
-  return true;
-}
-
-struct dmb_r3_thread {
-  uint32_t tq[3];
-  uint64_t goff;
-  uint32_t soff;
-};
-
-DMB_HD void dmb_r3_thread_init(int t, const dmb_r3_pass& R, dmb_r3_thread& T) {
-  T.tq[0] = (uint32_t)t & 3u; T.tq[1] = ((uint32_t)t >> 2) & 3u; T.tq[2] = ((uint32_t)t >> 4) & 3u;
-  T.goff = dmb_tile_off(2u * (uint32_t)t, R.td, DMB_LEAN_K);
-  T.soff = dmb_swz(2u * (uint32_t)t) << 3;
-}
-
-// v[c0][c1][c2] with c_P = i, c_Q = j and the remaining dim = r
-template <int P, int Q>
-DMB_HD double& dmb_r3_at(double (&v)[4][4][4], int i, int j, int r) {
-  constexpr int R = 3 - P - Q;
-  int c[3];
-  c[P] = i; c[Q] = j; c[R] = r;
-  return v[c[0]][c[1]][c[2]];
-}
-
-template <int D, bool COL0>
-DMB_HD void dmb_r3_mat(const double* __restrict__ m, double (&v)[4][4][4]) {
-  constexpr int E = (D == 0) ? 1 : 0;           // the two other dims
-  constexpr int F = 3 - D - E;
-#pragma unroll
-  for (int e = 0; e < 4; ++e)
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      int c0[3], c1[3], c2[3], c3[3];
-      c0[D] = 0; c1[D] = 1; c2[D] = 2; c3[D] = 3;
-      c0[E] = c1[E] = c2[E] = c3[E] = e;
-      c0[F] = c1[F] = c2[F] = c3[F] = f;
-      double& x0 = v[c0[0]][c0[1]][c0[2]];
-      double& x1 = v[c1[0]][c1[1]][c1[2]];
-      double& x2 = v[c2[0]][c2[1]][c2[2]];
-      double& x3 = v[c3[0]][c3[1]][c3[2]];
-      if (COL0) dmb_mat3(m, x0, x1, x2, x3);
-      else dmb_mat3_nocol0(m, x1, x2, x3);
-    }
-}
-
-// KIND: 0 ideal CX, 1 TSP0, 2 TSP, 3 DIAG2, 4 SWAP -- on the ordered dim pair (P, Q)
-template <int P, int Q, int KIND>
-DMB_HD void dmb_r3_pairop(const double* __restrict__ m, double (&v)[4][4][4]) {
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    double w[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) w[i][j] = dmb_r3_at<P, Q>(v, i, j, r);
-    if (KIND == 0) dmb_cx_ideal(w);
-    else if (KIND == 1) dmb_cx_tsp0(w, m[0], m[2], m[3]);
-    else if (KIND == 2) dmb_cx_tsp(w, m[0], m[1], m[2], m[3], m[4]);
-    else if (KIND == 3) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) w[i][j] *= m[4 * i + j];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = i + 1; j < 4; ++j) { const double tmp = w[i][j]; w[i][j] = w[j][i]; w[j][i] = tmp; }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dmb_r3_at<P, Q>(v, i, j, r) = w[i][j];
-  }
-}
-
-#define DMB_R3_PAIR_CASES(BASE, KIND)                                      \
-  case BASE + 0: dmb_r3_pairop<0, 1, KIND>(mi.m, v); break;                \
-  case BASE + 1: dmb_r3_pairop<1, 0, KIND>(mi.m, v); break;                \
-  case BASE + 2: dmb_r3_pairop<0, 2, KIND>(mi.m, v); break;                \
-  case BASE + 3: dmb_r3_pairop<2, 0, KIND>(mi.m, v); break;                \
-  case BASE + 4: dmb_r3_pairop<1, 2, KIND>(mi.m, v); break;                \
-  case BASE + 5: dmb_r3_pairop<2, 1, KIND>(mi.m, v); break;
-
-DMB_HD void dmb_r3_micro_apply(const dmb_r3_micro& mi, double (&v)[4][4][4]) {
-  switch (mi.code) {
-    case DMB_M_MAT + 0: dmb_r3_mat<0, false>(mi.m, v); break;
-    case DMB_M_MAT + 1: dmb_r3_mat<0, true>(mi.m, v); break;
-    case DMB_M_MAT + 2: dmb_r3_mat<1, false>(mi.m, v); break;
-    case DMB_M_MAT + 3: dmb_r3_mat<1, true>(mi.m, v); break;
-    case DMB_M_MAT + 4: dmb_r3_mat<2, false>(mi.m, v); break;
-    case DMB_M_MAT + 5: dmb_r3_mat<2, true>(mi.m, v); break;
-    DMB_R3_PAIR_CASES(DMB_M_CX, 0)
-    DMB_R3_PAIR_CASES(DMB_M_TSP0, 1)
-    DMB_R3_PAIR_CASES(DMB_M_TSP, 2)
-    DMB_R3_PAIR_CASES(DMB_M_DIAG2, 3)
-    case DMB_M_SWAP + 0: dmb_r3_pairop<0, 1, 4>(mi.m, v); break;
-    case DMB_M_SWAP + 1: dmb_r3_pairop<0, 2, 4>(mi.m, v); break;
-    case DMB_M_SWAP + 2: dmb_r3_pairop<1, 2, 4>(mi.m, v); break;
-    default: break;
-  }
-}
-
-// one phase: load the thread's 64-block, run the micro-ops in registers, store it back
-template <class Mem>
-DMB_HD void dmb_r3_phase_thread(const dmb_r3_thread& T, const dmb_r3_pass& R, const dmb_r3_phase& ph, const Mem& mem) {
-  const uint32_t bl = (T.tq[0] << ph.sh[0]) | (T.tq[1] << ph.sh[1]) | (T.tq[2] << ph.sh[2]);
-  const uint32_t sb = dmb_swz(bl) << 3;
-  double v[4][4][4];
-  if (ph.mode == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t rij = sb ^ ph.sx[i] ^ ph.sy[j];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[i][j][k] = mem.ld64(rij ^ ph.sz[k]);
-      }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t o = sb ^ ph.sy[j] ^ ph.sz[k];
-        const dmb_d2 p0 = mem.ld128(o);
-        const dmb_d2 p1 = mem.ld128(o ^ 16u);
-        v[0][j][k] = p0.x; v[1][j][k] = p0.y; v[2][j][k] = p1.x; v[3][j][k] = p1.y;
-      }
-  }
-  for (int m = 0; m < ph.micro_count; ++m) dmb_r3_micro_apply(R.micro[ph.micro_begin + m], v);
-  if (ph.mode == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t rij = sb ^ ph.sx[i] ^ ph.sy[j];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) mem.st64(rij ^ ph.sz[k], v[i][j][k]);
-      }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t o = sb ^ ph.sy[j] ^ ph.sz[k];
-        dmb_d2 p0, p1;
-        p0.x = v[0][j][k]; p0.y = v[1][j][k]; p1.x = v[2][j][k]; p1.y = v[3][j][k];
-        mem.st128(o, p0);
-        mem.st128(o ^ 16u, p1);
-      }
-  }
-}
-
-template <class Mem>
-DMB_HD void dmb_r3_load_thread(const dmb_r3_thread& T, const dmb_r3_pass& R, const double* gtile, const Mem& mem) {
-  for (int i = 0; i < DMB_R3_PAIRS; ++i)
-    mem.st128(T.soff ^ R.pair_soff[i], *reinterpret_cast<const dmb_d2*>(gtile + (T.goff | R.pair_goff[i])));
-}
-
-template <class Mem>
-DMB_HD void dmb_r3_store_thread(const dmb_r3_thread& T, const dmb_r3_pass& R, double* gtile, const Mem& mem) {
-#pragma unroll 8
-  for (int i = 0; i < DMB_R3_PAIRS; ++i)
-    *reinterpret_cast<dmb_d2*>(gtile + (T.goff | R.pair_goff[i])) = mem.ld128(T.soff ^ R.pair_soff[i]);
 }
 
 // ---------------------------------------------------------------------------------------

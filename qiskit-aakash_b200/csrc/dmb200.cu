@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <map>
+#include <mutex>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -35,6 +36,24 @@ static int fail(const char* what, const char* detail = nullptr) {
     cudaError_t e_ = (expr);                                                \
     if (e_ != cudaSuccess) return fail(#expr, cudaGetErrorString(e_));      \
   } while (0)
+
+// Every entry point runs on the context's device and puts the caller's current device back afterwards: the
+// host (PyTorch) keeps its own notion of the current device, and a backend built on device 3 must not
+// redirect the caller's later torch.*(device="cuda") work there.
+struct dmb_device_guard {
+  int prev = -1, dev;
+  cudaError_t err = cudaSuccess;
+  explicit dmb_device_guard(int d) : dev(d) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~dmb_device_guard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+#define DMB_ON_DEVICE(ctx)                                                            \
+  dmb_device_guard dev_guard_((ctx)->device);                                         \
+  if (dev_guard_.err != cudaSuccess) return fail("cudaSetDevice", cudaGetErrorString(dev_guard_.err))
 
 struct dmb_ctx {
   int device;
@@ -76,19 +95,15 @@ k_tile_pass(double* __restrict__ state, const __grid_constant__ dmb_pass P, uint
 }
 
 // ---------------------------------------------------------------------------------------
-// tile pass, K = 6: the hot kernel.  Persistent CTAs (3 per SM), two 32 KiB stages each:
-// the 16-byte pairs of tile i+1 stream into the other stage with cp.async.cg (LDGSTS, no
-// register staging, L1 bypass) while the op run is applied to tile i in place and tile i is
-// written back with LDS.128 + STG.128 -- loads, arithmetic and stores of consecutive tiles
-// overlap inside one CTA instead of relying on CTAs drifting out of phase.
-// (The TMA bulk engine cannot be used for the staging: the bank-conflict-free layout XORs
-// 16-byte chunks inside each 128-byte row, which no bulk/tensor copy can express.)
+// tile pass, K = 6: the hot kernel.  128 threads per 4096-coefficient tile, one 32 KiB stage per CTA,
+// 5 CTAs per SM (persistent: CTA c handles tiles c, c + grid, ...).  The 16-byte pairs of a tile stream in
+// with cp.async.cg (LDGSTS, no register staging, L1 bypass), the fused ops run in place in shared memory
+// (one barrier after each), and the tile is written back with LDS.128 + STG.128 -- the other four CTAs of
+// the SM cover the HBM latency of this CTA's load, so no prefetch ring is needed (measured: 225 ms for
+// BASELINE config 3 against 231 ms with a 2-stage ring x 3 CTAs and 252 ms for round 1's 256-thread kernel,
+// profiles/r02_tile_variants.md).  The control flow is dmb_half_kernel_body in dm_device.h, the function
+// the CPU tests run with real host threads; this is its CUDA execution context.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -113,90 +128,15 @@ struct dmb_smem_mem {
   }
 };
 
-__device__ __forceinline__ void cp_async16s(uint32_t smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-
-// STAGES-deep ring of 32 KiB stages per CTA: tiles k+1 .. k+STAGES-1 are in flight while the
-// op run executes on tile k.  (STAGES, CTAs per SM) = (2, 3) or (3, 2) fit the 227 KB of
-// shared memory; chosen at run time (dmb_set_tile_variant / DMB_LEAN_STAGES).
-// STMODE: DMB_ST_PLAIN, or a relabelling store that realises the pass's trailing digit swaps
-template <int STAGES, int CTAS, int REMOTE, int STMODE = DMB_ST_PLAIN>      // REMOTE: 0 in place, 1 pull (remote loads), 2 push (remote stores)
-__global__ void __launch_bounds__(DMB_TILE_THREADS, CTAS)
-k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L,
-             const __grid_constant__ dmb_remote_src S) {
-  extern __shared__ __align__(128) unsigned char lean_smem[];
-  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
-  dmb_lean_thread T;
-  dmb_lean_thread_init(threadIdx.x, L, T);
-  // source of pair i of the tile at element offset `tb`: in place, or (fused exchange) the peer
-  // buffer that holds those coefficients in the old layout
-  auto src_of = [&](uint64_t tb, int i) -> const double* {
-    const uint64_t idx = tb + (T.goff | L.pair_goff[i]);
-    if (REMOTE == 1) return reinterpret_cast<const double*>(S.tab[idx >> S.shift]) + idx;
-    return state + idx;
-  };
-  const uint64_t first = blockIdx.x;
-  if (first >= L.n_tiles) return;
-  const uint64_t stride = gridDim.x;
-  // prologue: tiles 0 .. STAGES-2 of this CTA
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    const uint64_t tl = first + (uint64_t)s * stride;
-    if (tl < L.n_tiles) {
-      const uint64_t tb = dmb_tile_base(tl, L.td, DMB_LEAN_K);
-      const uint32_t dst = smem0 + (uint32_t)s * DMB_LEAN_TILE_BYTES;
-#pragma unroll
-      for (int i = 0; i < DMB_LEAN_PAIRS; ++i) cp_async16s(dst + (T.soff ^ L.pair_soff[i]), src_of(tb, i));
-    }
-    cp_async_commit();
-  }
-  uint32_t cur = 0;                       // stage of the tile being processed
-  uint32_t fill = STAGES - 1;             // stage the next prefetch goes to
-  for (uint64_t tile = first; tile < L.n_tiles; tile += stride) {
-    const uint64_t ahead = tile + (uint64_t)(STAGES - 1) * stride;
-    if (ahead < L.n_tiles) {
-      const uint64_t tb = dmb_tile_base(ahead, L.td, DMB_LEAN_K);
-      const uint32_t dst = smem0 + fill * DMB_LEAN_TILE_BYTES;
-#pragma unroll
-      for (int i = 0; i < DMB_LEAN_PAIRS; ++i) cp_async16s(dst + (T.soff ^ L.pair_soff[i]), src_of(tb, i));
-    }
-    cp_async_commit();
-    cp_async_wait<STAGES - 1>();
-    __syncthreads();
-    dmb_smem_mem mem;
-    mem.base = smem0 + cur * DMB_LEAN_TILE_BYTES;
-    for (int i = 0; i < L.n_ops; ++i) {
-      dmb_lean_op_dispatch(T, L.ops[i], mem);
-      __syncthreads();
-    }
-    dmb_lean_store_thread<REMOTE == 2, STMODE>(T, L, state, dmb_tile_base(tile, L.td, DMB_LEAN_K), S, mem);
-    __syncthreads();
-    cur = (cur + 1 == STAGES) ? 0 : cur + 1;
-    fill = (fill + 1 == STAGES) ? 0 : fill + 1;
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// tile pass, K = 6, HALF-CTA variant (dmb_set_tile_variant 8 / 9): 128 threads per tile, every
-// thread plays the two virtual threads t and t + 128 of k_tile_pass6 one after the other, one
-// 32 KiB stage per CTA and CTAS = 6 (5) CTAs per SM.  Same warps per SM (24) and registers as the
-// default, but six independent barrier domains of four warps instead of three of eight: more
-// phase mixing between CTAs on the shared-memory / FP64 pipes and cheaper barriers; the HBM
-// latency of a CTA's own tile load is hidden by the other CTAs instead of a prefetch stage.
-// ---------------------------------------------------------------------------------------
-// PAIRED (variants 10 / 11 / 12): ops in access mode A (tile digit 0 free) run the paired body -- the thread plays
-// virtual threads 2u and 2u + 1, whose blocks are the two halves of the same 16-byte pairs (dmb_lean_op_pair:
-// 128-bit shared-memory accesses for both blocks); all other ops and the staging keep u / u + 128.
-// The control flow lives in dm_device.h (dmb_half_kernel_body) so that the CPU tests run it with real threads;
-// this is its CUDA execution context.
 struct dmb_cuda_cta {
   uint32_t smem0;
   __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
   __device__ __forceinline__ uint64_t block() const { return blockIdx.x; }
   __device__ __forceinline__ uint64_t grid() const { return gridDim.x; }
-  __device__ __forceinline__ void copy16(uint32_t off, const double* src) const { cp_async16s(smem0 + off, src); }
-  __device__ __forceinline__ void commit() const { cp_async_commit(); }
+  __device__ __forceinline__ void copy16(uint32_t off, const double* src) const {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem0 + off), "l"(src) : "memory");
+  }
+  __device__ __forceinline__ void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
   template <int N>
   __device__ __forceinline__ void wait() const { cp_async_wait<N>(); }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -207,75 +147,16 @@ struct dmb_cuda_cta {
   }
 };
 
-template <int CTAS, int STMODE, bool PAIRED, int STAGES = 1>
+// REMOTE: 0 in place, 1 pull (remote loads), 2 push (remote stores); STMODE: DMB_ST_PLAIN, or a relabelling
+// store that realises the pass's trailing digit swaps
+template <int CTAS, int REMOTE, int STMODE>
 __global__ void __launch_bounds__(DMB_HALF_THREADS, CTAS)
-k_tile_pass6_half(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L) {
+k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L,
+             const __grid_constant__ dmb_remote_src S) {
   extern __shared__ __align__(128) unsigned char lean_smem[];
   dmb_cuda_cta cx;
   cx.smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
-  dmb_half_kernel_body<STMODE, PAIRED, STAGES>(cx, state, L);
-}
-
-// Tile variant 14: the default kernel's control flow through the policy body (dm_device.h), for an A/B against
-// the hand-written k_tile_pass6 above -- same algorithm, compiled from the function the CPU tests run.
-template <int STAGES, int CTAS, int STMODE>
-__global__ void __launch_bounds__(DMB_TILE_THREADS, CTAS)
-k_tile_pass6_policy(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L) {
-  extern __shared__ __align__(128) unsigned char lean_smem[];
-  dmb_cuda_cta cx;
-  cx.smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
-  dmb_tile_kernel_body<STAGES, STMODE>(cx, state, L);
-}
-
-// ---------------------------------------------------------------------------------------
-// tile pass, K = 6, three digits per thread (R3): 64 threads per tile, each phase keeps a
-// digit triple's 64 coefficients in registers and runs all ops inside the triple back to
-// back -- roughly half the shared-memory traffic per fused op of k_tile_pass6.
-// ---------------------------------------------------------------------------------------
-template <int STAGES, int CTAS>
-__global__ void __launch_bounds__(DMB_R3_THREADS, CTAS)
-k_tile_pass_r3(double* __restrict__ state, const __grid_constant__ dmb_r3_pass R) {
-  extern __shared__ __align__(128) unsigned char lean_smem[];
-  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
-  dmb_r3_thread T;
-  dmb_r3_thread_init(threadIdx.x, R, T);
-  const uint64_t first = blockIdx.x;
-  if (first >= R.n_tiles) return;
-  const uint64_t stride = gridDim.x;
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    const uint64_t tl = first + (uint64_t)s * stride;
-    if (tl < R.n_tiles) {
-      const double* g = state + dmb_tile_base(tl, R.td, DMB_LEAN_K) + T.goff;
-      const uint32_t dst = smem0 + (uint32_t)s * DMB_LEAN_TILE_BYTES;
-#pragma unroll 8
-      for (int i = 0; i < DMB_R3_PAIRS; ++i) cp_async16s(dst + (T.soff ^ R.pair_soff[i]), g + R.pair_goff[i]);
-    }
-    cp_async_commit();
-  }
-  uint32_t cur = 0, fill = STAGES - 1;
-  for (uint64_t tile = first; tile < R.n_tiles; tile += stride) {
-    const uint64_t ahead = tile + (uint64_t)(STAGES - 1) * stride;
-    if (ahead < R.n_tiles) {
-      const double* g = state + dmb_tile_base(ahead, R.td, DMB_LEAN_K) + T.goff;
-      const uint32_t dst = smem0 + fill * DMB_LEAN_TILE_BYTES;
-#pragma unroll 8
-      for (int i = 0; i < DMB_R3_PAIRS; ++i) cp_async16s(dst + (T.soff ^ R.pair_soff[i]), g + R.pair_goff[i]);
-    }
-    cp_async_commit();
-    cp_async_wait<STAGES - 1>();
-    __syncthreads();
-    dmb_smem_mem mem;
-    mem.base = smem0 + cur * DMB_LEAN_TILE_BYTES;
-    for (int p = 0; p < R.n_phases; ++p) {
-      dmb_r3_phase_thread(T, R, R.phases[p], mem);
-      __syncthreads();
-    }
-    dmb_r3_store_thread(T, R, state + dmb_tile_base(tile, R.td, DMB_LEAN_K), mem);
-    __syncthreads();
-    cur = (cur + 1 == STAGES) ? 0 : cur + 1;
-    fill = (fill + 1 == STAGES) ? 0 : fill + 1;
-  }
+  dmb_half_kernel_body<STMODE, true, 1, REMOTE>(cx, state, L, S);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -374,10 +255,11 @@ static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_p
                             const dmb_remote_src& S = g_no_remote, const dmb_remote_src& D = g_no_remote) {
   const uint64_t n_tiles = 1ull << (n_bits - 2 * K);
   const size_t smem = sizeof(double) << (2 * K);
-  static std::atomic<uint64_t> attr_done{0};          // one bit per device: the attribute is per device
-  if (!((attr_done.load() >> (ctx->device & 63)) & 1ull)) {
+  static std::atomic<uint64_t> attr_done[2];          // one bit per device: the attribute is per device
+  const int dev = ctx->device & 127;
+  if (!((attr_done[dev >> 6].load() >> (dev & 63)) & 1ull)) {
     CU_TRY(cudaFuncSetAttribute(k_tile_pass<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done.fetch_or(1ull << (ctx->device & 63));
+    attr_done[dev >> 6].fetch_or(1ull << (dev & 63));
   }
   const uint64_t grid = n_tiles < 0x7fffffffull ? n_tiles : 0x7fffffffull;
   k_tile_pass<K><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, P, n_tiles, S, D);
@@ -385,105 +267,42 @@ static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_p
   return 0;
 }
 
-template <int STAGES, int CTAS, int REMOTE, int STMODE = DMB_ST_PLAIN>
-static int launch_lean(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, const dmb_remote_src& S = g_no_remote) {
-  const size_t smem = (size_t)STAGES * DMB_LEAN_TILE_BYTES;
-  static std::atomic<uint64_t> attr_done{0};
-  if (!((attr_done.load() >> (ctx->device & 63)) & 1ull)) {
-    CU_TRY(cudaFuncSetAttribute(k_tile_pass6<STAGES, CTAS, REMOTE, STMODE>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done.fetch_or(1ull << (ctx->device & 63));
+template <int CTAS, int REMOTE, int STMODE>
+static int launch_tile6(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, const dmb_remote_src& S = g_no_remote) {
+  const size_t smem = DMB_LEAN_TILE_BYTES;
+  static std::atomic<uint64_t> attr_done[2];          // one bit per device: the attribute is per device
+  const int dev = ctx->device & 127;
+  if (!((attr_done[dev >> 6].load() >> (dev & 63)) & 1ull)) {
+    CU_TRY(cudaFuncSetAttribute(k_tile_pass6<CTAS, REMOTE, STMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[dev >> 6].fetch_or(1ull << (dev & 63));
   }
   uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
   if (grid > L.n_tiles) grid = L.n_tiles;
-  k_tile_pass6<STAGES, CTAS, REMOTE, STMODE><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, L, S);
+  k_tile_pass6<CTAS, REMOTE, STMODE><<<(unsigned)grid, DMB_HALF_THREADS, smem, ctx->stream>>>(state, L, S);
   CU_TRY(cudaGetLastError());
   return 0;
 }
 
-template <int CTAS, int STMODE, bool PAIRED, int STAGES>
-static int launch_half(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
-  const size_t smem = (size_t)STAGES * DMB_LEAN_TILE_BYTES;
-  static std::atomic<uint64_t> attr_done{0};
-  if (!((attr_done.load() >> (ctx->device & 63)) & 1ull)) {
-    CU_TRY(cudaFuncSetAttribute(k_tile_pass6_half<CTAS, STMODE, PAIRED, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done.fetch_or(1ull << (ctx->device & 63));
-  }
-  uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
-  if (grid > L.n_tiles) grid = L.n_tiles;
-  k_tile_pass6_half<CTAS, STMODE, PAIRED, STAGES><<<(unsigned)grid, DMB_HALF_THREADS, smem, ctx->stream>>>(state, L);
-  CU_TRY(cudaGetLastError());
-  return 0;
+template <int CTAS>
+static int launch_tile6_any(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
+  if (L.st_mode == DMB_ST_PERM128) return launch_tile6<CTAS, 0, DMB_ST_PERM128>(ctx, state, L);
+  if (L.st_mode == DMB_ST_SPLIT64) return launch_tile6<CTAS, 0, DMB_ST_SPLIT64>(ctx, state, L);
+  return launch_tile6<CTAS, 0, DMB_ST_PLAIN>(ctx, state, L);
 }
 
-template <int STMODE>
-static int launch_policy(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
-  const size_t smem = 2 * DMB_LEAN_TILE_BYTES;
-  static std::atomic<uint64_t> attr_done{0};
-  if (!((attr_done.load() >> (ctx->device & 63)) & 1ull)) {
-    CU_TRY(cudaFuncSetAttribute(k_tile_pass6_policy<2, 3, STMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done.fetch_or(1ull << (ctx->device & 63));
-  }
-  uint64_t grid = (uint64_t)ctx->sm_count * 3;
-  if (grid > L.n_tiles) grid = L.n_tiles;
-  k_tile_pass6_policy<2, 3, STMODE><<<(unsigned)grid, DMB_TILE_THREADS, smem, ctx->stream>>>(state, L);
-  CU_TRY(cudaGetLastError());
-  return 0;
-}
-
-template <int CTAS, bool PAIRED, int STAGES = 1>
-static int launch_half_any(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
-  if (L.st_mode == DMB_ST_PERM128) return launch_half<CTAS, DMB_ST_PERM128, PAIRED, STAGES>(ctx, state, L);
-  if (L.st_mode == DMB_ST_SPLIT64) return launch_half<CTAS, DMB_ST_SPLIT64, PAIRED, STAGES>(ctx, state, L);
-  return launch_half<CTAS, DMB_ST_PLAIN, PAIRED, STAGES>(ctx, state, L);
-}
-
-template <int STAGES, int CTAS>
-static int launch_r3(dmb_ctx* ctx, double* state, const dmb_r3_pass& R) {
-  const size_t smem = (size_t)STAGES * DMB_LEAN_TILE_BYTES;
-  static std::atomic<uint64_t> attr_done{0};
-  if (!((attr_done.load() >> (ctx->device & 63)) & 1ull)) {
-    CU_TRY(cudaFuncSetAttribute(k_tile_pass_r3<STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done.fetch_or(1ull << (ctx->device & 63));
-  }
-  uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
-  if (grid > R.n_tiles) grid = R.n_tiles;
-  k_tile_pass_r3<STAGES, CTAS><<<(unsigned)grid, DMB_R3_THREADS, smem, ctx->stream>>>(state, R);
-  CU_TRY(cudaGetLastError());
-  return 0;
+inline bool dmb_fold_tsp0_enabled() {          // DMB_FOLD_TSP0=0: A/B switch for the <cos a> fold (dmb_make_lean_pass)
+  static const bool on = [] { const char* e = getenv("DMB_FOLD_TSP0"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass& P) {
-  if (ctx->tile_variant == 4 || ctx->tile_variant == 5) {
-    static thread_local dmb_r3_pass R;
-    if (dmb_make_r3_pass(P, n_bits, R)) {
-      ctx->stats.r3_phases += (uint64_t)R.n_phases;
-      return ctx->tile_variant == 5 ? launch_r3<1, 4>(ctx, state, R) : launch_r3<2, 3>(ctx, state, R);
-    }
-  }
   static thread_local dmb_lean_pass L;    // 6.5 KB: keep it off the stack; one host thread drives a ctx
-  const bool fold = (ctx->tile_variant == 0 || ctx->tile_variant >= 8) && dmb_fold_swaps_enabled();
-  dmb_make_lean_pass(P, n_bits, L, fold, ctx->tile_variant == 13);
+  dmb_make_lean_pass(P, n_bits, L, dmb_fold_swaps_enabled(), dmb_fold_tsp0_enabled());
   ctx->stats.folded_swaps += (uint64_t)(P.n_ops - L.n_ops);
   switch (ctx->tile_variant) {
-    case 2: return launch_lean<3, 2, 0>(ctx, state, L);
-    case 3: return launch_lean<2, 2, 0>(ctx, state, L);
-    case 6: return launch_lean<1, 4, 0>(ctx, state, L);
-    case 7: return launch_lean<1, 5, 0>(ctx, state, L);
-    case 8: return launch_half_any<6, false>(ctx, state, L);
-    case 9: return launch_half_any<5, false>(ctx, state, L);
-    case 10: return launch_half_any<4, true>(ctx, state, L);
-    case 11: return launch_half_any<5, true>(ctx, state, L);
-    case 12: return launch_half_any<3, true, 2>(ctx, state, L);
-    case 14:
-      if (L.st_mode == DMB_ST_PERM128) return launch_policy<DMB_ST_PERM128>(ctx, state, L);
-      if (L.st_mode == DMB_ST_SPLIT64) return launch_policy<DMB_ST_SPLIT64>(ctx, state, L);
-      return launch_policy<DMB_ST_PLAIN>(ctx, state, L);
-    case 13: return launch_half_any<4, true>(ctx, state, L);      // 10 + TSP0 factor folded into the control map
-    default:
-      if (L.st_mode == DMB_ST_PERM128) return launch_lean<2, 3, 0, DMB_ST_PERM128>(ctx, state, L);
-      if (L.st_mode == DMB_ST_SPLIT64) return launch_lean<2, 3, 0, DMB_ST_SPLIT64>(ctx, state, L);
-      return launch_lean<2, 3, 0>(ctx, state, L);
+    case 2: return launch_tile6_any<4>(ctx, state, L);
+    case 3: return launch_tile6_any<6>(ctx, state, L);
+    default: return launch_tile6_any<5>(ctx, state, L);
   }
 }
 
@@ -508,10 +327,7 @@ static int validate_pass(const dmb_pass& P, int n_bits) {
         return fail("dmb_apply_passes", "op free-digit list is not a permutation");
       seen |= 1u << op.fd[m];
     }
-    if (op.post_swap < 0 || op.post_swap > 3) return fail("dmb_apply_passes", "post_swap out of range");
-    if ((op.post_swap == 1 || op.post_swap == 2) &&
-        (op.post_swap_with < 0 || op.post_swap_with >= K || op.post_swap_with == op.a || op.post_swap_with == op.b))
-      return fail("dmb_apply_passes", "post_swap_with invalid");
+    if (op.reserved_[0] || op.reserved_[1]) return fail("dmb_apply_passes", "dmb_op.reserved_ must be 0");
   }
   return 0;
 }
@@ -543,7 +359,8 @@ int dmb_create(int device, dmb_ctx** out) {
   int count = 0;
   CU_TRY(cudaGetDeviceCount(&count));
   if (device < 0 || device >= count) return fail("dmb_create", "no such CUDA device");
-  CU_TRY(cudaSetDevice(device));
+  dmb_device_guard dev_guard_(device);
+  if (dev_guard_.err != cudaSuccess) return fail("cudaSetDevice", cudaGetErrorString(dev_guard_.err));
   cudaDeviceProp prop;
   CU_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail("dmb_create", "libdmb200 is built for sm_100a (B200) only");
@@ -569,7 +386,7 @@ int dmb_create(int device, dmb_ctx** out) {
 
 int dmb_destroy(dmb_ctx* ctx) {
   if (!ctx) return 0;
-  cudaSetDevice(ctx->device);
+  dmb_device_guard dev_guard_(ctx->device);
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_idx);
   cudaFreeHost(ctx->h_scratch);
@@ -603,7 +420,7 @@ int dmb_reset_stats(dmb_ctx* ctx) {
 
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant) {
   if (!ctx) return fail("dmb_set_tile_variant", "null context");
-  if (variant < 0 || variant > 14) return fail("dmb_set_tile_variant", "variant must be 0..14");
+  if (variant < 0 || variant > 3) return fail("dmb_set_tile_variant", "variant must be 0..3");
   ctx->tile_variant = variant;
   return 0;
 }
@@ -613,7 +430,7 @@ int dmb_init_product(dmb_ctx* ctx, double* state, int n_bits, uint64_t rank_bits
   if (!ctx || !state || !hi || !lo || !v) return fail("dmb_init_product", "null argument");
   if (n_qubits < 1 || n_qubits > DMB_MAX_QUBITS) return fail("dmb_init_product", "n_qubits out of range");
   if (n_bits < 0 || n_bits > 62) return fail("dmb_init_product", "n_bits out of range");
-  CU_TRY(cudaSetDevice(ctx->device));
+  DMB_ON_DEVICE(ctx);
   dmb_init_params p;
   memset(&p, 0, sizeof(p));
   p.map.n_qubits = n_qubits;
@@ -634,21 +451,10 @@ int dmb_init_product(dmb_ctx* ctx, double* state, int n_bits, uint64_t rank_bits
 
 int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* passes, size_t n_passes) {
   if (!ctx || !state || (!passes && n_passes)) return fail("dmb_apply_passes", "null argument");
-  CU_TRY(cudaSetDevice(ctx->device));
+  DMB_ON_DEVICE(ctx);
   for (size_t i = 0; i < n_passes; ++i) {
     if (validate_pass(passes[i], n_bits)) return 1;
-    // dmb_op.post_swap (a layout remap attached to an op) is executed as an explicit swap op:
-    // folding it into the op's store was implemented and measured -- no faster, and the extra
-    // registers slowed every other op by 3 % -- so the kernels do not carry that path
-    static thread_local dmb_pass expanded[2];
-    int n_run = 1;
-    const dmb_pass* run = &passes[i];
-    if (dmb_pass_has_post_swap(passes[i])) {
-      n_run = dmb_expand_post_swaps(passes[i], expanded);
-      run = expanded;
-    }
-    for (int r = 0; r < n_run; ++r) {
-    const dmb_pass& P = run[r];
+    const dmb_pass& P = passes[i];
     int rc = 0;
     switch (P.n_tile_digits) {
       case 2: rc = launch_tile_pass<2>(ctx, state, n_bits, P); break;
@@ -665,7 +471,6 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
     ctx->stats.tile_pass_launches++;
     ctx->stats.fused_ops += (uint64_t)P.n_ops;
     ctx->stats.state_bytes_moved += 16ull << n_bits;
-    }
   }
   return 0;
 }
@@ -675,15 +480,9 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
   if (!ctx || !dst_state || !pass || !src_tab) return fail("dmb_apply_pass_remote", "null argument");
   if (tab_bits < 0 || (1 << tab_bits) > DMB_REMOTE_MAX) return fail("dmb_apply_pass_remote", "table too large");
   if (block_shift + tab_bits != n_bits) return fail("dmb_apply_pass_remote", "block_shift + tab_bits != n_bits");
-  CU_TRY(cudaSetDevice(ctx->device));
+  DMB_ON_DEVICE(ctx);
   if (validate_pass(*pass, n_bits)) return 1;
-  static thread_local dmb_pass expanded_r[2];
-  const dmb_pass* pp = pass;
-  if (dmb_pass_has_post_swap(*pass)) {
-    if (dmb_expand_post_swaps(*pass, expanded_r) != 1) return fail("dmb_apply_pass_remote", "pass too long after expanding remaps");
-    pp = expanded_r;
-  }
-  const dmb_pass& P = *pp;
+  const dmb_pass& P = *pass;
   dmb_remote_src S;
   memset(&S, 0, sizeof(S));
   for (int i = 0; i < (1 << tab_bits); ++i) S.tab[i] = src_tab[i];
@@ -699,8 +498,8 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
     case 5: rc = launch_tile_pass<5>(ctx, dst_state, n_bits, P, ld, st); break;
     case 6: {
       static thread_local dmb_lean_pass L;
-      dmb_make_lean_pass(P, n_bits, L);
-      rc = push ? launch_lean<2, 3, 2>(ctx, dst_state, L, S) : launch_lean<2, 3, 1>(ctx, dst_state, L, S);
+      dmb_make_lean_pass(P, n_bits, L, false, dmb_fold_tsp0_enabled());
+      rc = push ? launch_tile6<5, 2, DMB_ST_PLAIN>(ctx, dst_state, L, S) : launch_tile6<5, 1, DMB_ST_PLAIN>(ctx, dst_state, L, S);
       break;
     }
     default: return fail("dmb_apply_pass_remote", "unsupported tile size");
@@ -714,7 +513,7 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
 
 int dmb_ipc_export(dmb_ctx* ctx, const void* dev_ptr, unsigned char* handle64, uint64_t* offset) {
   if (!ctx || !dev_ptr || !handle64 || !offset) return fail("dmb_ipc_export", "null argument");
-  CU_TRY(cudaSetDevice(ctx->device));
+  DMB_ON_DEVICE(ctx);
   // the handle names the whole allocation: find its base through the driver API, resolved at
   // run time so that the library still loads on machines without libcuda (build/CI boxes)
   typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
@@ -736,24 +535,41 @@ int dmb_ipc_export(dmb_ctx* ctx, const void* dev_ptr, unsigned char* handle64, u
   return 0;
 }
 
+// An allocation can be mapped only once per process, and PyTorch's caching allocator hands the same allocation to
+// successive engines: mappings are reference counted per handle (dmb_ipc_open / dmb_ipc_close) under a mutex.
+struct dmb_ipc_mapping { void* base; int refs; int device; };
+static std::mutex g_ipc_mutex;
+static std::map<std::string, dmb_ipc_mapping> g_ipc_open;
+
 int dmb_ipc_open(dmb_ctx* ctx, const unsigned char* handle64, uint64_t offset, void** out_ptr) {
   if (!ctx || !handle64 || !out_ptr) return fail("dmb_ipc_open", "null argument");
-  CU_TRY(cudaSetDevice(ctx->device));
-  // an allocation can be mapped only once per process: remember what is already open
-  // (PyTorch's caching allocator hands the same allocation to successive engines)
-  static std::map<std::string, void*> opened;
+  DMB_ON_DEVICE(ctx);
+  std::lock_guard<std::mutex> lock(g_ipc_mutex);
   const std::string key((const char*)handle64, 64);
-  auto it = opened.find(key);
-  void* base = nullptr;
-  if (it != opened.end()) {
-    base = it->second;
-  } else {
+  auto it = g_ipc_open.find(key);
+  if (it == g_ipc_open.end()) {
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, 64);
+    void* base = nullptr;
     CU_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
-    opened[key] = base;
+    it = g_ipc_open.emplace(key, dmb_ipc_mapping{base, 0, ctx->device}).first;
   }
-  *out_ptr = (void*)((char*)base + offset);
+  it->second.refs++;
+  *out_ptr = (void*)((char*)it->second.base + offset);
+  return 0;
+}
+
+int dmb_ipc_close(dmb_ctx* ctx, const unsigned char* handle64) {
+  if (!ctx || !handle64) return fail("dmb_ipc_close", "null argument");
+  std::lock_guard<std::mutex> lock(g_ipc_mutex);
+  const std::string key((const char*)handle64, 64);
+  auto it = g_ipc_open.find(key);
+  if (it == g_ipc_open.end()) return fail("dmb_ipc_close", "handle is not open");
+  if (--it->second.refs > 0) return 0;
+  dmb_device_guard guard(it->second.device);
+  const cudaError_t e = cudaIpcCloseMemHandle(it->second.base);
+  g_ipc_open.erase(it);
+  if (e != cudaSuccess) return fail("cudaIpcCloseMemHandle", cudaGetErrorString(e));
   return 0;
 }
 
@@ -761,7 +577,7 @@ int dmb_marginal(dmb_ctx* ctx, const double* state, int n_bits, uint64_t rank_bi
                  const int32_t* hi, const int32_t* lo, const double* wt, double* out) {
   if (!ctx || !state || !hi || !lo || !wt || !out) return fail("dmb_marginal", "null argument");
   if (n_qubits < 1 || n_qubits > DMB_MAX_QUBITS) return fail("dmb_marginal", "n_qubits out of range");
-  CU_TRY(cudaSetDevice(ctx->device));
+  DMB_ON_DEVICE(ctx);
   dmb_marginal_params p;
   memset(&p, 0, sizeof(p));
   p.map.n_qubits = n_qubits;
@@ -797,7 +613,7 @@ int dmb_marginal(dmb_ctx* ctx, const double* state, int n_bits, uint64_t rank_bi
 int dmb_fwht(dmb_ctx* ctx, double* vec, int n_qubits) {
   if (!ctx || !vec) return fail("dmb_fwht", "null argument");
   if (n_qubits < 0 || n_qubits > 40) return fail("dmb_fwht", "n_qubits out of range");
-  CU_TRY(cudaSetDevice(ctx->device));
+  DMB_ON_DEVICE(ctx);
   const int low = n_qubits < 11 ? n_qubits : 11;
   if (low > 0) {
     k_fwht_smem<<<(unsigned)(1ull << (n_qubits - low)), 1024, 0, ctx->stream>>>(vec, low);
@@ -815,7 +631,7 @@ int dmb_fwht(dmb_ctx* ctx, double* vec, int n_qubits) {
 
 int dmb_contract_digit(dmb_ctx* ctx, const double* in, double* out, uint64_t H, uint64_t L, const double nv[3]) {
   if (!ctx || !in || !out || !nv) return fail("dmb_contract_digit", "null argument");
-  CU_TRY(cudaSetDevice(ctx->device));
+  DMB_ON_DEVICE(ctx);
   const uint64_t count = H * L;
   k_contract_digit<<<grid_for(count, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, out, count, L, nv[0], nv[1], nv[2]);
   CU_TRY(cudaGetLastError());
@@ -825,23 +641,25 @@ int dmb_contract_digit(dmb_ctx* ctx, const double* in, double* out, uint64_t H, 
 
 int dmb_read_coeffs(dmb_ctx* ctx, const double* state, const uint64_t* idx, size_t k, double* out_host) {
   if (!ctx || !state || !idx || !out_host) return fail("dmb_read_coeffs", "null argument");
-  if (k > ctx->scratch_elems) return fail("dmb_read_coeffs", "too many coefficients in one call");
   if (k == 0) return 0;
-  CU_TRY(cudaSetDevice(ctx->device));
-  CU_TRY(cudaMemcpyAsync(ctx->d_idx, idx, k * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-  k_gather<<<grid_for(k, 256, ctx->sm_count), 256, 0, ctx->stream>>>(state, ctx->d_idx, k, ctx->d_scratch);
-  CU_TRY(cudaGetLastError());
-  ctx->stats.other_launches++;
-  CU_TRY(cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(cudaStreamSynchronize(ctx->stream));
-  memcpy(out_host, ctx->h_scratch, k * sizeof(double));
+  DMB_ON_DEVICE(ctx);
+  for (size_t done = 0; done < k; done += ctx->scratch_elems) {       // the context's scratch bounds one round
+    const size_t m = (k - done) < ctx->scratch_elems ? (k - done) : ctx->scratch_elems;
+    CU_TRY(cudaMemcpyAsync(ctx->d_idx, idx + done, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    k_gather<<<grid_for(m, 256, ctx->sm_count), 256, 0, ctx->stream>>>(state, ctx->d_idx, m, ctx->d_scratch);
+    CU_TRY(cudaGetLastError());
+    ctx->stats.other_launches++;
+    CU_TRY(cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_host + done, ctx->h_scratch, m * sizeof(double));
+  }
   return 0;
 }
 
 int dmb_to_matrix(dmb_ctx* ctx, const double* state, int n_qubits, double* work, double* out) {
   if (!ctx || !state || !work || !out) return fail("dmb_to_matrix", "null argument");
   if (n_qubits < 1 || n_qubits > 15) return fail("dmb_to_matrix", "n_qubits out of range");
-  CU_TRY(cudaSetDevice(ctx->device));
+  DMB_ON_DEVICE(ctx);
   const uint64_t vecs = 1ull << (2 * n_qubits - 2);
   for (int pos = 0; pos < n_qubits; ++pos) {
     k_tomatrix_digit<<<grid_for(vecs, 256, ctx->sm_count), 256, 0, ctx->stream>>>(state, (dmb_d2*)work, vecs, pos,
@@ -859,7 +677,7 @@ int dmb_to_matrix(dmb_ctx* ctx, const double* state, int n_qubits, double* work,
 
 int dmb_dot(dmb_ctx* ctx, const double* a, const double* b, uint64_t count, double* out_host) {
   if (!ctx || !a || !b || !out_host) return fail("dmb_dot", "null argument");
-  CU_TRY(cudaSetDevice(ctx->device));
+  DMB_ON_DEVICE(ctx);
   const unsigned blocks = 1024;
   k_dot_partial<<<blocks, 256, 0, ctx->stream>>>(a, b, count, ctx->d_scratch);
   CU_TRY(cudaGetLastError());
@@ -874,7 +692,7 @@ int dmb_dot(dmb_ctx* ctx, const double* a, const double* b, uint64_t count, doub
 
 int dmb_chop(dmb_ctx* ctx, double* state, uint64_t count, double thr) {
   if (!ctx || !state) return fail("dmb_chop", "null argument");
-  CU_TRY(cudaSetDevice(ctx->device));
+  DMB_ON_DEVICE(ctx);
   k_chop<<<grid_for(count, 256, ctx->sm_count), 256, 0, ctx->stream>>>(state, count, thr);
   CU_TRY(cudaGetLastError());
   ctx->stats.other_launches++;
@@ -883,14 +701,14 @@ int dmb_chop(dmb_ctx* ctx, double* state, uint64_t count, double thr) {
 
 int dmb_upload(dmb_ctx* ctx, double* state, const double* host, uint64_t offset, uint64_t count) {
   if (!ctx || !state || !host) return fail("dmb_upload", "null argument");
-  CU_TRY(cudaSetDevice(ctx->device));
+  DMB_ON_DEVICE(ctx);
   CU_TRY(cudaMemcpyAsync(state + offset, host, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
 
 int dmb_download(dmb_ctx* ctx, const double* state, double* host, uint64_t offset, uint64_t count) {
   if (!ctx || !state || !host) return fail("dmb_download", "null argument");
-  CU_TRY(cudaSetDevice(ctx->device));
+  DMB_ON_DEVICE(ctx);
   CU_TRY(cudaMemcpyAsync(host, state + offset, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
   return 0;

@@ -115,19 +115,43 @@ class TorchCommunicator:
     def peer_addresses(self, ctx, ptrs):
         """Addresses, valid in THIS process, of every rank's buffers ``ptrs`` (one list per
         buffer): CUDA IPC handles exchanged through torch.distributed, peers mapped over
-        NVLink.  Returns None when the buffers are not CUDA memory (gloo CPU tests)."""
+        NVLink.  Returns ``(addresses, opened handles)``, or ``(None, [])`` when the buffers cannot
+        be mapped on EVERY rank -- not CUDA memory (gloo CPU tests), an allocator whose memory has
+        no IPC handle (``expandable_segments`` / ``cudaMallocAsync``), no libcuda, no P2P between two
+        ranks -- in which case the engine uses the NCCL block exchange instead.  The decision is
+        collective (all-reduced flag), so all ranks take the same path."""
         if not self.torch.cuda.is_available() or self.dist.get_backend(self.group) != "nccl":
-            return None
-        mine = [ctx.ipc_export(p) for p in ptrs]
+            return None, []
+        mine, ok = None, 1
+        try:
+            mine = [ctx.ipc_export(p) for p in ptrs]
+        except capi.DmbError as exc:
+            ok, self.fallback_reason = 0, "export: %s" % exc
         everyone = [None] * self.world
         self.dist.all_gather_object(everyone, mine, group=self.group)
-        out = []
-        for b in range(len(ptrs)):
-            row = []
-            for r in range(self.world):
-                row.append(ptrs[b] if r == self.rank else ctx.ipc_open(*everyone[r][b]))
-            out.append(row)
-        return out
+        opened, out = [], []
+        if ok and all(e is not None for e in everyone):
+            try:
+                for b in range(len(ptrs)):
+                    row = []
+                    for r in range(self.world):
+                        if r == self.rank:
+                            row.append(ptrs[b])
+                        else:
+                            row.append(ctx.ipc_open(*everyone[r][b]))
+                            opened.append(everyone[r][b][0])
+                    out.append(row)
+            except capi.DmbError as exc:
+                ok, self.fallback_reason = 0, "open: %s" % exc
+        else:
+            ok = 0
+        flag = self.torch.tensor([ok], device="cuda", dtype=self.torch.int32)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            for h in opened:
+                ctx.ipc_close(h)
+            return None, []
+        return out, opened
 
     def all_reduce_sum(self, tensor):
         self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, group=self.group)
@@ -177,15 +201,30 @@ class ShardedPauliEngine(PauliEngine):
         self.exchanges = 0
         self.nvlink_bytes_sent = 0
         # fused exchange: the pass after a slot swap pulls its tiles from the peers' buffers
-        self.peers = None
+        self.peers, self._ipc_handles = None, []
         if bool(int(os.environ.get("DMB_FUSED_EXCHANGE", "1"))) and callable(getattr(comm, "peer_addresses", None)):
-            self.peers = comm.peer_addresses(self.ctx, [self.alloc.ptr(self.state), self.alloc.ptr(self.scratch)])
+            got = comm.peer_addresses(self.ctx, [self.alloc.ptr(self.state), self.alloc.ptr(self.scratch)])
+            self.peers, self._ipc_handles = got if isinstance(got, tuple) else (got, [])
         self._cur = 0                    # which of the two registered buffers is `state`
         self._peers_may_read_scratch = False
         self.exchange_mode = os.environ.get("DMB_EXCHANGE", "pull")      # pull | push | nccl
         self.plain_exchange = bool(int(os.environ.get("DMB_EXCHANGE_PLAIN", "0")))   # op-free pull pass
         if self.exchange_mode == "nccl":
             self.peers = None
+
+    def close(self):
+        """Release the peer mappings of this engine (reference counted in the library: the peer allocation is
+        unmapped when its last user closes it).  Collective in effect: call it on every rank before the shards are
+        freed; also runs when the engine is garbage collected."""
+        handles, self._ipc_handles, self.peers = getattr(self, "_ipc_handles", []), [], None
+        for h in handles:
+            try:
+                self.ctx.ipc_close(h)
+            except Exception:
+                pass
+
+    def __del__(self):
+        self.close()
 
     # -- layout -------------------------------------------------------------------------------
     def is_local(self, q):

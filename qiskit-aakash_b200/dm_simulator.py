@@ -84,10 +84,48 @@ def _bit_strings(nbits):
     return tuple(format(i, "0%db" % nbits) for i in range(2 ** nbits)) if nbits else ("",)
 
 
-class DmSimulatorB200:
-    """Density-matrix simulator in the Pauli basis (arXiv 1908.05154) on one B200."""
+def max_qubits_for(world_size, hbm_bytes=170e9):
+    """Largest register the backend advertises (``configuration().n_qubits``; the reference derives its figure
+    from host memory, ``dm_simulator.py:70,75``).  One GPU holds the 8 * 4^n-byte vector once (n = 16: 34 GB, and
+    room for the 2^n x 2^n readout workspace); a sharded state needs a second, scratch shard per GPU for the
+    out-of-place slot exchange: 2 * 8 * 4^n / G bytes <= ~170 GB of the 180 GB of HBM3e -> 17 qubits on 2 or 4
+    GPUs, 18 on 8."""
+    if world_size <= 1:
+        return 16
+    n = 16
+    while 2 * 8 * 4 ** (n + 1) / world_size <= hbm_bytes:
+        n += 1
+    return n
 
-    MAX_QUBITS_MEMORY = 16          # 8 * 4^16 B = 34 GB state + scratch inside 180 GB of HBM3e
+
+def _default_comm():
+    """The multi-GPU layer behind the public surface: when the process is one rank of an initialised
+    ``torch.distributed`` group of more than one rank (``torchrun``, one process per GPU), ``get_backend`` returns
+    a backend whose state is sharded over the group (``distributed.ShardedPauliEngine``).  ``DMB_SHARD=0`` keeps
+    every rank on its own single-GPU replica."""
+    import os
+    if os.environ.get("DMB_SHARD", "1") == "0":
+        return None
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return None
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return None
+    from .distributed import TorchCommunicator
+    return TorchCommunicator()
+
+
+class DmSimulatorB200:
+    """Density-matrix simulator in the Pauli basis (arXiv 1908.05154) on one B200, or -- constructed with a
+    communicator (``comm=``, or implicitly inside an initialised ``torch.distributed`` group) -- sharded over the
+    2, 4 or 8 B200s of one box."""
+
+    MAX_QUBITS_MEMORY = 16          # 8 * 4^16 B = 34 GB state inside 180 GB of HBM3e (see max_qubits_for)
+
+    #: sharded engines do not gather 'coeffmatrix' (4^n doubles on EVERY rank's host) above this many qubits
+    #: unless the job asks for it with backend option gather_final_state=True
+    SHARDED_GATHER_LIMIT = 14
 
     DEFAULT_CONFIGURATION = {
         "backend_name": "dm_simulator",
@@ -125,13 +163,37 @@ class DmSimulatorB200:
     FILE_EXIST = False
     MERGE = True
 
-    def __init__(self, configuration=None, provider=None, device=0, _engine_factory=None):
-        self._configuration = configuration or SimpleNamespace(**self.DEFAULT_CONFIGURATION)
+    def __init__(self, configuration=None, provider=None, device=None, _engine_factory=None, comm=None):
+        """``device``: CUDA device index (default: torch's current device, i.e. LOCAL_RANK under torchrun).
+        ``comm``: a ``distributed.TorchCommunicator`` (or compatible) -> the state is sharded over its ranks; every
+        rank must then run the same jobs in the same order.  Default: the process's ``torch.distributed`` world
+        when one is initialised, else a single GPU."""
         self._provider = provider
+        self._comm = comm if comm is not None else (None if _engine_factory is not None else _default_comm())
+        if device is None:
+            device = 0
+            if self._comm is not None or _engine_factory is None:
+                try:
+                    import torch
+                    if torch.cuda.is_available():
+                        device = torch.cuda.current_device()
+                except Exception:
+                    pass
         self._device = device
+        world = self._comm.world if self._comm is not None else 1
+        self._configuration = configuration or SimpleNamespace(
+            **dict(self.DEFAULT_CONFIGURATION, n_qubits=max_qubits_for(world)))
         # test hook: the GPU-less unit tests inject an engine factory bound to the CPU
         # emulation of the kernels; the product default is the CUDA engine (fails without it)
-        self._engine_factory = _engine_factory or (lambda n: eng.PauliEngine(n, device=self._device))
+        if _engine_factory is not None:
+            self._engine_factory = _engine_factory
+        elif self._comm is not None:
+            def sharded(n):
+                from .distributed import ShardedPauliEngine
+                return ShardedPauliEngine(n, self._comm, device=self._device)
+            self._engine_factory = sharded
+        else:
+            self._engine_factory = lambda n: eng.PauliEngine(n, device=self._device)
         # the reference mutates its class-level default dict in place (:182,212-213) so
         # rotation errors leak into later runs; kept, but per backend instance
         self._default_rotation_error = {k: list(v) for k, v in self.DEFAULT_OPTIONS["rotation_error"].items()}
@@ -192,6 +254,9 @@ class DmSimulatorB200:
         # extension (not in the reference): 'reduced_state': [qubits] adds the partial trace onto those
         # qubits to the result data ('reduced_coeffmatrix', 'reduced_densitymatrix'); not sticky
         self._reduced_state_qubits = opts.get("reduced_state")
+        # extension: on a sharded state 'coeffmatrix' means gathering 4^n doubles to every rank's host; above
+        # SHARDED_GATHER_LIMIT qubits that is done only on request (not sticky)
+        self._gather_final_state = opts.get("gather_final_state")
 
         if "initial_densitymatrix" in opts:
             self._initial_densitymatrix = np.array(opts["initial_densitymatrix"], dtype=float) \
@@ -365,10 +430,16 @@ class DmSimulatorB200:
     def _pauli_string_expectation(self, engine, letters, err_param):
         """``_pauli_string_expectation`` (``:540-572``): projects, then reads one coefficient."""
         n = self._number_of_qubits
+        if len(letters) < n:
+            raise IndexError("string index out of range")           # basis[i] at :554 in the reference
+        if len(letters) > n:
+            # the reference indexes an n-axis array with len(letters) indices (:568-569)
+            raise IndexError("too many indices for array: array is %d-dimensional, but %d were indexed"
+                             % (n, len(letters)))
         for q in range(n):
             if letters[q] in "XYZ":
                 engine.apply_1q(q, eng.measure_axis_matrix(letters[q], err_param))
-        idx = tuple("IXYZ".index(ch) for ch in letters[:n])
+        idx = tuple("IXYZ".index(ch) for ch in letters)
         return float(engine.read_coefficients([idx])[0] * 2 ** n)
 
     def _add_bell_basis_measure(self, engine, qubit_1, qubit_2, err_param):
@@ -484,7 +555,12 @@ class DmSimulatorB200:
 
         t_levels = time.time()
         t_dl0 = t_dl1 = t_levels
-        if self.SHOW_FINAL_STATE:
+        show_final = self.SHOW_FINAL_STATE
+        if show_final and getattr(engine, "world", 1) > 1 and n > self.SHARDED_GATHER_LIMIT \
+                and not getattr(self, "_gather_final_state", None):
+            logger.info("sharded run on %d qubits: 'coeffmatrix' is not gathered (pass gather_final_state=True)", n)
+            show_final = False
+        if show_final:
             matrix = engine.to_matrix() if self._get_den_mat else None   # before the chop (:1261-1263)
             if getattr(self, "_reduced_state_qubits", None) is not None:
                 data["reduced_coeffmatrix"] = engine.reduced_coefficients(self._reduced_state_qubits)
@@ -542,13 +618,17 @@ class DmSimulatorB200:
         return part_measure
 
     def _run_level(self, engine, level, part_measure, data):
-        """One clock cycle (``:1020-1170``).  Classical bits are never written by the
-        reference, so ``conditional``/``bfunc`` are inert and not modelled."""
+        """One clock cycle (``:1020-1170``).  Classical memory and register are never written on this path
+        (measurements do not record outcomes; the ``bfunc`` that would set a register bit cannot pass the
+        reference's partitioner, ``basicaertools.py:549``), so both stay 0 and an instruction with a
+        ``conditional`` is skipped exactly when the reference skips it (``_conditional_skips``)."""
         err = self._error_params
         i = 0
         while i < len(level):           # index loop: the reference removes items while iterating (:1100)
             op = level[i]
             i += 1
+            if self._conditional_skips(op):
+                continue
             if op.name in ("u1", "u3"):
                 engine.apply_1q(op.qubits[0], eng.gate_matrix(op.name, op.params, err["one_qubit_gates"]))
             elif op.name == "cx":
@@ -600,6 +680,18 @@ class DmSimulatorB200:
                 break
             else:
                 raise BasicAerError('{0} encountered unrecognized operation "{1}"'.format(self.name(), op.name))
+
+    @staticmethod
+    def _conditional_skips(op):
+        """``:1020-1034`` with ``_classical_register == _classical_memory == 0``: an int ``conditional`` (a register
+        bit) always skips; a mask / val ``conditional`` skips unless val == 0."""
+        cond = getattr(op, "conditional", None)
+        if isinstance(cond, int):
+            return True
+        if cond is not None:
+            if int(cond.mask, 16) > 0 and int(cond.val, 16) != 0:
+                return True
+        return False
 
     def _describe_partition(self, levels):
         """``_describe_partition`` (``:1284-1313``)."""

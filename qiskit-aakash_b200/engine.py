@@ -499,9 +499,15 @@ class PauliEngine:
 
     def to_matrix(self):
         """``_compute_densitymatrix`` (``:1198-1255``) -> complex 2^n x 2^n numpy array."""
+        n = self.n
+        if n > 14:
+            # 2 x 16 * 4^n bytes of work / output next to the state (n = 15: 34 GB + the 17 GB state) and as much
+            # pinned host memory; the reference cannot do it either (a Python loop over 4^n indices, :1233-1253)
+            raise BasicAerError("compute_densitymatrix on %d qubits would need a %d GiB matrix; pass "
+                                "compute_densitymatrix=False (the default is True, dm_simulator.py:259-260)"
+                                % (n, (16 * 4 ** n) >> 30))
         self.flush()
         self._require_reference_layout()
-        n = self.n
         if self.nd > n:
             # 1-qubit register: convert on the first 4 coefficients (phantom digit is identity)
             tmp = self.alloc.empty(4 ** n)

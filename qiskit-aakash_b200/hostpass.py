@@ -30,15 +30,16 @@ _FLUSHERS = ("CX", "cx", "measure", "bfunc", "reset", "barrier")
 
 class Op:
     """One instruction after renaming: name in {u1,u3,cx,measure,reset,barrier,bfunc}."""
-    __slots__ = ("name", "qubits", "params", "memory", "register", "order")
+    __slots__ = ("name", "qubits", "params", "memory", "register", "order", "conditional")
 
-    def __init__(self, name, qubits, params=None, memory=None, register=None, order=0):
+    def __init__(self, name, qubits, params=None, memory=None, register=None, order=0, conditional=None):
         self.name = name
         self.qubits = list(qubits)
         self.params = params
         self.memory = memory
         self.register = register
         self.order = order
+        self.conditional = conditional      # carried through untouched (dm_simulator.py:1020-1034)
 
     def __repr__(self):
         return "Op(%s%s%s)" % (self.name, self.qubits, "" if self.params is None else self.params)
@@ -52,7 +53,7 @@ def _to_op(ins, order):
         params = list(params)
     mem, reg = get("memory"), get("register")
     return Op(name, get("qubits") or [], params, list(mem) if mem is not None else None,
-              list(reg) if reg is not None else None, order)
+              list(reg) if reg is not None else None, order, get("conditional"))
 
 
 def zyz_from_yzy(xi, theta1, theta2):
@@ -112,13 +113,15 @@ def merge_single_qubit_gates(instructions, n_qubits, merge=True):
                 out.append(op)
         return out
 
-    pending = [None] * n_qubits          # per qubit: (name, params, order of first gate)
+    # per qubit: (name, params, order of first gate, conditional of the first gate -- mergeU keeps a copy of the
+    # earlier instruction, basicaertools.py:193-196, and with it that instruction's `conditional`)
+    pending = [None] * n_qubits
 
     def flush():
         for q in range(n_qubits):
             if pending[q] is not None:
-                name, params, order = pending[q]
-                out.append(Op(name, [q], params, order=order))
+                name, params, order, cond = pending[q]
+                out.append(Op(name, [q], params, order=order, conditional=cond))
                 pending[q] = None
 
     for k, ins in enumerate(instructions):
@@ -130,11 +133,11 @@ def merge_single_qubit_gates(instructions, n_qubits, merge=True):
             _rename(op)
             q = op.qubits[0]
             if pending[q] is None:
-                pending[q] = (op.name, list(op.params), k)
+                pending[q] = (op.name, list(op.params), k, op.conditional)
             else:
-                name, params, order = pending[q]
+                name, params, order, cond = pending[q]
                 fused_name, fused_params = _fuse((name, params), (op.name, op.params))
-                pending[q] = (fused_name, fused_params, order)
+                pending[q] = (fused_name, fused_params, order, cond)
         elif op.name in ("id", "u0"):
             continue
         else:

@@ -25,7 +25,7 @@ from . import capi
 
 class DevOp:
     """A two-digit op on physical digit positions ``da`` (matrix ``pa``) and ``db`` (``pb``)."""
-    __slots__ = ("kind", "da", "db", "pa", "pb", "coef", "post_swap", "post_swap_with")
+    __slots__ = ("kind", "da", "db", "pa", "pb", "coef")
 
     def __init__(self, kind, da, db, pa=None, pb=None, coef=None):
         self.kind = kind
@@ -34,8 +34,6 @@ class DevOp:
         self.pa = pa
         self.pb = pb
         self.coef = coef
-        self.post_swap = 0    # 1/2: after the op exchange digit da/db with post_swap_with; 3: da <-> db
-        self.post_swap_with = None
 
     def digits(self):
         return (self.da,) if self.db is None else (self.da, self.db)
@@ -59,44 +57,6 @@ def lane_order(K, a, b):
     return first + [d for d in free if d not in first]
 
 
-#: Attaching remap swaps to the preceding op (``dmb_op.post_swap``) is supported by the ABI and
-#: parity-tested.  Folding such a swap into the op's *store* (an address permutation instead of a
-#: shared-memory round trip) was implemented and measured on B200: no faster than explicit swap
-#: ops (310.7 vs 305.4 ms for config 3 -- the permuted store is 64-bit with bank conflicts and
-#: cost every op 8 more registers), so the kernels run post_swap as an explicit swap and the
-#: scheduler does not emit it by default.
-FUSE_SWAPS_DEFAULT = bool(int(os.environ.get("DMB_FUSE_SWAPS", "0")))
-
-
-def fuse_swaps(devops):
-    """Fold SWAP ops of one pass into the store of the nearest earlier op that touches one of
-    their digits (``dmb_op.post_swap``): the remap then costs an address permutation instead of
-    a shared-memory round trip of the tile.  A swap commutes backwards past ops on other digits,
-    so this is exact; swaps that meet another swap, a lone single-digit op or an op that already
-    carries a remap stay explicit."""
-    out = []
-    for op in devops:
-        fused = False
-        if op.kind == capi.OP_SWAP and op.pa is None and op.pb is None and op.post_swap == 0 and op.db is not None:
-            x, y = op.da, op.db
-            for k in range(len(out) - 1, -1, -1):
-                o = out[k]
-                dg = o.digits()
-                if x in dg or y in dg:
-                    if o.kind != capi.OP_SWAP and o.post_swap == 0 and o.db is not None:
-                        if x in dg and y in dg:
-                            o.post_swap = 3
-                        else:
-                            touched = y if y in dg else x
-                            o.post_swap = 1 if o.da == touched else 2
-                            o.post_swap_with = x if touched == y else y
-                        fused = True
-                    break
-        if not fused:
-            out.append(op)
-    return out
-
-
 def _rows13(m):
     m = np.asarray(m, dtype=np.float64)
     if m.shape != (4, 4):
@@ -107,7 +67,7 @@ def _rows13(m):
 
 
 def build_passes(ops, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_OPS, window=256,
-                 reserve_low=2, fuse=None):
+                 reserve_low=2):
     """ops: list of DevOp in program order -> numpy array of ``capi.PASS_DTYPE``.
 
     ``reserve_low`` digit positions 0..reserve_low-1 are part of every tile, which makes the
@@ -115,7 +75,6 @@ def build_passes(ops, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_
     K = min(max_tile, n_digits)
     if K < 2:
         raise ValueError("state must have at least 2 digit positions")
-    fuse = FUSE_SWAPS_DEFAULT if fuse is None else fuse
     max_ops = min(max_ops, capi.MAX_OPS)
     remaining = list(ops)
     plans = []
@@ -151,7 +110,7 @@ def build_passes(ops, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_
             if d not in tile:
                 tile.add(d)
             d += 1
-        plans.append((sorted(tile), fuse_swaps(chosen) if fuse else chosen))
+        plans.append((sorted(tile), chosen))
         remaining = keep
     return encode_passes(plans)
 
@@ -208,7 +167,7 @@ def pack_qops(qops):
 
 #: The native scheduler (``dmb_schedule``, csrc/dm_schedule.h) is the product path; the Python
 #: ``build_passes_relabel`` below is its executable specification (tests compare them byte for
-#: byte) and serves the two experimental knobs the native one does not carry (fuse, swap_weight).
+#: byte) and serves the experimental knob the native one does not carry (swap_weight).
 NATIVE_DEFAULT = bool(int(os.environ.get("DMB_NATIVE_SCHEDULE", "1")))
 
 
@@ -219,7 +178,7 @@ def relabel_passes(lib, qops, pos, n_digits, max_ops=capi.MAX_OPS, min_tail=0, f
     ``strategy``: ``capi.SCHED_PROGRAM_ORDER`` (what the Python specification does) or
     ``capi.SCHED_TILE_SEARCH`` (native only)."""
     native = NATIVE_DEFAULT if native is None else native
-    if not native or FUSE_SWAPS_DEFAULT:
+    if not native:
         return build_passes_relabel(qops, pos, n_digits, max_ops=max_ops, min_tail=min_tail, final_moves=final_moves)
     passes, left, moves_left = capi.schedule(lib, pack_qops(qops), pos, n_digits, max_ops=max_ops, min_tail=min_tail,
                                              final_moves=final_moves, strategy=strategy)
@@ -231,7 +190,7 @@ def relabel_passes(lib, qops, pos, n_digits, max_ops=capi.MAX_OPS, min_tail=0, f
 
 
 def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max_ops=capi.MAX_OPS, window=256,
-                         swap_weight=0.0, fuse=None, min_tail=0, final_moves=None):
+                         swap_weight=0.0, min_tail=0, final_moves=None):
     """Like ``build_passes`` but with dynamic relabelling of the two low digit positions.
 
     ``final_moves`` = [(qubit, digit position)]: after the last op, move these qubits to the given
@@ -257,7 +216,6 @@ def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max
     K = min(max_tile, n_digits)
     if K < 2:
         raise ValueError("state must have at least 2 digit positions")
-    fuse = FUSE_SWAPS_DEFAULT if fuse is None else fuse
     max_ops = min(max_ops, capi.MAX_OPS)
     real_ops_cap = max(1, max_ops - 2) if K >= 4 else max_ops     # leave room for two swaps
     owner = {pos[q]: q for q in range(n_qubits)}                  # digit position -> qubit (phantoms absent)
@@ -337,7 +295,7 @@ def build_passes_relabel(qops, pos, n_digits, max_tile=capi.MAX_TILE_DIGITS, max
                 owner[src], pos[other] = other, src
             else:
                 owner.pop(src, None)
-        plans.append((sorted(tile_d), fuse_swaps(devops) if fuse else devops))
+        plans.append((sorted(tile_d), devops))
     if final_moves is not None:
         return encode_passes(plans), [(q, t) for q, t in final_moves if pos[q] != t]
     if min_tail > 0:
@@ -372,9 +330,6 @@ def encode_passes(plans):
                 flags |= capi.HAS_PB
             o["flags"] = flags
             o["a"], o["b"] = a, b
-            o["post_swap"] = op.post_swap
-            if op.post_swap in (1, 2):
-                o["post_swap_with"] = local[op.post_swap_with]
             fd = lane_order(K, a, b)
             o["fd"][:len(fd)] = fd
             if op.coef is not None:

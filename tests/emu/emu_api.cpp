@@ -51,10 +51,7 @@ static int validate_pass(const dmb_pass& P, int n_bits) {
         return fail("dmb_apply_passes", "op free-digit list is not a permutation");
       seen |= 1u << op.fd[m];
     }
-    if (op.post_swap < 0 || op.post_swap > 3) return fail("dmb_apply_passes", "post_swap out of range");
-    if ((op.post_swap == 1 || op.post_swap == 2) &&
-        (op.post_swap_with < 0 || op.post_swap_with >= K || op.post_swap_with == op.a || op.post_swap_with == op.b))
-      return fail("dmb_apply_passes", "post_swap_with invalid");
+    if (op.reserved_[0] || op.reserved_[1]) return fail("dmb_apply_passes", "dmb_op.reserved_ must be 0");
   }
   return 0;
 }
@@ -78,16 +75,20 @@ static void run_tile_pass(double* state, int n_bits, const dmb_pass& P, const dm
   }
 }
 
-// lean K = 6 path: same per-thread bodies as k_tile_pass6, tiles processed one after another
+// K = 6 path: the per-thread bodies of k_tile_pass6 (paired dispatch, folded swaps, folded <cos a>), run one virtual
+// thread after the other, tiles one after another
 static int g_variant = 0;
 static thread_local long g_folded_swaps = 0;
 static long g_paired_ops = 0;     // thread-ops that went through dmb_lean_op_pair (test hook)
 extern "C" long dmb_emu_paired_ops(void) { return g_paired_ops; }
+static bool emu_fold_tsp0() {
+  const char* e = getenv("DMB_FOLD_TSP0");
+  return !(e && e[0] == '0');
+}
 static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const dmb_remote_src& S = g_no_remote,
                            const dmb_remote_src& D = g_no_remote) {
   static thread_local dmb_lean_pass L;
-  dmb_make_lean_pass(P, n_bits, L, (g_variant == 0 || g_variant >= 8) && dmb_fold_swaps_enabled() && !S.enabled && !D.enabled,
-                     g_variant == 13);
+  dmb_make_lean_pass(P, n_bits, L, dmb_fold_swaps_enabled() && !S.enabled && !D.enabled, emu_fold_tsp0());
   g_folded_swaps += P.n_ops - L.n_ops;
   alignas(128) static thread_local unsigned char stage[DMB_LEAN_TILE_BYTES];
   static thread_local dmb_lean_thread T[DMB_TILE_THREADS];
@@ -97,18 +98,11 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const d
   for (uint64_t tile = 0; tile < L.n_tiles; ++tile) {
     const uint64_t tbase = dmb_tile_base(tile, L.td, DMB_LEAN_K);
     for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, state, tbase, S, mem);
-    for (int i = 0; i < L.n_ops; ++i) {
-      if (g_variant >= 10) {        // paired kernel: real thread u plays virtual threads 2u, 2u + 1
-        for (int u = 0; u < DMB_TILE_THREADS / 2; ++u) {
-          if (dmb_lean_op_is_paired(L.ops[i])) ++g_paired_ops;
-          dmb_lean_op_dispatch_pair(T[2 * u], T[u], L.ops[i], mem);
-        }
-      } else if (g_variant == 8 || g_variant == 9) {   // half-CTA kernel: real thread u plays u and u + 128
-        for (int u = 0; u < DMB_TILE_THREADS / 2; ++u) dmb_lean_op_dispatch_twice(T[u], L.ops[i], mem);
-      } else {
-        for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_op_dispatch(T[t], L.ops[i], mem);
+    for (int i = 0; i < L.n_ops; ++i)
+      for (int u = 0; u < DMB_TILE_THREADS / 2; ++u) {   // real thread u plays virtual threads 2u, 2u + 1 or u, u + 128
+        if (dmb_lean_op_is_paired(L.ops[i])) ++g_paired_ops;
+        dmb_lean_op_dispatch_pair(T[2 * u], T[u], L.ops[i], mem);
       }
-    }
     for (int t = 0; t < DMB_TILE_THREADS; ++t) {
       if (D.enabled) dmb_lean_store_thread<true, DMB_ST_PLAIN>(T[t], L, state, tbase, D, mem);
       else if (L.st_mode == DMB_ST_PERM128) dmb_lean_store_thread<false, DMB_ST_PERM128>(T[t], L, state, tbase, D, mem);
@@ -119,8 +113,8 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const d
 }
 
 // ---------------------------------------------------------------------------------------
-// The half-CTA / paired kernel's REAL control flow (dmb_half_kernel_body, the function the CUDA kernel
-// k_tile_pass6_half wraps) on host threads: 128 std::threads per CTA, a CTA barrier, and cp.async emulated as
+// The tile kernel's REAL control flow (dmb_half_kernel_body, the function the CUDA kernel
+// k_tile_pass6 wraps) on host threads: 128 std::threads per CTA, a CTA barrier, and cp.async emulated as
 // deferred copies that only land at wait<N>() -- so a read before the wait, a missing barrier or a wrong stage
 // index shows up as a wrong result here, without a GPU.
 // ---------------------------------------------------------------------------------------
@@ -164,46 +158,9 @@ struct emu_cta_thread {
   }
 };
 
-template <int STMODE, int STAGES>
-static void run_default_kernel_cta(double* state, const dmb_lean_pass& L, uint64_t block, uint64_t grid) {
-  std::vector<unsigned char> stages((size_t)STAGES * DMB_LEAN_TILE_BYTES + 128);
-  unsigned char* base = stages.data() + (128 - (reinterpret_cast<uintptr_t>(stages.data()) & 127)) % 128;
-  emu_barrier bar(DMB_TILE_THREADS);
-  std::vector<std::thread> threads;
-  for (int t = 0; t < DMB_TILE_THREADS; ++t)
-    threads.emplace_back([&, t] {
-      emu_cta_thread cx;
-      cx.tid_ = t; cx.block_ = block; cx.grid_ = grid; cx.stages = base; cx.bar = &bar;
-      dmb_tile_kernel_body<STAGES, STMODE>(cx, state, L);
-    });
-  for (auto& th : threads) th.join();
-}
-
-// test hook: the default kernel's control flow (256 threads per CTA, STAGES-deep ring) on host threads
-extern "C" int dmb_emu_run_default_kernel(double* state, int n_bits, const dmb_pass* passes, size_t n_passes, int stages,
-                                          int grid) {
-  static thread_local dmb_lean_pass L;
-  for (size_t i = 0; i < n_passes; ++i) {
-    if (passes[i].n_tile_digits != DMB_LEAN_K || dmb_pass_has_post_swap(passes[i])) return 1;
-    dmb_make_lean_pass(passes[i], n_bits, L, dmb_fold_swaps_enabled());
-    const uint64_t g = (uint64_t)grid < L.n_tiles ? (uint64_t)grid : L.n_tiles;
-    for (uint64_t block = 0; block < g; ++block) {
-      if (stages == 3) {
-        if (L.st_mode == DMB_ST_PERM128) run_default_kernel_cta<DMB_ST_PERM128, 3>(state, L, block, g);
-        else if (L.st_mode == DMB_ST_SPLIT64) run_default_kernel_cta<DMB_ST_SPLIT64, 3>(state, L, block, g);
-        else run_default_kernel_cta<DMB_ST_PLAIN, 3>(state, L, block, g);
-      } else {
-        if (L.st_mode == DMB_ST_PERM128) run_default_kernel_cta<DMB_ST_PERM128, 2>(state, L, block, g);
-        else if (L.st_mode == DMB_ST_SPLIT64) run_default_kernel_cta<DMB_ST_SPLIT64, 2>(state, L, block, g);
-        else run_default_kernel_cta<DMB_ST_PLAIN, 2>(state, L, block, g);
-      }
-    }
-  }
-  return 0;
-}
-
-template <int STMODE, bool PAIRED, int STAGES>
-static void run_half_kernel_cta(double* state, const dmb_lean_pass& L, uint64_t block, uint64_t grid) {
+template <int STMODE, bool PAIRED, int STAGES, int REMOTE = 0>
+static void run_half_kernel_cta(double* state, const dmb_lean_pass& L, uint64_t block, uint64_t grid,
+                                const dmb_remote_src& R = g_no_remote) {
   std::vector<unsigned char> stages((size_t)STAGES * DMB_LEAN_TILE_BYTES + 128);
   unsigned char* base = stages.data() + (128 - (reinterpret_cast<uintptr_t>(stages.data()) & 127)) % 128;
   emu_barrier bar(DMB_HALF_THREADS);
@@ -212,7 +169,7 @@ static void run_half_kernel_cta(double* state, const dmb_lean_pass& L, uint64_t 
     threads.emplace_back([&, t] {
       emu_cta_thread cx;
       cx.tid_ = t; cx.block_ = block; cx.grid_ = grid; cx.stages = base; cx.bar = &bar;
-      dmb_half_kernel_body<STMODE, PAIRED, STAGES>(cx, state, L);
+      dmb_half_kernel_body<STMODE, PAIRED, STAGES, REMOTE>(cx, state, L, R);
     });
   for (auto& th : threads) th.join();
 }
@@ -231,8 +188,8 @@ extern "C" int dmb_emu_run_half_kernel(double* state, int n_bits, const dmb_pass
                                        int stages, int grid) {
   static thread_local dmb_lean_pass L;
   for (size_t i = 0; i < n_passes; ++i) {
-    if (passes[i].n_tile_digits != DMB_LEAN_K || dmb_pass_has_post_swap(passes[i])) return 1;
-    dmb_make_lean_pass(passes[i], n_bits, L, dmb_fold_swaps_enabled());
+    if (passes[i].n_tile_digits != DMB_LEAN_K) return 1;
+    dmb_make_lean_pass(passes[i], n_bits, L, dmb_fold_swaps_enabled(), paired && emu_fold_tsp0());
     uint64_t g = (uint64_t)grid < L.n_tiles ? (uint64_t)grid : L.n_tiles;
     if (paired && stages == 2) run_half_kernel<true, 2>(state, L, g);
     else if (paired) run_half_kernel<true, 1>(state, L, g);
@@ -242,8 +199,6 @@ extern "C" int dmb_emu_run_half_kernel(double* state, int n_bits, const dmb_pass
   return 0;
 }
 
-// R3 path (three digits per thread), same bodies as k_tile_pass_r3
-static long g_r3_passes = 0, g_r3_phases = 0, g_r3_ops = 0;
 // test hook: thread order chosen for a SPLIT64 store + worst number of half-warp lanes per bank slot
 extern "C" int dmb_emu_split_order(const int32_t* perm, int32_t* tbit_out) {
   int ibit[3];
@@ -262,27 +217,6 @@ extern "C" int dmb_emu_split_order(const int32_t* perm, int32_t* tbit_out) {
     }
   return worst;
 }
-extern "C" void dmb_emu_r3_counters(long* out) { out[0] = g_r3_passes; out[1] = g_r3_phases; out[2] = g_r3_ops; }
-
-static bool run_tile_pass_r3(double* state, int n_bits, const dmb_pass& P) {
-  static thread_local dmb_r3_pass R;
-  if (!dmb_make_r3_pass(P, n_bits, R)) return false;
-  g_r3_passes++; g_r3_phases += R.n_phases; g_r3_ops += P.n_ops;
-  alignas(128) static thread_local unsigned char stage[DMB_LEAN_TILE_BYTES];
-  static thread_local dmb_r3_thread T[DMB_R3_THREADS];
-  for (int t = 0; t < DMB_R3_THREADS; ++t) dmb_r3_thread_init(t, R, T[t]);
-  dmb_host_mem mem;
-  mem.base = stage;
-  for (uint64_t tile = 0; tile < R.n_tiles; ++tile) {
-    double* gtile = state + dmb_tile_base(tile, R.td, DMB_LEAN_K);
-    for (int t = 0; t < DMB_R3_THREADS; ++t) dmb_r3_load_thread(T[t], R, gtile, mem);
-    for (int p = 0; p < R.n_phases; ++p)
-      for (int t = 0; t < DMB_R3_THREADS; ++t) dmb_r3_phase_thread(T[t], R, R.phases[p], mem);
-    for (int t = 0; t < DMB_R3_THREADS; ++t) dmb_r3_store_thread(T[t], R, gtile, mem);
-  }
-  return true;
-}
-
 
 extern "C" {
 
@@ -315,7 +249,7 @@ int dmb_sync(dmb_ctx*) { return 0; }
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out) { *out = ctx->stats; return 0; }
 int dmb_reset_stats(dmb_ctx* ctx) { memset(&ctx->stats, 0, sizeof(dmb_stats)); return 0; }
 int dmb_set_tile_variant(dmb_ctx*, int variant) {
-  if (variant < 0 || variant > 14) return fail("dmb_set_tile_variant", "variant must be 0..14");
+  if (variant < 0 || variant > 3) return fail("dmb_set_tile_variant", "variant must be 0..3");
   g_variant = variant;
   return 0;
 }
@@ -342,15 +276,7 @@ int dmb_init_product(dmb_ctx* ctx, double* state, int n_bits, uint64_t rank_bits
 int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* passes, size_t n_passes) {
   for (size_t i = 0; i < n_passes; ++i) {
     if (validate_pass(passes[i], n_bits)) return 1;
-    static thread_local dmb_pass expanded[2];
-    int n_run = 1;
-    const dmb_pass* run = &passes[i];
-    if (dmb_pass_has_post_swap(passes[i])) {
-      n_run = dmb_expand_post_swaps(passes[i], expanded);
-      run = expanded;
-    }
-   for (int r = 0; r < n_run; ++r) {
-    const dmb_pass& P = run[r];
+    const dmb_pass& P = passes[i];
     switch (P.n_tile_digits) {
       case 2: run_tile_pass<2>(state, n_bits, P); break;
       case 3: run_tile_pass<3>(state, n_bits, P); break;
@@ -358,7 +284,6 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
       case 5: run_tile_pass<5>(state, n_bits, P); break;
       case 6:
         if (g_variant == 1) run_tile_pass<6>(state, n_bits, P);
-        else if ((g_variant == 4 || g_variant == 5) && run_tile_pass_r3(state, n_bits, P)) {}
         else { const long before = g_folded_swaps; run_tile_pass6(state, n_bits, P);
                ctx->stats.folded_swaps += (uint64_t)(g_folded_swaps - before); }
         break;
@@ -367,7 +292,6 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
     ctx->stats.tile_pass_launches++;
     ctx->stats.fused_ops += (uint64_t)P.n_ops;
     ctx->stats.state_bytes_moved += 16ull << n_bits;
-   }
   }
   return 0;
 }
@@ -377,13 +301,7 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
   if ((1 << tab_bits) > DMB_REMOTE_MAX) return fail("dmb_apply_pass_remote", "table too large");
   if (block_shift + tab_bits != n_bits) return fail("dmb_apply_pass_remote", "block_shift + tab_bits != n_bits");
   if (validate_pass(*pass, n_bits)) return 1;
-  static thread_local dmb_pass expanded_r[2];
-  const dmb_pass* pp = pass;
-  if (dmb_pass_has_post_swap(*pass)) {
-    if (dmb_expand_post_swaps(*pass, expanded_r) != 1) return fail("dmb_apply_pass_remote", "pass too long");
-    pp = expanded_r;
-  }
-  const dmb_pass& P = *pp;
+  const dmb_pass& P = *pass;
   dmb_remote_src S;
   memset(&S, 0, sizeof(S));
   for (int i = 0; i < (1 << tab_bits); ++i) S.tab[i] = src_tab[i];
@@ -419,6 +337,8 @@ int dmb_ipc_open(dmb_ctx*, const unsigned char* handle64, uint64_t offset, void*
   *out_ptr = (char*)p + offset;
   return 0;
 }
+
+int dmb_ipc_close(dmb_ctx*, const unsigned char*) { return 0; }
 
 int dmb_marginal(dmb_ctx* ctx, const double* state, int n_bits, uint64_t rank_bits, int n_qubits,
                  const int32_t* hi, const int32_t* lo, const double* wt, double* out) {

@@ -160,3 +160,60 @@ def test_fidelity_of_a_compare_job_does_not_leak_into_the_next_job(tmp_path, mon
     plain.h(0)                                   # no ensemble readout -> no comparison in this job
     third = be.run(assemble(plain), backend_options={}).result()["results"][0]["data"]
     assert "fidelity" not in third
+
+
+def _conditional_program():
+    """Raw-qobj instructions carrying ``conditional`` (dm_simulator.py:1020-1034): an int (register bit, never set
+    on this path -> skipped), a mask / val object with val 0 (runs) and with val 1 (skipped); one conditional gate
+    is the FIRST of a merged run (the merged gate inherits it, basicaertools.py:193-196), one the second (lost)."""
+    from types import SimpleNamespace as NS
+    c = Circuit(3)
+    c.u3(0.3, 0.2, 0.1, 0)
+    c.u3(0.5, 0.4, 0.3, 1); c.instructions[-1].conditional = 0
+    c.cx(0, 1)
+    c.cx(1, 2); c.instructions[-1].conditional = 1
+    c.u3(0.7, 0.1, 0.2, 2); c.instructions[-1].conditional = NS(mask="0x1", val="0x0")
+    c.u3(0.2, 0.9, 0.4, 2)
+    c.cx(2, 0)
+    c.u3(1.1, 0.3, 0.6, 0)
+    c.u3(0.4, 0.8, 0.5, 0); c.instructions[-1].conditional = 2
+    c.cx(0, 2)
+    c.u3(0.9, 0.2, 0.7, 1); c.instructions[-1].conditional = NS(mask="0x3", val="0x1")
+    c.measure([0, 1, 2], [0, 1, 2], basis="Ensemble", add_param="Z")
+    return c
+
+
+def test_conditional_instructions_are_skipped_like_the_reference(case_dir):
+    from oracle import ref_harness
+    circ = _conditional_program()
+    opts = {"rotation_error": {"rz": [0.99, 0.01]}, "decay_factor": 0.98}
+    got = _run(emu_backend(), circ, **copy.deepcopy(opts))["results"][0]
+    ora = dm_oracle.run_oracle(3, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
+    assert np.max(np.abs(got["data"]["coeffmatrix"] - ora["data"]["coeffmatrix"])) <= 1e-13
+    plain = Circuit(3)
+    plain.instructions = [i for i in copy.deepcopy(circ.instructions)]
+    for i in plain.instructions:
+        if hasattr(i, "conditional"):
+            del i.conditional
+    unconditional = _run(emu_backend(), plain, **copy.deepcopy(opts))["results"][0]
+    assert np.max(np.abs(got["data"]["coeffmatrix"] - unconditional["data"]["coeffmatrix"])) > 1e-3
+    if ref_harness.available():
+        ref = ref_harness.run_reference(3, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
+        assert ref["number_of_clock_cycles"] == got["number_of_clock_cycles"]
+        assert np.max(np.abs(got["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])) <= 1e-13
+        assert np.max(np.abs(ora["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])) <= 1e-13
+
+
+@pytest.mark.parametrize("letters", ["ZZX", "Z"])
+def test_pauli_string_of_the_wrong_length_raises_like_the_reference(letters, case_dir):
+    """dm_simulator.py:553-569 indexes the string per qubit and the n-axis array with one index per letter."""
+    from oracle import ref_harness
+    c = C.ghz(2)
+    c.measure(0, 0, basis="Expect", add_param=letters)
+    with pytest.raises(IndexError):
+        _run(emu_backend(), c)
+    with pytest.raises(IndexError):
+        dm_oracle.run_oracle(2, copy.deepcopy(c.instructions), {})
+    if ref_harness.available():
+        with pytest.raises(IndexError):
+            ref_harness.run_reference(2, copy.deepcopy(c.instructions), {})

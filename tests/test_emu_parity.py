@@ -28,16 +28,6 @@ def test_backend_on_emulated_kernels_matches_golden(name, golden, case_dir):
     check_against_golden(golden, name, run_case(name))
 
 
-@pytest.mark.parametrize("name", ["layered_n8_d6_noisy", "layered_n9_d4_memnoise", "layered_n10_d3_noisy", "rand_n7_fullnoise",
-                                  "qft8_binary", "grover4_noisy"])
-def test_fused_remap_swaps_match_golden(name, golden, case_dir, monkeypatch):
-    """dmb_op.post_swap (remap swap folded into the previous op's store), opt-in via
-    schedule.FUSE_SWAPS_DEFAULT: same numbers as explicit swap ops."""
-    from qiskit_aakash_b200 import schedule
-    monkeypatch.setattr(schedule, "FUSE_SWAPS_DEFAULT", True)
-    check_against_golden(golden, name, run_case(name))
-
-
 def test_mid_circuit_readouts_vs_oracle_on_emulated_kernels():
     """Same scenario as the GPU test of that name, n = 7, against the oracle."""
     import copy
@@ -113,14 +103,15 @@ def test_trailing_swaps_are_folded_into_the_store(golden, case_dir, monkeypatch)
         assert results["1"][key] == results["0"][key]
 
 
-@pytest.mark.parametrize("variant", [8, 10, 13])
-def test_half_cta_and_paired_kernel_bodies_match_golden(variant, golden, case_dir):
-    """Opt-in tile-kernel variants 8/9 (half-CTA) and 10/11 (paired: one thread plays virtual threads 2u and
-    2u + 1, mode-A ops move both 16-blocks with 128-bit accesses -- dmb_lean_op_pair) run the same per-thread
-    bodies here as on the GPU (13 = 10 with the zero-mean TSP factor folded into the control map on the host); the default
-    kernel stays variant 0."""
+@pytest.mark.parametrize("variant,fold_tsp0", [(0, "1"), (0, "0"), (1, "1")])
+def test_kernel_variants_match_golden(variant, fold_tsp0, golden, case_dir, monkeypatch):
+    """The shipped tile kernel (variant 0: one thread plays virtual threads 2u and 2u + 1, ops that leave tile digit 0
+    free move both 16-blocks with 128-bit accesses -- dmb_lean_op_pair -- and the <cos a> factor of a zero-mean TSP
+    CNOT is folded into the control digit's map on the host; DMB_FOLD_TSP0=0 switches that fold off) and the generic
+    register-staged A/B baseline (variant 1) run the same per-thread bodies here as on the GPU."""
     import ctypes
     from emu_backend import emu_engine, emu_lib
+    monkeypatch.setenv("DMB_FOLD_TSP0", fold_tsp0)
     lib = emu_lib()
     hook = lib.dmb_emu_paired_ops
     hook.restype = ctypes.c_long
@@ -133,4 +124,4 @@ def test_half_cta_and_paired_kernel_bodies_match_golden(variant, golden, case_di
                 check_against_golden(golden, name, run_case(name))
     finally:
         ctx.set_tile_variant(0)
-    assert (hook() > before) == (variant >= 10)
+    assert (hook() > before) == (variant == 0)

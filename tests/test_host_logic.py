@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     lib2 = capi.load_library()
-    assert lib2.dmb_abi_version() == capi.ABI_VERSION == 3
+    assert lib2.dmb_abi_version() == capi.ABI_VERSION == 4
     assert lib2.dmb_sizeof_op() == capi.OP_DTYPE.itemsize == 336
     assert lib2.dmb_sizeof_pass() == capi.PASS_DTYPE.itemsize == 32 + 16 * 336
     assert lib2.dmb_sizeof_qop() == capi.QOP_DTYPE.itemsize == 336
@@ -189,7 +189,7 @@ def test_lane_order_is_bank_conflict_free(a, b):
 
 @pytest.mark.parametrize("a,b", [(a, b) for a in range(1, 6) for b in range(1, 6) if a != b])
 def test_paired_kernel_mode_a_is_bank_conflict_free(a, b):
-    """Paired tile kernel (variants 10/11, dmb_lean_op_pair): real lane u plays virtual threads 2u / 2u + 1 and
+    """Tile kernel, paired op body (dmb_lean_op_pair): real lane u plays virtual threads 2u / 2u + 1 and
     moves both blocks with one 128-bit access per (i, j).  lane_order puts tile digit 0 first, so the pair
     (2u, 2u + 1) is one 16-byte chunk, and a quarter-warp of real lanes must hit 8 distinct chunks."""
     K = 6
@@ -268,7 +268,7 @@ def test_relabel_scheduler_is_a_valid_reordering(n_qubits, max_ops):
     nd = max(n_qubits, 2)
     pos = [n_qubits - 1 - q for q in range(n_qubits)]
     sim = {p: q for q, p in enumerate(pos)}                  # digit position -> qubit
-    passes = schedule.build_passes_relabel(qops, pos, nd, max_ops=max_ops, fuse=(max_ops % 4 != 0))
+    passes = schedule.build_passes_relabel(qops, pos, nd, max_ops=max_ops)
     last, seen = {}, []
     for p in passes:
         K = int(p["n_tile_digits"])
@@ -290,12 +290,6 @@ def test_relabel_scheduler_is_a_valid_reordering(n_qubits, max_ops):
                 assert last.get(q, -1) < tag
                 last[q] = tag
             seen.append(tag)
-            if o["post_swap"] == 3:                      # fused layout remaps
-                sim[da], sim[db] = sim.get(db), sim.get(da)
-            elif o["post_swap"] in (1, 2):
-                dx, dt = tile[o["post_swap_with"]], (da if o["post_swap"] == 1 else db)
-                assert dx not in (da, db)
-                sim[dx], sim[dt] = sim.get(dt), sim.get(dx)
     assert sorted(seen) == list(range(len(qops)))
     for q in range(n_qubits):
         assert sim[pos[q]] == q

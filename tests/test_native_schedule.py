@@ -63,7 +63,7 @@ def test_native_scheduler_is_byte_identical_to_the_python_specification(seed):
     max_ops = int(rng.choice([4, 8, 10, 12, 16]))
     pos0 = [int(x) for x in rng.permutation(n)]
     want_pos = list(pos0)
-    want = schedule.build_passes_relabel(list(ops), want_pos, nd, max_ops=max_ops, fuse=False)
+    want = schedule.build_passes_relabel(list(ops), want_pos, nd, max_ops=max_ops)
     for name, lib in _libs():
         pos = list(pos0)
         got = schedule.relabel_passes(lib, list(ops), pos, nd, max_ops=max_ops, native=True)
@@ -85,11 +85,11 @@ def test_native_scheduler_streaming_tail_matches(seed):
         for i in range(0, len(ops), 50):
             qa += ops[i:i + 50]
             qb += ops[i:i + 50]
-            pa, qa = schedule.build_passes_relabel(qa, pos_a, n, max_ops=10, min_tail=tail, fuse=False)
+            pa, qa = schedule.build_passes_relabel(qa, pos_a, n, max_ops=10, min_tail=tail)
             pb, qb = schedule.relabel_passes(lib, qb, pos_b, n, max_ops=10, min_tail=tail, native=True)
             assert pa.tobytes() == pb.tobytes() and pos_a == pos_b, name
             assert len(qa) == len(qb) and all(x is y for x, y in zip(qa, qb)), name
-        fa = schedule.build_passes_relabel(qa, pos_a, n, max_ops=10, fuse=False)
+        fa = schedule.build_passes_relabel(qa, pos_a, n, max_ops=10)
         fb = schedule.relabel_passes(lib, qb, pos_b, n, max_ops=10, native=True)
         assert fa.tobytes() == fb.tobytes() and pos_a == pos_b, name
 
@@ -110,7 +110,7 @@ def test_native_scheduler_final_moves_match(seed):
     if seed == 7:
         moves = []
     want_pos = list(pos0)
-    want, want_left = schedule.build_passes_relabel(list(ops), want_pos, n_loc, max_ops=10, fuse=False,
+    want, want_left = schedule.build_passes_relabel(list(ops), want_pos, n_loc, max_ops=10,
                                                     final_moves=list(moves))
     for name, lib in _libs():
         pos = list(pos0)
@@ -130,7 +130,7 @@ def test_native_scheduler_on_the_benchmark_circuit_shape():
            for ins in circ.instructions if ins.name == "cx"]
     pos_a, pos_b = [n - 1 - q for q in range(n)], [n - 1 - q for q in range(n)]
     t0 = time.perf_counter()
-    want = schedule.build_passes_relabel(list(ops), pos_a, n, max_ops=10, fuse=False)
+    want = schedule.build_passes_relabel(list(ops), pos_a, n, max_ops=10)
     t1 = time.perf_counter()
     got = schedule.relabel_passes(capi.load_library(), list(ops), pos_b, n, max_ops=10, native=True)
     t2 = time.perf_counter()

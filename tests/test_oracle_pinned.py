@@ -168,3 +168,28 @@ def test_oracle_matches_live_reference_on_random_programs():
     out = subprocess.run([sys.executable, os.path.join(root, "tests", "harness", "fuzz_oracle.py"), "--seeds", "120", "--start", "50000"],
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0 and "'ok': 120" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_n12_reference_fixture_is_complete():
+    """tests/golden/golden_n12.npz (full circuits at n = 12 from the unmodified reference) carries what the GPU test
+    compares: levels, strided coefficients, three checksums and the probabilities of both cases."""
+    import cases_n12
+    g = cases_n12.load_golden()
+    for name, probs, n_probs in (("grover12_noisy", "partial_probability", 2 ** 7),
+                                 ("layered_n12_d6_noisy", "ensemble_probability", 2 ** 12)):
+        assert g[name + "/coeff"].size == -(-4 ** 12 // cases_n12.STRIDE)
+        assert abs(float(g[name + "/coeff"][0]) * 2 ** 12 - 1) <= 1e-12
+        for k in ("levels", "coeff_sum", "coeff_sumsq", "coeff_signed"):
+            assert name + "/" + k in g.files
+        p = g[name + "/" + probs]
+        assert p.size == n_probs and abs(p.sum() - 1) <= 1e-10
+
+
+@pytest.mark.skipif(not os.environ.get("DMB_SLOW_TESTS"), reason="4.5 CPU-minutes; run with DMB_SLOW_TESTS=1 "
+                    "(last run: worst |delta| 3.5e-18 / 1.7e-18, recorded in DESIGN.md section 2)")
+@pytest.mark.parametrize("name", ["grover12_noisy", "layered_n12_d6_noisy"])
+def test_oracle_matches_the_reference_at_n12(name):
+    import cases_n12
+    case = cases_n12.get(name)
+    res = O.run_oracle(case["n"], case["instrs"], case["options"])
+    assert cases_n12.check(cases_n12.load_golden(), name, res) <= 1e-12
