@@ -105,8 +105,7 @@ int dmb_reset_stats(dmb_ctx* ctx);
 /* Tile-kernel variant for 4^6-coefficient tiles (A/B switch for measurements, not a feature):
  *   0 = the shipped kernel k_tile_pass6: 128 threads per tile, one 32 KiB cp.async stage per CTA, 5 CTAs per SM;
  *       ops that leave tile digit 0 free move two 16-blocks per thread with 128-bit shared-memory accesses
- *   1 = the generic register-staged kernel k_tile_pass<6> (one tile per CTA iteration), the A/B baseline
- *   2 / 3 = variant 0 with 4 / 6 CTAs per SM. */
+ *   1 = the generic register-staged kernel k_tile_pass<6> (one tile per CTA iteration), the A/B baseline. */
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant);
 
 /* ---- state initialisation (replaces DmSimulatorPy._initialize_densitymatrix,

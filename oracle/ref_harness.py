@@ -3,11 +3,14 @@
 This module exists to pin ``oracle/dm_oracle.py`` (the CPU restatement) and to
 generate the golden fixtures under ``tests/golden/``.  It imports the reference's
 own files **by path** from ``/root/reference`` (read-only; present in the build
-container, absent on the GPU box), so it can only be used where that tree exists:
+container, absent on the GPU box) or, where that tree does not exist, from the copy of
+exactly these three files that ``oracle/stage_ref.py`` (run by ``__graft_entry__.build()`` in
+the build container) stages under the git-ignored ``oracle/_ref/`` so that it travels to the
+GPU box with the snapshot -- ``bench.py``'s CPU legs then time the real reference there:
 
-    /root/reference/qiskit/providers/basicaer/exceptions.py
-    /root/reference/qiskit/providers/basicaer/basicaertools.py
-    /root/reference/qiskit/providers/basicaer/dm_simulator.py
+    <root>/qiskit/providers/basicaer/exceptions.py
+    <root>/qiskit/providers/basicaer/basicaertools.py
+    <root>/qiskit/providers/basicaer/dm_simulator.py
 
 ``import qiskit`` itself cannot work here (marshmallow / ply / matplotlib are not
 installed), therefore the handful of modules the two hot-path
@@ -23,7 +26,19 @@ import sys
 import types
 from types import SimpleNamespace as NS
 
-REFERENCE_ROOT = os.environ.get("DMB_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root():
+    env = os.environ.get("DMB_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile(os.path.join("/root/reference", "qiskit", "providers", "basicaer", "dm_simulator.py")):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = _pick_root()
 _BASICAER = os.path.join(REFERENCE_ROOT, "qiskit", "providers", "basicaer")
 
 _loaded = None

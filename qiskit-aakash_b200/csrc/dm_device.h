@@ -171,19 +171,6 @@ DMB_HD void dmb_cx_tsp0(double (&v)[4][4], double c, double c2, double s2) {
   v[2][0] = c * yx; v[2][1] = c * yi; v[2][2] = -(c * xz); v[2][3] = c * xy;
 }
 
-// The same with the factor c already applied by the control digit's map (DMB_KIND_TSP0F).
-DMB_HD void dmb_cx_tsp0f(double (&v)[4][4], double c2, double s2) {
-  const double iy = v[0][2], zy = v[3][2], iz = v[0][3], zz = v[3][3];
-  v[0][2] = s2 * iy + c2 * zy;
-  v[3][2] = c2 * iy + s2 * zy;
-  v[0][3] = s2 * iz + c2 * zz;
-  v[3][3] = c2 * iz + s2 * zz;
-  const double xi = v[1][0], xx = v[1][1], xy = v[1][2], xz = v[1][3];
-  const double yi = v[2][0], yx = v[2][1], yy = v[2][2], yz = v[2][3];
-  v[1][0] = xx; v[1][1] = xi; v[1][2] = yz; v[1][3] = -yy;
-  v[2][0] = yx; v[2][1] = yi; v[2][2] = -xz; v[2][3] = xy;
-}
-
 // Ideal CNOT: the same map with (c,s,c2,s2,cs) = (1,0,1,0,0) -- a signed permutation.
 DMB_HD void dmb_cx_ideal(double (&v)[4][4]) {
   double t;
@@ -346,7 +333,6 @@ DMB_HD uint32_t dmb_st_source(uint32_t l2, const int32_t* perm) {
 // code (no flag branches, no register moves at control-flow merges: 302 -> ~190 issued
 // instructions per op); everything else runs the generic body.
 #define DMB_KIND_TSP0 5
-#define DMB_KIND_TSP0F 6      // TSP0 whose <cos a> factor was folded into rows 1-2 of the control digit's map (paired body only)
 DMB_HD int dmb_variant_id(int kindx, int ma, int mb, int mode) { return ((kindx * 3 + ma) * 3 + mb) * 3 + mode; }
 inline bool dmb_variant_is_specialised(int kindx, int ma, int mb) {
   if (ma == mb && (ma == 1 || ma == 2))
@@ -405,8 +391,7 @@ inline bool dmb_fold_swaps_enabled() {         // DMB_FOLD_SWAPS=0 keeps trailin
   return on;
 }
 
-inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, bool fold_swaps = false,
-                               bool fold_tsp0 = false) {
+inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, bool fold_swaps = false) {
   L.n_tiles = 1ull << (n_bits - 2 * DMB_LEAN_K);
   L.n_ops = P.n_ops;
   L.pad_ = 0;
@@ -466,13 +451,6 @@ inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, 
     q.variant = dmb_variant_is_specialised(kx, ma, mb) ? dmb_variant_id(kx, ma, mb, q.mode) : -1;
     // thread digit 0 sits on tile digit 0: virtual threads 2u and 2u+1 own the two halves of every 16-byte pair
     if (q.mode == DMB_MODE_A && o.fd[0] == 0) q.flags |= DMB_PAIRABLE;
-    // The zero-mean TSP CNOT scales the eight X/Y-on-control entries by <cos a> after permuting them among
-    // themselves, so the factor moves into rows 1-2 of the control digit's map (8 FP64 fewer per block, exact up
-    // to one rounding).  Only for ops the paired body runs -- no other body knows the folded kind.
-    if (fold_tsp0 && kx == DMB_KIND_TSP0 && (q.flags & DMB_PAIRABLE) && ma == mb && ma != 0) {
-      for (int i = 0; i < 8; ++i) q.pa[i] *= q.coef[0];
-      q.variant = dmb_variant_id(DMB_KIND_TSP0F, ma, mb, q.mode);
-    }
   }
 }
 
@@ -627,7 +605,6 @@ DMB_HD void dmb_spec_math(const dmb_lean_op& op, double (&v)[4][4]) {
   }
   if constexpr (KINDX == DMB_OP_CX) dmb_cx_ideal(v);
   else if constexpr (KINDX == DMB_KIND_TSP0) dmb_cx_tsp0(v, op.coef[0], op.coef[2], op.coef[3]);
-  else if constexpr (KINDX == DMB_KIND_TSP0F) dmb_cx_tsp0f(v, op.coef[2], op.coef[3]);
   else if constexpr (KINDX == DMB_OP_CX_TSP) dmb_cx_tsp(v, op.coef[0], op.coef[1], op.coef[2], op.coef[3], op.coef[4]);
   else if constexpr (KINDX == DMB_OP_SWAP) {
 #pragma unroll
@@ -800,8 +777,6 @@ DMB_HD void dmb_lean_op_dispatch_pair(const dmb_lean_thread& P0, const dmb_lean_
       DMB_PAIR_CASE(DMB_OP_CX_TSP, 2, 2)
       DMB_PAIR_CASE(DMB_KIND_TSP0, 1, 1)
       DMB_PAIR_CASE(DMB_KIND_TSP0, 2, 2)
-      DMB_PAIR_CASE(DMB_KIND_TSP0F, 1, 1)
-      DMB_PAIR_CASE(DMB_KIND_TSP0F, 2, 2)
       DMB_PAIR_CASE(DMB_OP_SWAP, 0, 0)
       default: break;
     }

@@ -99,7 +99,7 @@ k_tile_pass(double* __restrict__ state, const __grid_constant__ dmb_pass P, uint
 // 5 CTAs per SM (persistent: CTA c handles tiles c, c + grid, ...).  The 16-byte pairs of a tile stream in
 // with cp.async.cg (LDGSTS, no register staging, L1 bypass), the fused ops run in place in shared memory
 // (one barrier after each), and the tile is written back with LDS.128 + STG.128 -- the other four CTAs of
-// the SM cover the HBM latency of this CTA's load, so no prefetch ring is needed (measured: 225 ms for
+// the SM cover the HBM latency of this CTA's load, so no prefetch ring is needed (measured: 223 ms for
 // BASELINE config 3 against 231 ms with a 2-stage ring x 3 CTAs and 252 ms for round 1's 256-thread kernel,
 // profiles/r02_tile_variants.md).  The control flow is dmb_half_kernel_body in dm_device.h, the function
 // the CPU tests run with real host threads; this is its CUDA execution context.
@@ -267,6 +267,7 @@ static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_p
   return 0;
 }
 
+#define DMB_TILE_CTAS 5      // CTAs per SM of k_tile_pass6 (measured on config 3: 4 -> 232.0 ms, 5 -> 223.0 ms, 6 -> 226.7 ms)
 template <int CTAS, int REMOTE, int STMODE>
 static int launch_tile6(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, const dmb_remote_src& S = g_no_remote) {
   const size_t smem = DMB_LEAN_TILE_BYTES;
@@ -290,20 +291,11 @@ static int launch_tile6_any(dmb_ctx* ctx, double* state, const dmb_lean_pass& L)
   return launch_tile6<CTAS, 0, DMB_ST_PLAIN>(ctx, state, L);
 }
 
-inline bool dmb_fold_tsp0_enabled() {          // DMB_FOLD_TSP0=0: A/B switch for the <cos a> fold (dmb_make_lean_pass)
-  static const bool on = [] { const char* e = getenv("DMB_FOLD_TSP0"); return !(e && e[0] == '0'); }();
-  return on;
-}
-
 static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass& P) {
   static thread_local dmb_lean_pass L;    // 6.5 KB: keep it off the stack; one host thread drives a ctx
-  dmb_make_lean_pass(P, n_bits, L, dmb_fold_swaps_enabled(), dmb_fold_tsp0_enabled());
+  dmb_make_lean_pass(P, n_bits, L, dmb_fold_swaps_enabled());
   ctx->stats.folded_swaps += (uint64_t)(P.n_ops - L.n_ops);
-  switch (ctx->tile_variant) {
-    case 2: return launch_tile6_any<4>(ctx, state, L);
-    case 3: return launch_tile6_any<6>(ctx, state, L);
-    default: return launch_tile6_any<5>(ctx, state, L);
-  }
+  return launch_tile6_any<DMB_TILE_CTAS>(ctx, state, L);
 }
 
 static int validate_pass(const dmb_pass& P, int n_bits) {
@@ -420,7 +412,7 @@ int dmb_reset_stats(dmb_ctx* ctx) {
 
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant) {
   if (!ctx) return fail("dmb_set_tile_variant", "null context");
-  if (variant < 0 || variant > 3) return fail("dmb_set_tile_variant", "variant must be 0..3");
+  if (variant < 0 || variant > 1) return fail("dmb_set_tile_variant", "variant must be 0 or 1");
   ctx->tile_variant = variant;
   return 0;
 }
@@ -498,8 +490,9 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
     case 5: rc = launch_tile_pass<5>(ctx, dst_state, n_bits, P, ld, st); break;
     case 6: {
       static thread_local dmb_lean_pass L;
-      dmb_make_lean_pass(P, n_bits, L, false, dmb_fold_tsp0_enabled());
-      rc = push ? launch_tile6<5, 2, DMB_ST_PLAIN>(ctx, dst_state, L, S) : launch_tile6<5, 1, DMB_ST_PLAIN>(ctx, dst_state, L, S);
+      dmb_make_lean_pass(P, n_bits, L);
+      rc = push ? launch_tile6<DMB_TILE_CTAS, 2, DMB_ST_PLAIN>(ctx, dst_state, L, S)
+                : launch_tile6<DMB_TILE_CTAS, 1, DMB_ST_PLAIN>(ctx, dst_state, L, S);
       break;
     }
     default: return fail("dmb_apply_pass_remote", "unsupported tile size");

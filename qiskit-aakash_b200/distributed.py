@@ -22,8 +22,10 @@ high bit of qubit 1's digit.
   whose global bits are not this rank's and folds pending maps of global qubits in as
   weights), one all-reduce of 2^n doubles, then the Walsh-Hadamard transform.
 
-Expect and Bell readouts work on a sharded state (owner rank reads, all-reduce).  Not sharded
-yet ("next"): N-basis ensemble, Pauli->matrix, compare/store.
+Every readout of the reference works on a sharded state: ensemble X/Y/Z/N, Expect and Bell (owner rank
+reads, all-reduce), ``store_densitymatrix`` / ``compare`` / ``stored_density_matrix`` as per-rank slice files
+(``canonicalise`` + ``store_shards`` / ``load_slice``: nothing is gathered), Pauli->matrix after a device-side
+all-gather (small registers only).
 """
 from __future__ import annotations
 
@@ -34,6 +36,15 @@ import numpy as np
 from . import capi, schedule
 from .engine import PauliEngine, TorchCudaAllocator, shared_context
 from .exceptions import BasicAerError
+
+
+def join_shard_files(stem, world, out=None):
+    """Concatenate the per-rank files of a sharded dump (``ShardedPauliEngine.store_shards``) into the single
+    ``<stem>.npy`` the reference writes and reads (``dm_simulator.py:1271-1282``)."""
+    parts = [np.load(ShardedPauliEngine.shard_file(stem, r, world), mmap_mode="r") for r in range(world)]
+    vec = np.concatenate(parts)
+    np.save(out or stem, vec)
+    return vec
 
 
 def log2_exact(x):
@@ -158,6 +169,11 @@ class TorchCommunicator:
 
     def barrier(self):
         self.dist.barrier(group=self.group)
+
+    def all_gather_device(self, out, shard):
+        """out[r * len(shard) : (r + 1) * len(shard)] = rank r's ``shard`` (device tensors; NCCL over NVLink)."""
+        k = shard.numel()
+        self.dist.all_gather([out[r * k:(r + 1) * k] for r in range(self.world)], shard, group=self.group)
 
     def all_gather_host(self, arr):
         out = [None] * self.world
@@ -404,7 +420,9 @@ class ShardedPauliEngine(PauliEngine):
                 for d in range(1 << px.block_bits):
                     sr, sb = px.image(self.rank, d)
                     tab[d] = (old[sr] + ((sb - d) << px.B) * 8) % (1 << 64)
+                ev = self._event_pair()
                 self.ctx.apply_pass_remote(self.alloc.ptr(self.scratch), self.n_bits, fused_pass, tab, px.B)
+                self._event_done(ev)
             else:
                 new = self.peers[self._cur ^ 1]      # the peers' idle buffers (free since the last barrier)
                 for s_blk in range(1 << px.block_bits):
@@ -421,6 +439,26 @@ class ShardedPauliEngine(PauliEngine):
         self.state, self.scratch = self.scratch, self.state
         self.exchanges += 1
         self.nvlink_bytes_sent += px.bytes_sent()
+
+    # optional CUDA-event timing of the exchange launches (bench.py: NVLink GB/s per exchange)
+    exchange_events = None
+
+    def alloc_has_events(self):
+        t = getattr(self.alloc, "torch", None)
+        return t is not None and t.cuda.is_available()
+
+    def _event_pair(self):
+        if self.exchange_events is None:
+            return None
+        t = self.alloc.torch
+        a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        a.record()
+        return a, b
+
+    def _event_done(self, ev):
+        if ev is not None:
+            ev[1].record()
+            self.exchange_events.append(ev)
 
     def _own_scratch(self):
         """Call before writing the scratch shard outside an exchange.  After a fused pull the
@@ -546,16 +584,21 @@ class ShardedPauliEngine(PauliEngine):
         self._localise_all_pending()
 
     def to_matrix(self):
-        """``_compute_densitymatrix`` of a sharded state: result formatting for registers small
-        enough that the 2^n x 2^n matrix is wanted at all -- the coefficient vector is gathered
-        (``download``) and converted by the single-device kernels on every rank's own GPU."""
+        """``_compute_densitymatrix`` of a sharded state (registers small enough that the 2^n x 2^n matrix is wanted
+        at all): the state is brought into the reference order, the shards are all-gathered DEVICE to device
+        (NCCL over NVLink -- no host round trip, no pickling) and every rank's GPU runs the Pauli->matrix kernels
+        on the full vector."""
         n = self.n
-        if 3 * 16 * 4 ** n > (64 << 30):
+        if n > 14 or 3 * 16 * 4 ** n > (64 << 30):
             raise BasicAerError("compute_densitymatrix on %d sharded qubits would need a %d GiB matrix; pass "
                                 "compute_densitymatrix=False" % (n, (16 * 4 ** n) >> 30))
-        vec = self.download()
+        self.canonicalise()
         src = self.alloc.empty(4 ** n)
-        self.ctx.upload(self.alloc.ptr(src), vec)
+        if callable(getattr(self.comm, "all_gather_device", None)):
+            self.ctx.sync()
+            self.comm.all_gather_device(src, self.state)
+        else:
+            self.ctx.upload(self.alloc.ptr(src), self.download())
         work = self.alloc.empty(2 * 4 ** n)
         out = self.alloc.empty(2 * 4 ** n)
         self.ctx.to_matrix(self.alloc.ptr(src), n, self.alloc.ptr(work), self.alloc.ptr(out))
@@ -579,6 +622,121 @@ class ShardedPauliEngine(PauliEngine):
             guard += 1
             if guard > 4:
                 raise BasicAerError("internal: pending maps could not be localised")
+
+    # -- canonical (reference-order) layout: rank r holds the contiguous slice [r * size, (r + 1) * size) ----
+    def _exchange_and_relabel(self):
+        self.exchange()
+        for q in range(self.n):
+            if self.pos[q] >= self.n_loc:
+                self.pos[q] -= self.m
+            elif self.pos[q] >= self.n_loc - self.m:
+                self.pos[q] += self.m
+
+    def _local_permute(self, wanted):
+        """Move qubit q to LOCAL slot wanted[q] (dict; all slots < n_loc) with SWAP ops in ordinary tile passes;
+        the displaced qubits take the vacated slots."""
+        pos = list(self.pos)
+        owner = {pos[q]: q for q in range(self.n)}
+        ops = []
+        for q, t in sorted(wanted.items(), key=lambda kv: -kv[1]):
+            if pos[q] >= self.n_loc or t >= self.n_loc:
+                raise BasicAerError("internal: _local_permute on a global slot")
+            if pos[q] != t:
+                other = owner[t]
+                ops.append(schedule.DevOp(capi.OP_SWAP, pos[q], t))
+                owner[pos[q]], pos[other] = other, pos[q]
+                owner[t], pos[q] = q, t
+        if ops:
+            self.run_passes(schedule.build_passes(ops, self.nd, max_ops=self.max_ops_per_pass,
+                                                  reserve_low=self.reserve_low))
+        self.pos = pos
+
+    def canonicalise(self):
+        """Bring the sharded state into the reference's order (qubit q at slot n-1-q), so that rank r's shard is
+        the contiguous slice [r * 4^n / G, (r+1) * 4^n / G) of ``DmSimulatorPy._densitymatrix`` -- what per-rank
+        dumps, per-rank uploads and the device-side all-gather need.  At most two slot exchanges: one to bring
+        wrongly placed global qubits home, one to send qubits 0 .. m-1 out in order; everything else is SWAP ops
+        in ordinary tile passes."""
+        self._localise_all_pending()
+        n, n_loc, m = self.n, self.n_loc, self.m
+        target = [n - 1 - q for q in range(n)]
+        if self.pos == target:
+            return
+        outer = [q for q in range(n) if target[q] >= n_loc]          # the qubits that belong in the global slots
+        if any(self.pos[q] != target[q] for q in outer):
+            if any(self.pos[q] >= n_loc for q in outer):
+                # some of them are global but in the wrong slot: bring the global slots home first, after making
+                # sure none of `outer` sits in the top local slots (those go out in the same exchange)
+                low = [s for s in range(n_loc - m) if all(self.pos[q] != s for q in outer)]
+                parked = {}
+                for q in outer:
+                    if n_loc - m <= self.pos[q] < n_loc:
+                        parked[q] = low.pop(0)
+                self._local_permute(parked)
+                self._exchange_and_relabel()
+            self._local_permute({q: target[q] - m for q in outer})
+            self._exchange_and_relabel()
+        self._local_permute({q: target[q] for q in range(n) if target[q] < n_loc})
+        if self.pos != target:
+            raise BasicAerError("internal: canonicalise did not reach the reference layout")
+
+    def download_shard(self, out=None):
+        """This rank's contiguous slice of the reference-order coefficient vector (no gather)."""
+        self.canonicalise()
+        shard = out if out is not None else np.empty(self.size)
+        self.ctx.download(self.sptr, shard)
+        return shard
+
+    @staticmethod
+    def shard_file(stem, rank, world):
+        """Per-rank file name of a sharded dump: ``<stem>.<rank>-of-<world>.npy`` (rank r holds elements
+        [r * 4^n / world, (r+1) * 4^n / world) of the reference-order vector)."""
+        return "%s.%03d-of-%03d.npy" % (stem, rank, world)
+
+    def store_shards(self, stem):
+        """``_store_density_matrix`` (``dm_simulator.py:1271-1275``) at sharded sizes: every rank writes its own
+        slice; nothing is gathered.  ``join_shard_files`` rebuilds the single file the reference writes."""
+        np.save(self.shard_file(stem, self.rank, self.world), self.download_shard())
+        self.comm.barrier()
+
+    def load_slice(self, stem):
+        """This rank's slice of a stored vector: from its shard file when a sharded dump exists, else memory-mapped
+        out of the single ``<stem>.npy`` the reference (or a one-GPU run) wrote.  Returns None when neither exists."""
+        import os as _os
+        name = self.shard_file(stem, self.rank, self.world)
+        if _os.path.exists(name):
+            part = np.load(name)
+        elif _os.path.exists(stem + ".npy"):
+            full = np.load(stem + ".npy", mmap_mode="r")
+            if full.size != 4 ** self.n:
+                raise BasicAerError("stored coefficients have the wrong length")
+            part = np.ascontiguousarray(full.reshape(-1)[self.rank * self.size:(self.rank + 1) * self.size])
+        else:
+            return None
+        if part.size != self.size:
+            raise BasicAerError("stored coefficients have the wrong length")
+        return np.ascontiguousarray(part, dtype=np.float64)
+
+    def upload_slice(self, part):
+        """Start from a stored state given as this rank's slice of the reference-order vector."""
+        self.pos = [self.n - 1 - q for q in range(self.n)]
+        self.ctx.upload(self.sptr, part)
+        self.h2d_bytes += part.nbytes
+        self.pending = [None] * self.n
+        self.queue = []
+
+    def overlap_with_slice(self, part):
+        """dot(stored, state) from per-rank slices: canonical layout, per-shard device reduction, one all-reduce."""
+        self.canonicalise()
+        self._own_scratch()
+        self.ctx.upload(self.alloc.ptr(self.scratch), part)
+        local = self.ctx.dot(self.alloc.ptr(self.scratch), self.sptr, self.size)
+        t = self.alloc.empty(1)
+        self.ctx.upload(self.alloc.ptr(t), np.array([local]))
+        self.comm.all_reduce_sum(t)
+        out = np.empty(1)
+        self.ctx.download(self.alloc.ptr(t), out)
+        return float(out[0])
 
     def chop(self, thr):
         self._localise_all_pending()
@@ -629,7 +787,8 @@ class ShardedPauliEngine(PauliEngine):
 
 
 class ShardedCircuitRunner:
-    """bench.py helper: compile the circuit once, then time init -> steps -> marginal."""
+    """bench.py helper: compile the circuit once (the backend's own level loop on an engine that does not launch),
+    then time init -> steps -> marginal."""
 
     def __init__(self, n, circ, opts, device=0, comm=None, engine=None):
         import copy
@@ -637,19 +796,20 @@ class ShardedCircuitRunner:
         from .dm_simulator import DmSimulatorB200
         self.n = n
         self.comm = comm or TorchCommunicator()
-        self.engine = engine or ShardedPauliEngine(n, self.comm, device=device)
-        be = DmSimulatorB200(device=device)
+        self.engine = e = engine or ShardedPauliEngine(n, self.comm, device=device)
+        be = DmSimulatorB200(device=device, _engine_factory=lambda nq: e)
         be._set_options(None, copy.deepcopy(opts))
+        be._number_of_qubits = n
         be._initialize_errors()
-        ops = hostpass.merge_single_qubit_gates(circ.instructions, n, True)
+        ops = hostpass.merge_single_qubit_gates(circ.instructions, n, be.MERGE)
         levels, self.n_levels = hostpass.partition_levels(ops, n)
-        e = self.engine
+        mem = be._error_params["memory"]
+        noise = eng.memory_noise_matrix(mem["decoherence"], mem["thermalization"], mem["amplitude_decay"])
+        noisy = not np.array_equal(noise, np.eye(4))
         for level in levels[:self.n_levels]:
-            for op in level:
-                if op.name in ("u1", "u3"):
-                    e.apply_1q(op.qubits[0], eng.gate_matrix(op.name, op.params, be._error_params["one_qubit_gates"]))
-                elif op.name == "cx":
-                    e.apply_cx(op.qubits[0], op.qubits[1], be._error_params["two_qubit_gates"])
+            be._run_level(e, level, None, {})
+            if noisy:
+                e.apply_1q_all(noise)
         self.steps = e.compile(final=True)
         self.final_pos = list(e.pos)
         self.final_pending = list(e.pending)
@@ -684,6 +844,7 @@ class ShardedCircuitRunner:
         self.engine.ctx.reset_stats()
         self.engine.exchanges = 0
         self.engine.nvlink_bytes_sent = 0
+        self.engine.exchange_events = [] if self.engine.alloc_has_events() else None
         self._ev = []
 
     def counters(self):
@@ -697,38 +858,35 @@ class ShardedCircuitRunner:
     def timed_pass_launches(self):
         return sum(ev[2] for ev in self._ev)
 
-    def e2e(self, args, circ_fn, opts, n_gates, device=0):
-        """Public-API timing on the sharded engine: backend.run(qobj).result() on every rank,
-        ensemble probabilities delivered to host memory; SHOW_FINAL_STATE is switched off (the
-        reference's own class flag) because gathering a 4^n vector from all ranks to one host
-        is result formatting, not the hot path.  Max over ranks."""
-        import copy
-        import time
+    def exchange_stats(self):
+        """NVLink traffic of the timed region: bytes each GPU pulled per slot swap and the rate it arrived at
+        (CUDA events around the fused exchange launch, which also applies that pass's ops)."""
+        e = self.engine
+        if not e.exchanges:
+            return {"exchanges": 0}
+        out = {"exchanges": e.exchanges, "mode": e.exchange_mode if e.peers is not None else "nccl",
+               "bytes_per_gpu_per_exchange": e.nvlink_bytes_sent // e.exchanges,
+               "nvlink_bytes_sent_per_gpu": e.nvlink_bytes_sent}
+        evs = getattr(e, "exchange_events", None)
+        if evs:
+            import torch
+            torch.cuda.synchronize()
+            ms = [a.elapsed_time(b) for a, b in evs]
+            out["avg_exchange_ms"] = sum(ms) / len(ms)
+            out["inbound_gbps_per_gpu"] = out["bytes_per_gpu_per_exchange"] / (out["avg_exchange_ms"] * 1e-3) / 1e9
+            out["nvlink5_line_rate_gbps"] = 900.0
+        return out
+
+    def close(self):
+        """Unmap the peers' buffers on every rank, THEN free this rank's shards (CUDA IPC: exported memory must
+        outlive its importers' mappings)."""
         import torch
-        from .dm_simulator import DmSimulatorB200, assemble
-        comm = self.comm
-        self.engine = None                      # the resident plan's buffers go back to torch's cache
-        be = DmSimulatorB200(_engine_factory=lambda nq: ShardedPauliEngine(nq, comm, device=device))
-        be.SHOW_FINAL_STATE = False
-        run_opts = dict(opts, compute_densitymatrix=False)
-        reps = max(1, min(args.steps, 2))
-        times, h2d = [], 0
-        for it in range(reps + 1):
-            comm.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            res = be.run(assemble(circ_fn()), backend_options=copy.deepcopy(run_opts)).result()
-            probs = res["results"][0]["data"]["ensemble_probability"]
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            if it:
-                times.append(dt)
-            h2d = be.last_engine_stats["h2d_bytes"]
-            be._engine = None
-            del res
-        t = torch.tensor([sum(times) / len(times)], device="cuda", dtype=torch.float64)
-        comm.dist.all_reduce(t, op=comm.dist.ReduceOp.MAX)
-        dt = float(t.item())
-        return {"value": n_gates * 16.0 * 4 ** self.n / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(8 * 2 ** self.n),
-                "prob_sum": float(sum(probs.values())), "note": "SHOW_FINAL_STATE=False (no 4^n gather)"}
+        if self.engine is not None:
+            self.engine.ctx.sync()
+            self.engine.close()
+            self.comm.barrier()
+        self.engine = None
+        self.steps = None
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+            self.comm.barrier()

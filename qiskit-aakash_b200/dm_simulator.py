@@ -313,11 +313,23 @@ class DmSimulatorB200:
             self.STORE_LOCAL = opts["store_densitymatrix"]
         if "compare" in opts:
             self.COMPARE = opts["compare"]
-            try:
-                self._density_matrix_stored = np.load("stored_coefficients.npy")
-                self.FILE_EXIST = True
-            except FileNotFoundError:
-                print("Stored Coefficient File does not exist")
+            comm = getattr(self, "_comm", None)
+            if comm is not None and comm.world > 1:
+                # sharded: every rank reads only its own slice, at the readout (engine.load_slice)
+                import os
+                from .distributed import ShardedPauliEngine
+                self._density_matrix_stored = None
+                if os.path.exists(ShardedPauliEngine.shard_file("stored_coefficients", comm.rank, comm.world)) \
+                        or os.path.exists("stored_coefficients.npy"):
+                    self.FILE_EXIST = True
+                else:
+                    print("Stored Coefficient File does not exist")
+            else:
+                try:
+                    self._density_matrix_stored = np.load("stored_coefficients.npy")
+                    self.FILE_EXIST = True
+                except FileNotFoundError:
+                    print("Stored Coefficient File does not exist")
 
     def _initialize_errors(self):
         """``_initialize_errors`` (``:273-282``)."""
@@ -354,6 +366,21 @@ class DmSimulatorB200:
                 raise BasicAerError("Wrong input binary string length")
             # kron order of :324-332: character i of the string belongs to qubit n-1-i
             engine.init_product([[1, 0, 0, 1 if s[n - 1 - q] == "0" else -1] for q in range(n)], scale)
+        elif self._custom_densitymatrix == "stored_density_matrix" and callable(getattr(engine, "load_slice", None)):
+            # sharded: every rank uploads its own slice (its shard file, or its part of the single file, memory-mapped)
+            part = engine.load_slice("stored_density_matrix")
+            if part is None:
+                print("Stored Coefficient File does not exist")
+                raise BasicAerError("stored_density_matrix.npy not found")
+            first = part[0] if engine.rank == 0 else None
+            if first is None:
+                import os
+                name0 = engine.shard_file("stored_density_matrix", 0, engine.world)
+                src = np.load(name0 if os.path.exists(name0) else "stored_density_matrix.npy", mmap_mode="r")
+                first = float(src.reshape(-1)[0])
+            if first != 2.0 ** (-n):
+                raise BasicAerError("Trace of initial densitymatrix is not one: {} != {}".format(first * 2 ** n, 1))
+            engine.upload_slice(part)
         elif self._custom_densitymatrix == "stored_density_matrix":
             try:
                 vec = np.load("stored_density_matrix.npy")
@@ -392,15 +419,19 @@ class DmSimulatorB200:
         else:
             probs = engine.marginal_probabilities(basis, err_param)
         prob = dict(zip(self._keys(n), probs))
+        sharded = callable(getattr(engine, "store_shards", None))
         if self.STORE_LOCAL:
-            vec = engine.download()
-            comm = getattr(engine, "comm", None)
-            if comm is None or comm.rank == 0:               # sharded: one writer, the others wait for the file
-                np.save("stored_coefficients", vec)
-            if comm is not None:
-                comm.barrier()
+            if sharded:
+                # per-rank slice files, nothing gathered; distributed.join_shard_files rebuilds the single
+                # stored_coefficients.npy of the reference (:1271-1275) when it is wanted
+                engine.store_shards("stored_coefficients")
+            else:
+                np.save("stored_coefficients", engine.download())
         if self.COMPARE and self.FILE_EXIST:
-            self._fidelity = engine.overlap_with(self._density_matrix_stored) * 2 ** n
+            if sharded and self._density_matrix_stored is None:
+                self._fidelity = engine.overlap_with_slice(engine.load_slice("stored_coefficients")) * 2 ** n
+            else:
+                self._fidelity = engine.overlap_with(self._density_matrix_stored) * 2 ** n
         return prob
 
     def _single_measure(self, engine, qubit, basis, nvec=None):

@@ -75,20 +75,16 @@ static void run_tile_pass(double* state, int n_bits, const dmb_pass& P, const dm
   }
 }
 
-// K = 6 path: the per-thread bodies of k_tile_pass6 (paired dispatch, folded swaps, folded <cos a>), run one virtual
+// K = 6 path: the per-thread bodies of k_tile_pass6 (paired dispatch, folded swaps), run one virtual
 // thread after the other, tiles one after another
 static int g_variant = 0;
 static thread_local long g_folded_swaps = 0;
 static long g_paired_ops = 0;     // thread-ops that went through dmb_lean_op_pair (test hook)
 extern "C" long dmb_emu_paired_ops(void) { return g_paired_ops; }
-static bool emu_fold_tsp0() {
-  const char* e = getenv("DMB_FOLD_TSP0");
-  return !(e && e[0] == '0');
-}
 static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const dmb_remote_src& S = g_no_remote,
                            const dmb_remote_src& D = g_no_remote) {
   static thread_local dmb_lean_pass L;
-  dmb_make_lean_pass(P, n_bits, L, dmb_fold_swaps_enabled() && !S.enabled && !D.enabled, emu_fold_tsp0());
+  dmb_make_lean_pass(P, n_bits, L, dmb_fold_swaps_enabled() && !S.enabled && !D.enabled);
   g_folded_swaps += P.n_ops - L.n_ops;
   alignas(128) static thread_local unsigned char stage[DMB_LEAN_TILE_BYTES];
   static thread_local dmb_lean_thread T[DMB_TILE_THREADS];
@@ -189,7 +185,7 @@ extern "C" int dmb_emu_run_half_kernel(double* state, int n_bits, const dmb_pass
   static thread_local dmb_lean_pass L;
   for (size_t i = 0; i < n_passes; ++i) {
     if (passes[i].n_tile_digits != DMB_LEAN_K) return 1;
-    dmb_make_lean_pass(passes[i], n_bits, L, dmb_fold_swaps_enabled(), paired && emu_fold_tsp0());
+    dmb_make_lean_pass(passes[i], n_bits, L, dmb_fold_swaps_enabled());
     uint64_t g = (uint64_t)grid < L.n_tiles ? (uint64_t)grid : L.n_tiles;
     if (paired && stages == 2) run_half_kernel<true, 2>(state, L, g);
     else if (paired) run_half_kernel<true, 1>(state, L, g);
@@ -249,7 +245,7 @@ int dmb_sync(dmb_ctx*) { return 0; }
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out) { *out = ctx->stats; return 0; }
 int dmb_reset_stats(dmb_ctx* ctx) { memset(&ctx->stats, 0, sizeof(dmb_stats)); return 0; }
 int dmb_set_tile_variant(dmb_ctx*, int variant) {
-  if (variant < 0 || variant > 3) return fail("dmb_set_tile_variant", "variant must be 0..3");
+  if (variant < 0 || variant > 1) return fail("dmb_set_tile_variant", "variant must be 0 or 1");
   g_variant = variant;
   return 0;
 }

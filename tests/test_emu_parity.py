@@ -103,15 +103,13 @@ def test_trailing_swaps_are_folded_into_the_store(golden, case_dir, monkeypatch)
         assert results["1"][key] == results["0"][key]
 
 
-@pytest.mark.parametrize("variant,fold_tsp0", [(0, "1"), (0, "0"), (1, "1")])
-def test_kernel_variants_match_golden(variant, fold_tsp0, golden, case_dir, monkeypatch):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_kernel_variants_match_golden(variant, golden, case_dir):
     """The shipped tile kernel (variant 0: one thread plays virtual threads 2u and 2u + 1, ops that leave tile digit 0
-    free move both 16-blocks with 128-bit accesses -- dmb_lean_op_pair -- and the <cos a> factor of a zero-mean TSP
-    CNOT is folded into the control digit's map on the host; DMB_FOLD_TSP0=0 switches that fold off) and the generic
-    register-staged A/B baseline (variant 1) run the same per-thread bodies here as on the GPU."""
+    free move both 16-blocks with 128-bit accesses -- dmb_lean_op_pair) and the generic register-staged A/B baseline
+    (variant 1) run the same per-thread bodies here as on the GPU."""
     import ctypes
     from emu_backend import emu_engine, emu_lib
-    monkeypatch.setenv("DMB_FOLD_TSP0", fold_tsp0)
     lib = emu_lib()
     hook = lib.dmb_emu_paired_ops
     hook.restype = ctypes.c_long

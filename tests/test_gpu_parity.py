@@ -265,7 +265,7 @@ def _extra_variants():
 @pytest.mark.parametrize("variant", [1] + _extra_variants())
 def test_tile_variant_parity(variant, backend, golden, case_dir, monkeypatch):
     """Parity of the non-default tile-kernel variants that ship in the library (1 = the generic register-staged
-    A/B baseline; DMB_TEST_TILE_VARIANT=2,3 adds the CTA-count variants while they exist): the golden cases that
+    A/B baseline; DMB_TEST_TILE_VARIANT adds experimental ones while they exist): the golden cases that
     reach the K = 6 kernel, 60 random programs with n >= 6, and the n = 14 round trip."""
     import os
     import sys

@@ -27,7 +27,26 @@ def _prep(n, seed):
     return circ
 
 
+_KIND = "emu"
+
+
+@pytest.fixture(autouse=True, params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def _which_backend(request):
+    """Every test of this module runs on the emulated kernels in the CPU suite and on the real library under
+    ``-m gpu``."""
+    global _KIND
+    _KIND = request.param
+    if _KIND == "cuda":
+        import __graft_entry__ as g
+        g.build()
+    yield
+    _KIND = "emu"
+
+
 def _backend():
+    if _KIND == "cuda":
+        from qiskit_aakash_b200 import DmSimulatorB200
+        return DmSimulatorB200()
     from emu_backend import emu_backend
     return emu_backend()
 

@@ -5,7 +5,6 @@ import numpy as np
 import pytest
 from scipy.stats import unitary_group
 
-from emu_backend import emu_backend
 from qiskit_aakash_b200 import QuantumCircuit, execute, unitary as U
 from qiskit_aakash_b200.exceptions import BasicAerError
 
@@ -111,17 +110,28 @@ def _circuit(seed, n=4):
     return qc, full
 
 
-def test_default_rejects_unitary_like_the_reference():
+@pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def backend(request):
+    """The emulated kernels in the CPU suite, the real library on a B200 under ``-m gpu``."""
+    if request.param == "cuda":
+        import __graft_entry__ as g
+        g.build()
+        from qiskit_aakash_b200 import DmSimulatorB200
+        return DmSimulatorB200
+    from emu_backend import emu_backend
+    return emu_backend
+
+
+def test_default_rejects_unitary_like_the_reference(backend):
     qc, _ = _circuit(1)
     with pytest.raises(BasicAerError, match="unrecognized instruction: unitary"):
-        execute(qc, emu_backend()).result()
+        execute(qc, backend()).result()
 
 
-@pytest.mark.parametrize("seed", range(4))
-def test_unitary_gates_without_quirks_match_dense_evolution(seed):
-    n = 4
+@pytest.mark.parametrize("seed,n", [(0, 4), (1, 4), (2, 4), (3, 4), (4, 7), (5, 8)])
+def test_unitary_gates_without_quirks_match_dense_evolution(seed, n, backend):
     qc, full = _circuit(seed, n)
-    res = execute(qc, emu_backend(), reference_quirks=False, compute_densitymatrix=True).result()["results"][0]
+    res = execute(qc, backend(), reference_quirks=False, compute_densitymatrix=True).result()["results"][0]
     rho0 = np.zeros((2 ** n, 2 ** n), dtype=complex)
     rho0[0, 0] = 1
     rho = full @ rho0 @ full.conj().T
@@ -129,11 +139,11 @@ def test_unitary_gates_without_quirks_match_dense_evolution(seed):
     assert abs(res["data"]["coeffmatrix"][0] * 2 ** n - 1) <= 1e-12
 
 
-def test_unitary_goes_through_the_noise_model():
+def test_unitary_goes_through_the_noise_model(backend):
     """Unrolled gates are ordinary u3 / cx: the TSP error is charged three times per two-qubit unitary."""
     qc = QuantumCircuit(2, 2)
     qc.unitary(unitary_group.rvs(4, random_state=9), [0, 1])
-    be = emu_backend()
+    be = backend()
     clean = execute(qc, be, reference_quirks=False).result()["results"][0]["data"]["coeffmatrix"]
     noisy = execute(qc, be, reference_quirks=False, tsp_model_error=[0.9, 0.0]).result()["results"][0]["data"]["coeffmatrix"]
     assert np.dot(noisy, noisy) < np.dot(clean, clean) - 1e-3      # purity drops
