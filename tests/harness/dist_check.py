@@ -48,7 +48,7 @@ def main():
             engines.append(e)
             return e
 
-        be = DmSimulatorB200(_engine_factory=factory)
+        be = DmSimulatorB200(_engine_factory=factory, comm=comm)
         c2 = C.Circuit(n)
         c2.instructions = copy.deepcopy(circ.instructions)
         res = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
@@ -65,6 +65,54 @@ def main():
                               "d_coeff": d_c, "exchanges": engines[0].exchanges, "fused_exchange": engines[0].peers is not None,
                               "nvlink_bytes_sent_per_rank": engines[0].nvlink_bytes_sent}))
         dist.barrier()
+    # sharded dumps: store -> per-rank slice files (no gather), compare and restart from them, canonical layout;
+    # through the PUBLIC constructor (DmSimulatorB200(comm=...): what get_backend returns inside a process group)
+    import tempfile
+    n = 9
+    tmp = [tempfile.mkdtemp(prefix="dmb_dist_") if rank == 0 else None]
+    dist.broadcast_object_list(tmp, src=0)
+    os.chdir(tmp[0])
+    opts = dict(cases.FULL_NOISE, compute_densitymatrix=False)
+    first = cases._rand_circuit(n, 50, 71)
+    first.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="Z")
+    assert DmSimulatorB200(comm=comm, device=local).configuration().n_qubits == {2: 17, 4: 17, 8: 18}.get(world, 16)
+    backends = []
+
+    def run_public(circ, o):
+        # a fresh backend per job: store_densitymatrix / compare stick to the instance like in the reference
+        backends.append(DmSimulatorB200(comm=comm, device=local))
+        c2 = C.Circuit(n)
+        c2.instructions = copy.deepcopy(circ.instructions)
+        return backends[-1].run(assemble(c2), backend_options=copy.deepcopy(o)).result()["results"][0]
+
+    run_public(first, dict(opts, store_densitymatrix=True))
+    assert os.path.exists(distributed.ShardedPauliEngine.shard_file("stored_coefficients", rank, world))
+    assert not os.path.exists("stored_coefficients.npy")
+    second = cases._rand_circuit(n, 50, 72)
+    second.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="Z")
+    fid = run_public(second, dict(opts, compare=True))["data"]["fidelity"]
+    be = backends[-1]
+    shard = be._engine.download_shard()
+    full = be._engine.download()
+    size = 4 ** n // world
+    d_dump = float(np.max(np.abs(shard - full[rank * size:(rank + 1) * size])))
+    if rank == 0:
+        joined = distributed.join_shard_files("stored_coefficients", world, out="joined")
+        os.makedirs("oracle")
+        os.chdir("oracle")
+        dm_oracle.run_oracle(n, copy.deepcopy(first.instructions), dict(copy.deepcopy(opts), store_densitymatrix=True))
+        d_dump = max(d_dump, float(np.max(np.abs(joined - np.load("stored_coefficients.npy")))))
+        want = dm_oracle.run_oracle(n, copy.deepcopy(second.instructions), dict(copy.deepcopy(opts), compare=True))["data"]["fidelity"]
+        d_dump = max(d_dump, abs(fid - want))
+        os.chdir(tmp[0])
+        worst = max(worst, d_dump)
+        print(json.dumps({"check": "sharded_dumps", "world": world, "n": n, "d": d_dump, "fidelity": fid}))
+    t = torch.tensor([d_dump], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert float(t.item()) <= 1e-10, float(t.item())
+    for b in backends:
+        b._engine = None
+    dist.barrier()
     # random programs (tests/harness/fuzz_emu.py's generator: every measurement mode mid-circuit, resets, random
     # options) -- includes the pattern that exposed the scratch-shard race after a fused pull (a readout
     # that uses the scratch shard as workspace right after an exchange)
