@@ -895,85 +895,6 @@ DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L,
 }
 
 // ---------------------------------------------------------------------------------------
-// Ring kernel (k_tile_ring6 in dmb200.cu): ONE persistent CTA per SM, G compute groups of 128 threads sharing a
-// ring of NST > G 32 KiB stages.
-//
-// Why: in k_tile_pass6 a CTA loads its tile, waits for it, computes, writes back -- while it waits, its 4 warps
-// are idle, and the op phase is latency-bound: throughput follows the number of warps that are computing
-// (profiles/r02_ring_kernel.md: 16 always-busy warps are slower than 20 sometimes-waiting ones).  Here every one
-// of the SM's 20 compute warps has its next tile prefetched while it works:
-//   * slot i of CTA b is tile b + i * grid; it lives in stage i % NST during ring round i / NST and is processed
-//     by group i % G (op bodies and write-back of k_tile_pass6, unchanged; a named barrier per group);
-//   * the group that has written slot i back re-uses the stage it just freed: its 128 threads issue the cp.async
-//     copies of slot i + NST and attach them to the stage's FULL mbarrier (cp.async.mbarrier.arrive: the arrival
-//     fires when that thread's copies have landed) -- NST - G tiles are in flight ahead of the groups, nobody
-//     waits for HBM in the steady state, and no EMPTY barrier is needed (a stage is refilled by its last user);
-//   * the group that owns slot i + NST waits on FULL[stage] with the round's parity before its first op.
-// Written against an execution-context policy like dmb_half_kernel_body so that the same control flow runs with
-// real host threads in tests/emu:
-//   tid / block / grid, copy16(stage byte offset, src), mem(stage byte offset) as before, plus
-//   group_sync(g)                       barrier of compute group g (128 threads)
-//   full_arrive_after_copies(stage)     arrive on FULL[stage] once my copies so far have landed
-//   full_wait(stage, parity)            wait for FULL[stage] to complete the round with this parity
-//   mark_consumed(stage, rounds) / wait_consumed(stage, rounds)
-//                                       a per-stage count of consumed rounds in shared memory.  mbarrier waits only
-//                                       know a phase's PARITY: a group that reached the wait for round r while
-//                                       the stage was still filling for round r - 1 would sail through (the
-//                                       groups are not synchronised with each other, so nothing but timing
-//                                       forbids that).  Waiting for "round r - 1 consumed" first pins the phase.
-// ---------------------------------------------------------------------------------------
-template <int STMODE, int REMOTE, int G, int NST, class Ctx>
-DMB_HD void dmb_ring_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L, const dmb_remote_src& R) {
-  static_assert(NST > G, "the ring needs at least one stage in flight ahead of the compute groups");
-  const int tid = cx.tid();
-  const int role = tid / DMB_HALF_THREADS;              // compute group
-  const int u = tid - role * DMB_HALF_THREADS;
-  const uint64_t first = cx.block(), stride = cx.grid();
-  if (first >= L.n_tiles) return;
-  const uint64_t n_slots = (L.n_tiles - first + stride - 1) / stride;
-  dmb_lean_thread S0, S1;                               // staging: virtual threads u and u + 128
-  dmb_lean_thread_init(u, L, S0);
-  dmb_lean_thread_init(u + DMB_HALF_THREADS, L, S1);
-  dmb_lean_thread P0;                                   // paired ops: virtual thread 2u (index digits only)
-  dmb_lean_thread_init(2 * u, L, P0);
-  auto fetch = [&](uint64_t slot) {                     // this group's 128 threads copy the slot's 2048 16-byte pairs
-    const uint32_t stage = (uint32_t)(slot % NST);
-    const uint64_t tb = dmb_tile_base(first + slot * stride, L.td, DMB_LEAN_K);
-    const uint32_t dst = stage * DMB_LEAN_TILE_BYTES;
-#pragma unroll
-    for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
-      const uint64_t i0 = tb + (S0.goff | L.pair_goff[i]), i1 = tb + (S1.goff | L.pair_goff[i]);
-      cx.copy16(dst + (S0.soff ^ L.pair_soff[i]),
-                REMOTE == 1 ? reinterpret_cast<const double*>(R.tab[i0 >> R.shift]) + i0 : state + i0);
-      cx.copy16(dst + (S1.soff ^ L.pair_soff[i]),
-                REMOTE == 1 ? reinterpret_cast<const double*>(R.tab[i1 >> R.shift]) + i1 : state + i1);
-    }
-    cx.full_arrive_after_copies(stage);
-  };
-  // prologue: the first NST slots, dealt to the groups round robin
-  for (uint64_t slot = (uint64_t)role; slot < (uint64_t)NST && slot < n_slots; slot += G) fetch(slot);
-  for (uint64_t slot = (uint64_t)role; slot < n_slots; slot += G) {
-    const uint32_t stage = (uint32_t)(slot % NST);
-    const uint32_t round = (uint32_t)(slot / NST);
-    if (round > 0) cx.wait_consumed(stage, round);      // the previous round of this stage is over: FULL is in phase `round`
-    cx.full_wait(stage, round & 1u);
-    const auto mem = cx.mem(stage * DMB_LEAN_TILE_BYTES);
-    for (int i = 0; i < L.n_ops; ++i) {
-      dmb_lean_op_dispatch_pair(P0, S0, L.ops[i], mem);
-      cx.group_sync(role);
-    }
-    const uint64_t tb = dmb_tile_base(first + slot * stride, L.td, DMB_LEAN_K);
-    dmb_lean_store_thread<REMOTE == 2, STMODE>(S0, L, state, tb, R, mem);
-    dmb_lean_store_thread<REMOTE == 2, STMODE>(S1, L, state, tb, R, mem);
-    cx.group_sync(role);                                // every thread's shared-memory reads of the stage are done
-    if (slot + NST < n_slots) {
-      if (u == 0) cx.mark_consumed(stage, round + 1u);
-      fetch(slot + NST);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------
 // Element-wise kernels (one logical thread per output element)
 // ---------------------------------------------------------------------------------------
 struct dmb_qubit_map {              // where each qubit's digit lives in the global index

@@ -160,77 +160,6 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
 }
 
 // ---------------------------------------------------------------------------------------
-// tile pass, K = 6, RING kernel: one persistent CTA per SM, G compute groups of 128 threads, NST 32 KiB stages,
-// one FULL mbarrier per stage (control flow: dmb_ring_kernel_body in dm_device.h; this is its CUDA execution
-// context).  cp.async copies complete on the stage's FULL mbarrier (cp.async.mbarrier.arrive.noinc: the barrier
-// is initialised with one expected arrival per thread of the issuing group), waiting threads spin on
-// mbarrier.try_wait.parity, groups synchronise on named barriers 1 .. G.
-// ---------------------------------------------------------------------------------------
-struct dmb_ring_cta {
-  uint32_t smem0;          // stages
-  uint32_t bar0;           // FULL[NST], 8 bytes each, then the consumed-round counters (4 bytes each)
-  uint32_t cnt0;
-  __device__ __forceinline__ void mark_consumed(uint32_t stage, uint32_t rounds) const {
-    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(cnt0 + 4u * stage), "r"(rounds) : "memory");
-  }
-  __device__ __forceinline__ void wait_consumed(uint32_t stage, uint32_t rounds) const {
-    uint32_t seen;
-    do {
-      asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(seen) : "r"(cnt0 + 4u * stage) : "memory");
-    } while (seen < rounds);
-  }
-  __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
-  __device__ __forceinline__ uint64_t block() const { return blockIdx.x; }
-  __device__ __forceinline__ uint64_t grid() const { return gridDim.x; }
-  __device__ __forceinline__ void copy16(uint32_t off, const double* src) const {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem0 + off), "l"(src) : "memory");
-  }
-  __device__ __forceinline__ dmb_smem_mem mem(uint32_t off) const {
-    dmb_smem_mem m;
-    m.base = smem0 + off;
-    return m;
-  }
-  __device__ __forceinline__ void group_sync(int g) const {
-    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(DMB_HALF_THREADS) : "memory");
-  }
-  __device__ __forceinline__ void full_arrive_after_copies(uint32_t stage) const {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar0 + 8u * stage) : "memory");
-  }
-  __device__ __forceinline__ void full_wait(uint32_t stage, uint32_t parity) const {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar0 + 8u * stage), "r"(parity) : "memory");
-  }
-};
-
-template <int G, int NST, int REMOTE, int STMODE>
-__global__ void __launch_bounds__(G * DMB_HALF_THREADS, 1)
-k_tile_ring6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L,
-             const __grid_constant__ dmb_remote_src S) {
-  extern __shared__ __align__(128) unsigned char lean_smem[];
-  dmb_ring_cta cx;
-  cx.smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
-  cx.bar0 = cx.smem0 + (uint32_t)NST * DMB_LEAN_TILE_BYTES;
-  cx.cnt0 = cx.bar0 + 8u * NST;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < NST; ++s) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cx.bar0 + 8u * s), "r"(DMB_HALF_THREADS) : "memory");
-      asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(cx.cnt0 + 4u * s), "r"(0) : "memory");
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  dmb_ring_kernel_body<STMODE, REMOTE, G, NST>(cx, state, L, S);
-}
-
-// ---------------------------------------------------------------------------------------
 // element-wise kernels
 // ---------------------------------------------------------------------------------------
 __global__ void k_init_product(double* __restrict__ state, uint64_t count, const __grid_constant__ dmb_init_params p) {
@@ -355,29 +284,6 @@ static int launch_tile6(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, con
   return 0;
 }
 
-template <int G, int NST, int REMOTE, int STMODE>
-static int launch_ring6(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, const dmb_remote_src& S = g_no_remote) {
-  const size_t smem = (size_t)NST * DMB_LEAN_TILE_BYTES + 16 * NST;
-  static std::atomic<uint64_t> attr_done[2];
-  const int dev = ctx->device & 127;
-  if (!((attr_done[dev >> 6].load() >> (dev & 63)) & 1ull)) {
-    CU_TRY(cudaFuncSetAttribute(k_tile_ring6<G, NST, REMOTE, STMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done[dev >> 6].fetch_or(1ull << (dev & 63));
-  }
-  uint64_t grid = (uint64_t)ctx->sm_count;
-  if (grid > L.n_tiles) grid = L.n_tiles;
-  k_tile_ring6<G, NST, REMOTE, STMODE><<<(unsigned)grid, G * DMB_HALF_THREADS, smem, ctx->stream>>>(state, L, S);
-  CU_TRY(cudaGetLastError());
-  return 0;
-}
-
-template <int G, int NST>
-static int launch_ring6_any(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
-  if (L.st_mode == DMB_ST_PERM128) return launch_ring6<G, NST, 0, DMB_ST_PERM128>(ctx, state, L);
-  if (L.st_mode == DMB_ST_SPLIT64) return launch_ring6<G, NST, 0, DMB_ST_SPLIT64>(ctx, state, L);
-  return launch_ring6<G, NST, 0, DMB_ST_PLAIN>(ctx, state, L);
-}
-
 template <int CTAS>
 static int launch_tile6_any(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
   if (L.st_mode == DMB_ST_PERM128) return launch_tile6<CTAS, 0, DMB_ST_PERM128>(ctx, state, L);
@@ -389,12 +295,7 @@ static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_
   static thread_local dmb_lean_pass L;    // 6.5 KB: keep it off the stack; one host thread drives a ctx
   dmb_make_lean_pass(P, n_bits, L, dmb_fold_swaps_enabled());
   ctx->stats.folded_swaps += (uint64_t)(P.n_ops - L.n_ops);
-  switch (ctx->tile_variant) {
-    case 2: return launch_ring6_any<5, 7>(ctx, state, L);
-    case 3: return launch_ring6_any<5, 6>(ctx, state, L);
-    case 4: return launch_ring6_any<4, 6>(ctx, state, L);
-    default: return launch_tile6_any<DMB_TILE_CTAS>(ctx, state, L);
-  }
+  return launch_tile6_any<DMB_TILE_CTAS>(ctx, state, L);
 }
 
 static int validate_pass(const dmb_pass& P, int n_bits) {
@@ -511,7 +412,7 @@ int dmb_reset_stats(dmb_ctx* ctx) {
 
 int dmb_set_tile_variant(dmb_ctx* ctx, int variant) {
   if (!ctx) return fail("dmb_set_tile_variant", "null context");
-  if (variant < 0 || variant > 4) return fail("dmb_set_tile_variant", "variant must be 0..4");
+  if (variant < 0 || variant > 1) return fail("dmb_set_tile_variant", "variant must be 0 or 1");
   ctx->tile_variant = variant;
   return 0;
 }

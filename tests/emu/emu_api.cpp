@@ -197,107 +197,6 @@ extern "C" int dmb_emu_run_half_kernel(double* state, int n_bits, const dmb_pass
   return 0;
 }
 
-// ---------------------------------------------------------------------------------------
-// The ring kernel's REAL control flow (dmb_ring_kernel_body, what k_tile_ring6 wraps) on host threads:
-// G * 128 std::threads per CTA, named group barriers, mbarriers emulated with the hardware's phase-parity
-// semantics, cp.async emulated as copies that land only when the issuing thread's cp.async.mbarrier.arrive fires.
-// ---------------------------------------------------------------------------------------
-struct emu_mbarrier {
-  std::mutex m;
-  std::condition_variable cv;
-  int expected = 1, count = 0;
-  long completed = 0;                       // number of completed phases; the current phase has parity completed & 1
-  void arrive() {
-    std::unique_lock<std::mutex> lk(m);
-    if (++count == expected) { count = 0; ++completed; cv.notify_all(); }
-  }
-  void wait(uint32_t parity) {              // returns once the phase with this parity has completed
-    std::unique_lock<std::mutex> lk(m);
-    cv.wait(lk, [&] { return (uint32_t)(completed & 1) != parity; });
-  }
-};
-
-struct emu_ring_shared {
-  unsigned char* stages;
-  std::vector<emu_mbarrier> full;
-  std::vector<std::atomic<uint32_t>> consumed;
-  std::vector<std::unique_ptr<emu_barrier>> groups;
-};
-
-struct emu_ring_thread {
-  int tid_;
-  uint64_t block_, grid_;
-  emu_ring_shared* sh;
-  std::vector<std::pair<uint32_t, const double*>> pending;
-  int tid() const { return tid_; }
-  uint64_t block() const { return block_; }
-  uint64_t grid() const { return grid_; }
-  void copy16(uint32_t off, const double* src) { pending.emplace_back(off, src); }
-  void full_arrive_after_copies(uint32_t stage) {
-    for (auto& c : pending) memcpy(sh->stages + c.first, c.second, 16);
-    pending.clear();
-    sh->full[stage].arrive();
-  }
-  void full_wait(uint32_t stage, uint32_t parity) { sh->full[stage].wait(parity); }
-  void group_sync(int g) { sh->groups[g]->wait(); }
-  void mark_consumed(uint32_t stage, uint32_t rounds) { sh->consumed[stage].store(rounds); }
-  void wait_consumed(uint32_t stage, uint32_t rounds) { while (sh->consumed[stage].load() < rounds) std::this_thread::yield(); }
-  dmb_host_mem mem(uint32_t off) const {
-    dmb_host_mem m;
-    m.base = sh->stages + off;
-    return m;
-  }
-};
-
-template <int STMODE, int G, int NST>
-static void run_ring_kernel_cta(double* state, const dmb_lean_pass& L, uint64_t block, uint64_t grid) {
-  std::vector<unsigned char> buf((size_t)NST * DMB_LEAN_TILE_BYTES + 128);
-  emu_ring_shared sh;
-  sh.stages = buf.data() + (128 - (reinterpret_cast<uintptr_t>(buf.data()) & 127)) % 128;
-  sh.full = std::vector<emu_mbarrier>(NST);
-  sh.consumed = std::vector<std::atomic<uint32_t>>(NST);
-  for (auto& c : sh.consumed) c.store(0);
-  for (auto& b : sh.full) b.expected = DMB_HALF_THREADS;
-  for (int g = 0; g < G; ++g) sh.groups.emplace_back(new emu_barrier(DMB_HALF_THREADS));
-  std::vector<std::thread> threads;
-  for (int t = 0; t < G * DMB_HALF_THREADS; ++t)
-    threads.emplace_back([&, t] {
-      emu_ring_thread cx;
-      cx.tid_ = t; cx.block_ = block; cx.grid_ = grid; cx.sh = &sh;
-      dmb_remote_src none;
-      none.enabled = 0;
-      dmb_ring_kernel_body<STMODE, 0, G, NST>(cx, state, L, none);
-    });
-  for (auto& th : threads) th.join();
-}
-
-template <int G, int NST>
-static void run_ring_kernel(double* state, const dmb_lean_pass& L, uint64_t grid) {
-  for (uint64_t block = 0; block < grid; ++block) {
-    if (L.st_mode == DMB_ST_PERM128) run_ring_kernel_cta<DMB_ST_PERM128, G, NST>(state, L, block, grid);
-    else if (L.st_mode == DMB_ST_SPLIT64) run_ring_kernel_cta<DMB_ST_SPLIT64, G, NST>(state, L, block, grid);
-    else run_ring_kernel_cta<DMB_ST_PLAIN, G, NST>(state, L, block, grid);
-  }
-}
-
-// test hook: run `n_passes` K = 6 passes through the threaded ring-kernel body (groups: 2 or 4 compute groups,
-// stages: ring depth, grid CTAs).  CTAs run one after another (they are independent: disjoint tiles).
-extern "C" int dmb_emu_run_ring_kernel(double* state, int n_bits, const dmb_pass* passes, size_t n_passes, int groups,
-                                       int stages, int grid) {
-  static thread_local dmb_lean_pass L;
-  for (size_t i = 0; i < n_passes; ++i) {
-    if (passes[i].n_tile_digits != DMB_LEAN_K) return 1;
-    dmb_make_lean_pass(passes[i], n_bits, L, dmb_fold_swaps_enabled());
-    uint64_t g = (uint64_t)grid < L.n_tiles ? (uint64_t)grid : L.n_tiles;
-    if (groups == 5 && stages == 7) run_ring_kernel<5, 7>(state, L, g);
-    else if (groups == 2 && stages == 3) run_ring_kernel<2, 3>(state, L, g);
-    else if (groups == 2 && stages == 5) run_ring_kernel<2, 5>(state, L, g);
-    else if (groups == 3 && stages == 4) run_ring_kernel<3, 4>(state, L, g);
-    else return 2;
-  }
-  return 0;
-}
-
 // test hook: thread order chosen for a SPLIT64 store + worst number of half-warp lanes per bank slot
 extern "C" int dmb_emu_split_order(const int32_t* perm, int32_t* tbit_out) {
   int ibit[3];
@@ -348,7 +247,7 @@ int dmb_sync(dmb_ctx*) { return 0; }
 int dmb_get_stats(dmb_ctx* ctx, dmb_stats* out) { *out = ctx->stats; return 0; }
 int dmb_reset_stats(dmb_ctx* ctx) { memset(&ctx->stats, 0, sizeof(dmb_stats)); return 0; }
 int dmb_set_tile_variant(dmb_ctx*, int variant) {
-  if (variant < 0 || variant > 4) return fail("dmb_set_tile_variant", "variant must be 0..4");
+  if (variant < 0 || variant > 1) return fail("dmb_set_tile_variant", "variant must be 0 or 1");
   g_variant = variant;
   return 0;
 }

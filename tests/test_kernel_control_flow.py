@@ -50,26 +50,3 @@ def test_threaded_kernel_body_equals_sequential_emulation(paired, stages, grid):
     assert rc == 0
     assert np.array_equal(got, want)
     assert not np.array_equal(got, start)
-
-
-@pytest.mark.parametrize("groups,stages,grid", [(2, 3, 1), (2, 5, 2), (5, 7, 1), (3, 4, 3), (2, 3, 5)])
-def test_ring_kernel_control_flow_on_host_threads(groups, stages, grid):
-    """``dmb_ring_kernel_body`` (the persistent kernel k_tile_ring6): groups x 128 real host threads per CTA -- compute
-    groups with their own barriers that refill the stage they just freed, FULL mbarriers with phase parity, copies
-    that land only when the issuing thread's arrive fires -- on passes from the real scheduler (relabelling stores
-    included); more and fewer tiles than ring slots.  Must reproduce the sequential emulation bit for bit."""
-    n = 8                                              # 16 tiles
-    P = _passes(n, 6, 70 + groups + stages, 8)
-    lib = emu_lib()
-    raw = ctypes.CDLL(lib._name)
-    start = np.random.default_rng(13).standard_normal(4 ** n)
-    want = start.copy()
-    ctx = capi.Context(lib, 0)
-    ctx.set_tile_variant(0)
-    ctx.apply_passes(want.ctypes.data, 2 * n, P)
-    got = start.copy()
-    rc = raw.dmb_emu_run_ring_kernel(ctypes.c_void_p(got.ctypes.data), ctypes.c_int(2 * n), P.ctypes.data_as(ctypes.c_void_p),
-                                     ctypes.c_size_t(len(P)), ctypes.c_int(groups), ctypes.c_int(stages), ctypes.c_int(grid))
-    assert rc == 0
-    assert np.array_equal(got, want)
-    assert not np.array_equal(got, start)
