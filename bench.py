@@ -540,7 +540,10 @@ def time_e2e(args, world, device, circ_fn, opts, n, n_gates, state_bytes):
         t = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+        dist.barrier()                   # every rank has unmapped its peers' shards before anyone frees them
     torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
     return {"value": n_gates * 16.0 * 4 ** n / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3,
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int((state_bytes if full_state else 0) + 8 * 2 ** n),
             "prob_sum": float(sum(probs.values())), "breakdown_ms": breakdown,

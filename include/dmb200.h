@@ -87,6 +87,8 @@ typedef struct dmb_stats {
   uint64_t fused_ops;            /* dmb_op entries executed                                */
   uint64_t state_bytes_moved;    /* algorithmic HBM bytes of tile passes: 16 B x elements  */
   uint64_t folded_swaps;         /* trailing SWAP ops realised by the relabelling write-back instead */
+  uint64_t small_plan_launches;  /* launches that ran a whole pass list (states of <= 16 tiles), counted in
+                                    tile_pass_launches too                                   */
 } dmb_stats;
 
 /* ---- context ------------------------------------------------------------------------ */
@@ -121,7 +123,10 @@ int dmb_init_product(dmb_ctx* ctx, double* state, int n_bits, uint64_t rank_bits
  *      amp_decay :397-425, _add_qasm_measure_X/Y/Z/N :574-704, the projections of
  *      _pauli_string_expectation :553-566, the mask of _add_bell_basis_measure :749-756,
  *      _add_qasm_reset :810-823) -- pre-scheduled into tile passes by the host.
- * `passes` is HOST memory; it is consumed before the call returns (kernel parameters).
+ * `passes` is HOST memory; it is consumed before the call returns (kernel parameters, or a
+ * staged copy).  For states of at most 4^8 coefficients a call with several passes is ONE launch:
+ * the tiles' CTAs form a thread-block cluster and meet at the cluster barrier between passes
+ * (dmb_stats.small_plan_launches; environment DMB_SMALL_PATH=0 disables this).
  * DMB_OP_SWAP ops WITHOUT maps at the end of a pass's op list are not executed in shared
  * memory: they are realised by the tile's write-back addressing (same result, counted in
  * dmb_stats.folded_swaps; environment DMB_FOLD_SWAPS=0 disables this).                   */

@@ -65,6 +65,10 @@ struct dmb_ctx {
   double* h_scratch;        // pinned host mirror
   uint64_t* d_idx;
   size_t scratch_elems;
+  // small-state path (whole pass list in one launch): device copy of the pre-converted passes + pinned staging
+  unsigned char* d_plan;
+  unsigned char* h_plan;
+  cudaEvent_t plan_copied;
 };
 
 static const size_t kScratchElems = 1 << 16;
@@ -157,6 +161,80 @@ k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L
   dmb_cuda_cta cx;
   cx.smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
   dmb_half_kernel_body<STMODE, true, 1, REMOTE>(cx, state, L, S);
+}
+
+// ---------------------------------------------------------------------------------------
+// Small states (at most 4^8 coefficients = 512 KiB, i.e. 1, 4 or 16 tiles): the WHOLE pass list of a flush in ONE
+// launch.  A circuit on <= 8 qubits is launch-bound when every pass is a kernel (QFT-8: five passes on a state
+// that lives in L2); here the tiles' CTAs form one thread-block cluster (16 CTAs: non-portable size, opted in),
+// each pass is "load my tile, run the ops, write it back" exactly as in k_tile_pass6, and between passes the
+// CTAs meet at the hardware cluster barrier (release / acquire: the write-backs of pass p are visible to the loads
+// of pass p + 1, which fetch through L2).  The pre-converted passes (dmb_lean_pass) are read from global memory.
+// States below one 4^6 tile (n_digits = K < 6): a single CTA keeps the one tile in shared memory across all passes.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(DMB_HALF_THREADS)
+k_small_passes6(double* __restrict__ state, const dmb_lean_pass* __restrict__ plan, int n_passes) {
+  extern __shared__ __align__(128) unsigned char lean_smem[];
+  dmb_cuda_cta cx;
+  cx.smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
+  const auto mem = cx.mem(0);
+  const int t = (int)threadIdx.x;
+  dmb_remote_src none;
+  none.enabled = 0;
+  for (int p = 0; p < n_passes; ++p) {
+    const dmb_lean_pass& L = plan[p];
+    dmb_lean_thread S0, S1, P0;
+    dmb_lean_thread_init(t, L, S0);
+    dmb_lean_thread_init(t + DMB_HALF_THREADS, L, S1);
+    dmb_lean_thread_init(2 * t, L, P0);
+    const uint64_t tb = dmb_tile_base(blockIdx.x, L.td, DMB_LEAN_K);
+#pragma unroll
+    for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
+      cx.copy16(S0.soff ^ L.pair_soff[i], state + tb + (S0.goff | L.pair_goff[i]));
+      cx.copy16(S1.soff ^ L.pair_soff[i], state + tb + (S1.goff | L.pair_goff[i]));
+    }
+    cx.commit();
+    cx.wait<0>();
+    __syncthreads();
+    for (int i = 0; i < L.n_ops; ++i) {
+      dmb_lean_op_dispatch_pair(P0, S0, L.ops[i], mem);
+      __syncthreads();
+    }
+    if (L.st_mode == DMB_ST_PERM128) {
+      dmb_lean_store_thread<false, DMB_ST_PERM128>(S0, L, state, tb, none, mem);
+      dmb_lean_store_thread<false, DMB_ST_PERM128>(S1, L, state, tb, none, mem);
+    } else if (L.st_mode == DMB_ST_SPLIT64) {
+      dmb_lean_store_thread<false, DMB_ST_SPLIT64>(S0, L, state, tb, none, mem);
+      dmb_lean_store_thread<false, DMB_ST_SPLIT64>(S1, L, state, tb, none, mem);
+    } else {
+      dmb_lean_store_thread<false, DMB_ST_PLAIN>(S0, L, state, tb, none, mem);
+      dmb_lean_store_thread<false, DMB_ST_PLAIN>(S1, L, state, tb, none, mem);
+    }
+    cluster_barrier();       // also a CTA barrier: the stage is free for the next pass's copies
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(DMB_TILE_THREADS)
+k_small_passes(double* __restrict__ state, const dmb_pass* __restrict__ plan, int n_passes) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int MAXPAIRS = ((1 << (2 * K - 1)) + DMB_TILE_THREADS - 1) / DMB_TILE_THREADS;
+  const int t = threadIdx.x;
+  dmb_remote_src none;
+  none.enabled = 0;
+  // n_digits == K: every pass's tile is the whole state in ascending digit order -- stage it once
+  dmb_tile_load_thread<MAXPAIRS>(t, state, 0, smem, plan[0].tile_digit, K, none);
+  __syncthreads();
+  for (int p = 0; p < n_passes; ++p)
+    for (int i = 0; i < plan[p].n_ops; ++i) {
+      dmb_tile_op_thread(t, plan[p].ops[i], smem, K);
+      __syncthreads();
+    }
+  dmb_tile_store_thread<MAXPAIRS>(t, state, 0, smem, plan[0].tile_digit, K, none);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -382,6 +460,11 @@ int dmb_destroy(dmb_ctx* ctx) {
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_idx);
   cudaFreeHost(ctx->h_scratch);
+  if (ctx->d_plan) {
+    cudaFree(ctx->d_plan);
+    cudaFreeHost(ctx->h_plan);
+    cudaEventDestroy(ctx->plan_copied);
+  }
   delete ctx;
   return 0;
 }
@@ -441,9 +524,94 @@ int dmb_init_product(dmb_ctx* ctx, double* state, int n_bits, uint64_t rank_bits
   return 0;
 }
 
+static const size_t kPlanBytes = 1 << 20;          // 1 MiB: 157 pre-converted K = 6 passes per launch
+
+static bool small_path_enabled() {                 // DMB_SMALL_PATH=0: one launch per pass also for small states (A/B)
+  static const bool on = [] { const char* e = getenv("DMB_SMALL_PATH"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+// n_passes >= 2 passes on a state of at most 16 tiles, all validated: one launch for all of them
+static int apply_passes_small(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* passes, size_t n_passes) {
+  const int K = passes[0].n_tile_digits;
+  if (!ctx->d_plan) {
+    CU_TRY(cudaMalloc(&ctx->d_plan, kPlanBytes));
+    CU_TRY(cudaMallocHost(&ctx->h_plan, kPlanBytes));
+    CU_TRY(cudaEventCreateWithFlags(&ctx->plan_copied, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(ctx->plan_copied, ctx->stream));
+  }
+  const size_t item = K == DMB_LEAN_K ? sizeof(dmb_lean_pass) : sizeof(dmb_pass);
+  const size_t per_launch = kPlanBytes / item;
+  for (size_t done = 0; done < n_passes; done += per_launch) {
+    const size_t m = (n_passes - done) < per_launch ? (n_passes - done) : per_launch;
+    CU_TRY(cudaEventSynchronize(ctx->plan_copied));        // the staging buffer is free again
+    if (K == DMB_LEAN_K) {
+      dmb_lean_pass* h = reinterpret_cast<dmb_lean_pass*>(ctx->h_plan);
+      for (size_t i = 0; i < m; ++i) {
+        dmb_make_lean_pass(passes[done + i], n_bits, h[i], dmb_fold_swaps_enabled());
+        ctx->stats.folded_swaps += (uint64_t)(passes[done + i].n_ops - h[i].n_ops);
+      }
+    } else {
+      memcpy(ctx->h_plan, passes + done, m * item);
+    }
+    CU_TRY(cudaMemcpyAsync(ctx->d_plan, ctx->h_plan, m * item, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaEventRecord(ctx->plan_copied, ctx->stream));
+    if (K == DMB_LEAN_K) {
+      const unsigned n_tiles = 1u << (n_bits - 2 * DMB_LEAN_K);
+      static std::atomic<uint64_t> attr_done[2];
+      const int dev = ctx->device & 127;
+      if (!((attr_done[dev >> 6].load() >> (dev & 63)) & 1ull)) {
+        CU_TRY(cudaFuncSetAttribute(k_small_passes6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DMB_LEAN_TILE_BYTES));
+        CU_TRY(cudaFuncSetAttribute(k_small_passes6, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        attr_done[dev >> 6].fetch_or(1ull << (dev & 63));
+      }
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(n_tiles, 1, 1);
+      cfg.blockDim = dim3(DMB_HALF_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = DMB_LEAN_TILE_BYTES;
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = n_tiles;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      CU_TRY(cudaLaunchKernelEx(&cfg, k_small_passes6, state, reinterpret_cast<const dmb_lean_pass*>(ctx->d_plan), (int)m));
+    } else {
+      const dmb_pass* d = reinterpret_cast<const dmb_pass*>(ctx->d_plan);
+      const size_t smem = sizeof(double) << (2 * K);
+      switch (K) {
+        case 2: k_small_passes<2><<<1, DMB_TILE_THREADS, smem, ctx->stream>>>(state, d, (int)m); break;
+        case 3: k_small_passes<3><<<1, DMB_TILE_THREADS, smem, ctx->stream>>>(state, d, (int)m); break;
+        case 4: k_small_passes<4><<<1, DMB_TILE_THREADS, smem, ctx->stream>>>(state, d, (int)m); break;
+        default: k_small_passes<5><<<1, DMB_TILE_THREADS, smem, ctx->stream>>>(state, d, (int)m); break;
+      }
+      CU_TRY(cudaGetLastError());
+    }
+    ctx->stats.tile_pass_launches++;
+    ctx->stats.small_plan_launches++;
+  }
+  for (size_t i = 0; i < n_passes; ++i) {
+    ctx->stats.fused_ops += (uint64_t)passes[i].n_ops;
+    ctx->stats.state_bytes_moved += 16ull << n_bits;
+  }
+  return 0;
+}
+
 int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* passes, size_t n_passes) {
   if (!ctx || !state || (!passes && n_passes)) return fail("dmb_apply_passes", "null argument");
   DMB_ON_DEVICE(ctx);
+  if (n_passes >= 2 && n_bits <= 16 && ctx->tile_variant == 0 && small_path_enabled()) {
+    bool same = true;
+    for (size_t i = 0; i < n_passes; ++i) {
+      if (validate_pass(passes[i], n_bits)) return 1;
+      if (passes[i].n_tile_digits != passes[0].n_tile_digits) same = false;
+    }
+    const int K = passes[0].n_tile_digits;
+    if (same && (K == DMB_LEAN_K || 2 * K == n_bits)) return apply_passes_small(ctx, state, n_bits, passes, n_passes);
+  }
   for (size_t i = 0; i < n_passes; ++i) {
     if (validate_pass(passes[i], n_bits)) return 1;
     const dmb_pass& P = passes[i];

@@ -51,6 +51,29 @@ def test_cuda_backend_matches_golden(name, golden, backend, case_dir):
     check_against_golden(golden, name, _run(backend, case["n"], case["instrs"], case["options"], name))
 
 
+@pytest.mark.parametrize("name", ["qft8", "qft8_binary", "rand_n7_fullnoise", "rand_n6_clean", "rand_n4_nomerge",
+                                  "layered_n8_d6_noisy"])
+def test_small_states_run_their_pass_list_in_one_launch(name, golden, backend, case_dir):
+    """(f)4: at most 4^8 coefficients -> all passes of a flush are ONE launch (k_small_passes6: the tiles' CTAs are a
+    thread-block cluster that meets at the cluster barrier between passes; k_small_passes<K> below one tile), and
+    the results are the reference's (golden fixtures; QFT-8 is BASELINE configs[0])."""
+    case = cases.get(name)
+    cases.write_files(case, ".")
+    be = backend()
+    res = be.run(__import__("qiskit_aakash_b200").assemble(_circ(case)), backend_options=case["options"]).result()
+    check_against_golden(golden, name, res["results"][0])
+    st = be.last_engine_stats
+    assert st["small_plan_launches"] >= 1
+    assert st["tile_pass_launches"] < st["passes"] or st["passes"] == st["small_plan_launches"]
+
+
+def _circ(case):
+    from qiskit_aakash_b200 import circuits as C
+    c = C.Circuit(case["n"], "c")
+    c.instructions = case["instrs"]
+    return c
+
+
 def _compare_with_oracle(backend, n, instrs, options):
     from oracle import dm_oracle
     got = _run(backend, n, copy.deepcopy(instrs), copy.deepcopy(options))
