@@ -180,6 +180,13 @@ def shared_context(lib, device_index):
 
 
 class PauliEngine:
+    # plan recording (dm_simulator.CompiledCircuit): when `tape` is a list every device-facing step is appended to it,
+    # so that the same circuit can be re-run later without any host-side lowering (class defaults: off)
+    tape = None
+    tape_outputs = 0
+    tape_valid = True
+    last_output = None
+
     def __init__(self, n_qubits, lib=None, allocator=None, device=0, max_ops_per_pass=None,
                  reserve_low=None, relabel=None):
         if n_qubits < 1 or n_qubits > capi.MAX_QUBITS:
@@ -239,10 +246,63 @@ class PauliEngine:
             lo.append(2 * self.n)
             v.append([1.0, 0.0, 0.0, 0.0])
         self.ctx.init_product(self.sptr, self.n_bits, 0, hi, lo, v, scale)
+        self._record(("init", list(hi), list(lo), [list(x) for x in v], float(scale)))
         self.pending = [None] * self.n
         self.queue = []
 
+    # -- plan recording ---------------------------------------------------------------------
+    def _record(self, entry, output=False):
+        """Append a device-facing step to the tape; returns the index of its host output (if it has one)."""
+        if self.tape is None:
+            return None
+        self.tape.append(entry)
+        if output:
+            self.tape_outputs += 1
+            return self.tape_outputs - 1
+        return None
+
+    def _not_replayable(self):
+        self.tape_valid = False
+
+    def replay(self, tape):
+        """Run a recorded tape on this engine's buffers: the C-ABI calls of the recording run, nothing else.
+        Returns the host outputs in recording order."""
+        ctx, outs = self.ctx, []
+        ctx.set_stream(self.alloc.stream())
+        for entry in tape:
+            kind = entry[0]
+            if kind == "init":
+                ctx.init_product(self.sptr, self.n_bits, 0, entry[1], entry[2], entry[3], entry[4])
+            elif kind == "passes":
+                ctx.apply_passes(self.sptr, self.n_bits, entry[1])
+            elif kind == "marginal":
+                n = entry[4]
+                out = self.alloc.empty(2 ** n)
+                ctx.marginal(self.sptr, self.n_bits, 0, entry[1], entry[2], entry[3], self.alloc.ptr(out))
+                ctx.fwht(self.alloc.ptr(out), n)
+                host = np.empty(2 ** n)
+                ctx.download(self.alloc.ptr(out), host)
+                outs.append(host)
+            elif kind == "chop":
+                ctx.chop(self.sptr, self.size, entry[1])
+            elif kind == "to_matrix":
+                n = self.n
+                work = self.alloc.empty(2 * 4 ** n)
+                out = self.alloc.empty(2 * 4 ** n)
+                ctx.to_matrix(self.sptr, n, self.alloc.ptr(work), self.alloc.ptr(out))
+                host = np.empty(2 * 4 ** n)
+                ctx.download(self.alloc.ptr(out), host)
+                outs.append(host.view(np.complex128).reshape(2 ** n, 2 ** n))
+            elif kind == "download":
+                host = np.empty(4 ** self.n)
+                ctx.download(self.sptr, host)
+                outs.append(host)
+            else:
+                raise BasicAerError("internal: unknown tape entry %r" % (kind,))
+        return outs
+
     def upload(self, vec):
+        self._not_replayable()
         vec = np.ascontiguousarray(vec, dtype=np.float64).reshape(-1)
         if vec.size != 4 ** self.n:
             raise BasicAerError("Wrong input stored density matrix")
@@ -364,6 +424,7 @@ class PauliEngine:
         if len(passes):
             self.ctx.set_stream(self.alloc.stream())
             self.ctx.apply_passes(self.sptr, self.n_bits, passes)
+            self._record(("passes", passes.copy()))
             self.passes_run += len(passes)
             self.h2d_bytes += passes.nbytes
 
@@ -387,11 +448,13 @@ class PauliEngine:
         self.ctx.fwht(self.alloc.ptr(out), n)
         host = np.empty(2 ** n)
         self.ctx.download(self.alloc.ptr(out), host)
+        self.last_output = self._record(("marginal", list(hi), list(lo), wt.copy(), n), output=True)
         return host
 
     def n_basis_probabilities(self, nvec, err):
         """Basis 'N' of ``_add_ensemble_measure`` (``:457-462``): contract every digit
         (I, X, Y, Z) -> (I, err * n.(X,Y,Z)), then the same Walsh-Hadamard transform."""
+        self._not_replayable()
         self.flush()
         self._require_reference_layout()
         n = self.n
@@ -427,6 +490,7 @@ class PauliEngine:
 
     def read_flat(self, flat_indices):
         """Coefficients at flat indices of the CURRENT layout (digit of qubit q at bits 2*pos[q])."""
+        self._not_replayable()
         self.settle()
         return self.ctx.read_coeffs(self.sptr, flat_indices)
 
@@ -491,11 +555,13 @@ class PauliEngine:
         self._require_reference_layout()
         host = out if out is not None else np.empty(4 ** self.n)
         self.ctx.download(self.sptr, host)
+        self.last_output = self._record(("download",), output=True)
         return host
 
     def chop(self, thr):
         self.flush()
         self.ctx.chop(self.sptr, self.size, thr)
+        self._record(("chop", float(thr)))
 
     def to_matrix(self):
         """``_compute_densitymatrix`` (``:1198-1255``) -> complex 2^n x 2^n numpy array."""
@@ -510,6 +576,7 @@ class PauliEngine:
         self._require_reference_layout()
         if self.nd > n:
             # 1-qubit register: convert on the first 4 coefficients (phantom digit is identity)
+            self._not_replayable()
             tmp = self.alloc.empty(4 ** n)
             self.ctx.upload(self.alloc.ptr(tmp), self.ctx.read_coeffs(self.sptr, list(range(4 ** n))))
             src_ptr = self.alloc.ptr(tmp)
@@ -520,10 +587,12 @@ class PauliEngine:
         self.ctx.to_matrix(src_ptr, n, self.alloc.ptr(work), self.alloc.ptr(out))
         host = np.empty(2 * 4 ** n)
         self.ctx.download(self.alloc.ptr(out), host)
+        self.last_output = self._record(("to_matrix",), output=True)
         return host.view(np.complex128).reshape(2 ** n, 2 ** n)
 
     def overlap_with(self, other_vec):
         """dot(other, state) (``_state_overlap``, ``:1277-1282``, without the 2^n factor)."""
+        self._not_replayable()
         self.flush()
         self._require_reference_layout()
         other_vec = np.ascontiguousarray(other_vec, dtype=np.float64).reshape(-1)

@@ -82,6 +82,23 @@ def main():
                               "prob_sum": psum, "data_keys": keys,
                               "breakdown_ms": {k: round(1e3 * v, 2) for k, v in st.items() if k.startswith("t_")}}))
             sys.stdout.flush()
+        if world == 1 and circ.n_qubits <= 12:
+            # compiled replay (DmSimulatorB200.compile): the same job without any host-side lowering
+            comp = DmSimulatorB200(device=local).compile(assemble(build()), backend_options=copy.deepcopy(opts))
+            if comp is not None:
+                ts = []
+                for rep in range(20):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    res = comp.run()
+                    torch.cuda.synchronize()
+                    ts.append(time.perf_counter() - t0)
+                probs = res["results"][0]["data"].get("ensemble_probability") or res["results"][0]["data"].get("partial_probability")
+                print(json.dumps({"config": name, "mode": "compiled replay", "wall_s_best": round(min(ts), 6),
+                                  "wall_s_median": round(sorted(ts)[len(ts) // 2], 6), "launches": comp.launches,
+                                  "tape_entries": len(comp._tape), "prob_sum": float(sum(probs.values())) if probs else None,
+                                  "data_keys": sorted(res["results"][0]["data"].keys())}))
+                sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,4 +1,4 @@
-"""Small end-to-end run for compute-sanitizer (memcheck / racecheck): n = 7 noisy layered circuit
+"""Small end-to-end runs for compute-sanitizer (memcheck / racecheck): n = 7 / 9 / 5 noisy layered circuits
 through the backend (lean tile kernel, swaps, marginal, FWHT, matrix conversion, chop, download)."""
 import os
 import sys
@@ -10,8 +10,10 @@ import __graft_entry__ as g  # noqa: E402
 g.build()
 from qiskit_aakash_b200 import BasicAer, execute, circuits  # noqa: E402
 
-circ = circuits.random_layered(7, 4, 7)
 opts = dict(circuits.noisy_options(), **circuits.grover_options())
-res = execute(circ, BasicAer.get_backend("dm_simulator"), **opts).result()
-d = res["results"][0]["data"]
-print("sanitize_smoke ok: prob sum %.15f trace %.15f" % (sum(d["ensemble_probability"].values()), d["coeffmatrix"][0] * 2 ** 7))
+for n in (7, 9, 5):        # 7: single-launch cluster path (4 tiles); 9: k_tile_pass6 (64 tiles); 5: below one tile
+    circ = circuits.random_layered(n, 4, 7)
+    res = execute(circ, BasicAer.get_backend("dm_simulator"), **dict(opts, compute_densitymatrix=(n <= 7))).result()
+    d = res["results"][0]["data"]
+    print("sanitize_smoke ok n=%d: prob sum %.15f trace %.15f" % (n, sum(d["ensemble_probability"].values()),
+                                                                    d["coeffmatrix"][0] * 2 ** n))
