@@ -230,6 +230,9 @@ int dmb_chop(dmb_ctx* ctx, double* state, uint64_t count, double thr);
  *      'coeffmatrix' :1181-1183); host memory should be pinned for full PCIe speed ------ */
 int dmb_upload(dmb_ctx* ctx, double* state, const double* host, uint64_t offset, uint64_t count);
 int dmb_download(dmb_ctx* ctx, const double* state, double* host, uint64_t offset, uint64_t count);
+/* The same without waiting: `host` (pinned) is valid after the next dmb_sync.  Lets a caller queue several
+ * readouts of one job and wait once.                                                                    */
+int dmb_download_async(dmb_ctx* ctx, const double* state, double* host, uint64_t offset, uint64_t count);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "dmb_chop": (_i, [_vp, _vp, _u64, _d]),
     "dmb_upload": (_i, [_vp, _vp, _vp, _u64, _u64]),
     "dmb_download": (_i, [_vp, _vp, _vp, _u64, _u64]),
+    "dmb_download_async": (_i, [_vp, _vp, _vp, _u64, _u64]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -263,6 +264,11 @@ class Context:
         host = np.ascontiguousarray(host, dtype=np.float64)
         self._check(self.lib.dmb_upload(self._h, state_ptr, _ptr(host), int(offset), host.size))
         self.sync()      # the host array may be a temporary
+
+    def download_async(self, state_ptr, host, offset=0):
+        """D2H copy without waiting: ``host`` (a C-contiguous float64 array in pinned memory) is valid after ``sync()``."""
+        assert host.dtype == np.float64 and host.flags["C_CONTIGUOUS"]
+        self._check(self.lib.dmb_download_async(self._h, state_ptr, _ptr(host), int(offset), host.size))
 
     def download(self, state_ptr, host, offset=0):
         assert host.dtype == np.float64 and host.flags["C_CONTIGUOUS"]

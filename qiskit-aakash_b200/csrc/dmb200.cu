@@ -875,4 +875,11 @@ int dmb_download(dmb_ctx* ctx, const double* state, double* host, uint64_t offse
   return 0;
 }
 
+int dmb_download_async(dmb_ctx* ctx, const double* state, double* host, uint64_t offset, uint64_t count) {
+  if (!ctx || !state || !host) return fail("dmb_download_async", "null argument");
+  DMB_ON_DEVICE(ctx);
+  CU_TRY(cudaMemcpyAsync(host, state + offset, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
 }  // extern "C"

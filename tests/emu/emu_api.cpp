@@ -426,4 +426,9 @@ int dmb_download(dmb_ctx*, const double* state, double* host, uint64_t offset, u
   return 0;
 }
 
+int dmb_download_async(dmb_ctx*, const double* state, double* host, uint64_t offset, uint64_t count) {
+  memcpy(host, state + offset, count * sizeof(double));
+  return 0;
+}
+
 }  // extern "C"

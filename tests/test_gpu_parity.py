@@ -51,7 +51,7 @@ def test_cuda_backend_matches_golden(name, golden, backend, case_dir):
     check_against_golden(golden, name, _run(backend, case["n"], case["instrs"], case["options"], name))
 
 
-@pytest.mark.parametrize("name", ["qft8", "qft8_binary", "rand_n7_fullnoise", "rand_n6_clean", "rand_n4_nomerge",
+@pytest.mark.parametrize("name", ["qft8", "qft8_binary", "rand_n7_fullnoise", "rand_n6_fullnoise", "rand_n4_nomerge",
                                   "layered_n8_d6_noisy"])
 def test_small_states_run_their_pass_list_in_one_launch(name, golden, backend, case_dir):
     """(f)4: at most 4^8 coefficients -> all passes of a flush are ONE launch (k_small_passes6: the tiles' CTAs are a
@@ -63,8 +63,10 @@ def test_small_states_run_their_pass_list_in_one_launch(name, golden, backend, c
     res = be.run(__import__("qiskit_aakash_b200").assemble(_circ(case)), backend_options=case["options"]).result()
     check_against_golden(golden, name, res["results"][0])
     st = be.last_engine_stats
-    assert st["small_plan_launches"] >= 1
-    assert st["tile_pass_launches"] < st["passes"] or st["passes"] == st["small_plan_launches"]
+    if st["passes"] > st["tile_pass_launches"]:        # some flush had more than one pass: it went out as one launch
+        assert st["small_plan_launches"] >= 1
+    else:                                              # every flush of this circuit was a single pass
+        assert st["small_plan_launches"] == 0
 
 
 def _circ(case):
