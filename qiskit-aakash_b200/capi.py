@@ -29,13 +29,14 @@ PASS_DTYPE = np.dtype([("n_tile_digits", "<i4"), ("n_ops", "<i4"), ("tile_digit"
 QOP_DTYPE = np.dtype([("kind", "<i4"), ("flags", "<i4"), ("qa", "<i4"), ("qb", "<i4"), ("pa", "<f8", (12,)),
                       ("pb", "<f8", (12,)), ("coef", "<f8", (16,))])
 
-ABI_VERSION = 4          # include/dmb200.h DMB_ABI_VERSION
+ABI_VERSION = 5          # include/dmb200.h DMB_ABI_VERSION
 
 
 class Stats(ctypes.Structure):
     _fields_ = [("tile_pass_launches", ctypes.c_uint64), ("other_launches", ctypes.c_uint64),
                 ("fused_ops", ctypes.c_uint64), ("state_bytes_moved", ctypes.c_uint64),
-                ("folded_swaps", ctypes.c_uint64), ("small_plan_launches", ctypes.c_uint64)]
+                ("folded_swaps", ctypes.c_uint64), ("small_plan_launches", ctypes.c_uint64),
+                ("direct_io_ops", ctypes.c_uint64)]
 
 
 class DmbError(RuntimeError):

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     lib2 = capi.load_library()
-    assert lib2.dmb_abi_version() == capi.ABI_VERSION == 4
+    assert lib2.dmb_abi_version() == capi.ABI_VERSION == 5
     assert lib2.dmb_sizeof_op() == capi.OP_DTYPE.itemsize == 336
     assert lib2.dmb_sizeof_pass() == capi.PASS_DTYPE.itemsize == 32 + 16 * 336
     assert lib2.dmb_sizeof_qop() == capi.QOP_DTYPE.itemsize == 336
