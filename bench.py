@@ -420,8 +420,7 @@ def run_ours(args):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": pass_ms, "algorithmic_bytes_per_launch": per_launch_bytes,
                 "fused_ops_per_launch": counters["fused_ops"] / launches,
-                "swaps_folded_into_store_per_launch": counters.get("folded_swaps", 0) / launches,
-                "direct_io_ops_per_launch": counters.get("direct_io_ops", 0) / launches}
+                "swaps_folded_into_store_per_launch": counters.get("folded_swaps", 0) / launches}
     if world == 1 and n <= 14:
         roofline.update(unfused_launch_points(runner.engine, n, peak))
         roofline["note"] = ("launches that fuse more than ~3 ops are shared-memory-bandwidth bound (one 64 KiB round "
@@ -429,11 +428,10 @@ def run_ours(args):
                             "improves; see staging_only / one_gate_per_launch for the HBM-bound operating points")
     # second roofline of the same launches: shared-memory traffic of the op phase.  Every op executed in shared
     # memory reads and writes the whole tile (2 x 8 B per coefficient), staging adds one write (cp.async) and one
-    # read (write-back); a first / last op with direct global I/O (dmb_stats.direct_io_ops) saves one of those plus
-    # its own read / write, i.e. one round trip; peak = 128 B/clk/SM x SMs x the SM clock sampled during the run.
+    # read (write-back); peak = 128 B/clk/SM x SMs x the SM clock sampled during the run.
     try:
         smem_ops = (counters["fused_ops"] - counters.get("folded_swaps", 0)) / launches
-        smem_bytes = (smem_ops + 1.0 - counters.get("direct_io_ops", 0) / launches) * 16.0 * 4 ** n / world
+        smem_bytes = (smem_ops + 1.0) * 16.0 * 4 ** n / world
         sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
         mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
         if mhz:

@@ -22,7 +22,6 @@
 #define DMB_TILE_THREADS 256
 
 struct alignas(16) dmb_d2 { double x, y; };
-struct alignas(16) dmb_d4 { double x, y, z, w; };
 
 // ---------------------------------------------------------------------------------------
 // Tile addressing
@@ -301,30 +300,6 @@ struct alignas(16) dmb_lean_op {
   double pa[12], pb[12], coef[16];
 };
 
-// Direct global I/O of a pass's FIRST and LAST op (dmb_io_op below).  The op phase is bound by the shared-memory
-// crossbar (128 B/clk/SM: one 64 KiB round trip of the tile per op), and staging a tile costs one more round trip
-// (cp.async writes it, the write-back reads it).  So the first op of a pass reads its 16-blocks straight from the
-// state vector into registers (instead of cp.async -> LDS) and the last one writes its result straight back
-// (instead of STS -> LDS -> STG): a pass with m ops makes m - 1 round trips through shared memory instead of m + 1.
-// The addresses are table driven like the shared-memory ones: the global BYTE offset of block element (i, j) of a
-// thread is  thread part | gij[4 i + j]  (disjoint bit fields), the thread part scatters the thread's index digits
-// with the shifts gsh[].  For the last op the tables use the digit positions AFTER the pass's folded swaps, i.e. the
-// relabelling store costs nothing extra.  `axis` names the register axis that is contiguous in global memory:
-//   DMB_AX_PAIR  the two halves of a 16-byte pair (paired ops, tile digit 0 stays global digit 0): 128-bit accesses,
-//                the neighbouring lane (high bit of digit 0) completes the 32-byte sector;
-//   DMB_AX_I / DMB_AX_J  the block's first / second digit lands on global digit 0: the four values are 32 contiguous
-//                bytes, moved as one 256-bit access (LDG.256 / STG.256).
-//   DMB_AX_LANE  (last op, paired) the digit that lands on global digit 0 is a free digit of the op: it is dealt to
-//                lane bits 1-2, so four neighbouring lanes write the 32 bytes of a sector with 64-bit stores.
-enum { DMB_AX_PAIR = 0, DMB_AX_I = 1, DMB_AX_J = 2, DMB_AX_LANE = 3 };
-struct alignas(16) dmb_lean_gop {
-  uint64_t gij[16];     // byte offset of block element (i, j)
-  uint64_t gpair;       // paired ops: byte distance between the blocks of virtual threads 2u and 2u + 1
-  uint32_t gsh[4];      // left shift (bits, the x8 included) placing thread digit m in the byte offset
-  int32_t axis;
-  int32_t enabled;
-};
-
 struct alignas(16) dmb_lean_pass {
   uint64_t n_tiles;
   int32_t n_ops;
@@ -343,7 +318,6 @@ struct alignas(16) dmb_lean_pass {
   // of a half-warp read 16 distinct 8-byte bank slots while a warp still writes whole 128-byte lines
   int32_t st_tbit[8];
   uint64_t st_pair_goff[DMB_LEAN_PAIRS];
-  dmb_lean_gop gfirst, glast;           // direct global I/O of ops[0] / ops[n_ops - 1] (enabled = 0: staged)
   dmb_lean_op ops[DMB_MAX_OPS];
 };
 enum { DMB_ST_PLAIN = 0, DMB_ST_PERM128 = 1, DMB_ST_SPLIT64 = 2 };
@@ -417,35 +391,7 @@ inline bool dmb_fold_swaps_enabled() {         // DMB_FOLD_SWAPS=0 keeps trailin
   return on;
 }
 
-inline int dmb_direct_io_mask() {           // DMB_DIRECT_IO=0..3: bit 0 first op reads, bit 1 last op writes the state directly (A/B switch)
-  static const int on = [] { const char* e = getenv("DMB_DIRECT_IO"); return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3; }();
-  return on;
-}
-
-// Tables of a direct-I/O op.  pos[k] = global digit position that tile digit k's content is read from / written to,
-// k0 = the tile digit whose content sits at global digit 0 there.  False when the op's register blocks hold no run of
-// 32 contiguous bytes (the new digit 0 is neither an op digit nor, for a paired op, the pair axis): stays staged.
-inline bool dmb_make_gop(const dmb_lean_op& q, int a, int b, const int* fd, const int* pos, int k0, dmb_lean_gop& G) {
-  const bool paired = q.mode == DMB_MODE_A;
-  if (paired && !(q.flags & DMB_PAIRABLE)) return false;
-  int axis;
-  if (k0 == a) axis = DMB_AX_I;
-  else if (k0 == b) axis = DMB_AX_J;
-  else if (paired && k0 == 0) axis = DMB_AX_PAIR;
-  else if (paired && fd[1] == k0) axis = DMB_AX_LANE;
-  else return false;
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 4; ++j)
-      G.gij[4 * i + j] = (((uint64_t)i << (2 * pos[a])) | ((uint64_t)j << (2 * pos[b]))) << 3;
-  for (int m = 0; m < 4; ++m) G.gsh[m] = (uint32_t)(2 * pos[fd[m]] + 3);
-  G.gpair = 8ull << (2 * pos[0]);
-  G.axis = axis;
-  G.enabled = 1;
-  return true;
-}
-
-// direct_io: bit 0 / bit 1 allow the first / last op of the pass to access the state vector directly (dmb_lean_gop)
-inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, bool fold_swaps = false, int direct_io = 0) {
+inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, bool fold_swaps = false) {
   L.n_tiles = 1ull << (n_bits - 2 * DMB_LEAN_K);
   L.n_ops = P.n_ops;
   L.pad_ = 0;
@@ -505,45 +451,6 @@ inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, 
     q.variant = dmb_variant_is_specialised(kx, ma, mb) ? dmb_variant_id(kx, ma, mb, q.mode) : -1;
     // thread digit 0 sits on tile digit 0: virtual threads 2u and 2u+1 own the two halves of every 16-byte pair
     if (q.mode == DMB_MODE_A && o.fd[0] == 0) q.flags |= DMB_PAIRABLE;
-  }
-  memset(&L.gfirst, 0, sizeof(L.gfirst));
-  memset(&L.glast, 0, sizeof(L.glast));
-  if (L.n_ops >= 1 && direct_io) {
-    int pos[DMB_LEAN_K], fd[4];
-    if (direct_io & 2) {                       // last op: positions after the folded swaps
-      const int k = L.n_ops - 1;
-      const dmb_op& o = P.ops[k];
-      dmb_lean_op& q = L.ops[k];
-      for (int j = 0; j < DMB_LEAN_K; ++j) pos[j] = P.tile_digit[dest[j]];
-      for (int m = 0; m < 4; ++m) fd[m] = o.fd[m];
-      if (q.flags & DMB_PAIRABLE) {
-        // any lane order with tile digit 0 first is conflict free in mode A (the swizzle spreads every digit over
-        // the chunk index): deal the next lane bits to the digit that lands on the second-lowest position, so that
-        // a warp's stores fill whole 128-byte lines
-        // (and first of all to the digit that lands on global digit 0, when that is a free digit of the op)
-        const int want[2] = {L.st_perm[0], L.st_perm[1]};
-        int w = 0;
-        fd[w++] = 0;
-        for (int c = 0; c < 2; ++c)
-          if (want[c] != 0 && want[c] != o.a && want[c] != o.b && (c == 0 || want[c] != want[0])) fd[w++] = want[c];
-        for (int m = 0; m < 4; ++m) {
-          bool used = false;
-          for (int x = 0; x < w; ++x) used = used || fd[x] == o.fd[m];
-          if (!used) fd[w++] = o.fd[m];
-        }
-      }
-      // a pass of ONE op would read and write the state in the same phase: fine in place, but a relabelling
-      // store writes other addresses than the thread has read (no barrier in between) -> keep that store staged
-      const bool hazard = L.n_ops == 1 && (direct_io & 1) && !identity;
-      if (!hazard && dmb_make_gop(q, o.a, o.b, fd, pos, L.st_perm[0], L.glast))
-        for (int m = 0; m < 4; ++m) q.sh[m] = (uint32_t)(2 * fd[m]);
-    }
-    if (direct_io & 1) {                       // first op: the digits are where the tile says
-      const dmb_op& o = P.ops[0];
-      for (int j = 0; j < DMB_LEAN_K; ++j) pos[j] = P.tile_digit[j];
-      for (int m = 0; m < 4; ++m) fd[m] = (int)(L.ops[0].sh[m] >> 1);
-      dmb_make_gop(L.ops[0], o.a, o.b, fd, pos, 0, L.gfirst);
-    }
   }
 }
 
@@ -882,198 +789,6 @@ DMB_HD bool dmb_lean_op_is_paired(const dmb_lean_op& op) {
   return (op.flags & DMB_PAIRABLE) && op.variant >= 0 && (op.variant % 3) == 0;
 }
 
-// ---------------------------------------------------------------------------------------
-// Direct-I/O op (see dmb_lean_gop): the first / last op of a pass, reading its blocks from the state vector (GL) or
-// from the stage, writing them to the stage or to the state vector (GS).  One real thread holds two 16-blocks, as in
-// the op bodies above: a paired op (mode A) the blocks of virtual threads 2u / 2u + 1 (halves of the same 16-byte
-// pairs), any other op those of virtual threads u / u + 128.  Runs twice per tile at most, so ONE copy of the code
-// serves every combination: the source / destination patterns are uniform run-time branches around one arithmetic
-// switch (same statements as the specialised bodies, so the result does not depend on the path taken).
-//   Ctx: ldg128 / ldg256 / stg64 / stg128 / stg256 (byte pointer) -- global accesses that bypass L1
-// ---------------------------------------------------------------------------------------
-#define DMB_IO_MATH_CASE(K, A, B) \
-  case (K * 3 + A) * 3 + B: dmb_spec_math<K, A, B>(op, v0); dmb_spec_math<K, A, B>(op, v1); break;
-
-DMB_HD void dmb_io_math(const dmb_lean_op& op, double (&v0)[4][4], double (&v1)[4][4]) {
-  switch (op.variant >= 0 ? op.variant / 3 : -1) {
-    DMB_IO_MATH_CASE(DMB_OP_MATS, 1, 1)
-    DMB_IO_MATH_CASE(DMB_OP_MATS, 2, 2)
-    DMB_IO_MATH_CASE(DMB_OP_CX, 1, 1)
-    DMB_IO_MATH_CASE(DMB_OP_CX, 2, 2)
-    DMB_IO_MATH_CASE(DMB_OP_CX, 0, 0)
-    DMB_IO_MATH_CASE(DMB_OP_CX_TSP, 1, 1)
-    DMB_IO_MATH_CASE(DMB_OP_CX_TSP, 2, 2)
-    DMB_IO_MATH_CASE(DMB_KIND_TSP0, 1, 1)
-    DMB_IO_MATH_CASE(DMB_KIND_TSP0, 2, 2)
-    DMB_IO_MATH_CASE(DMB_OP_SWAP, 0, 0)
-#ifndef DMB_EXP_NOGENERIC
-    default: dmb_lean_math(op, v0); dmb_lean_math(op, v1); break;
-#endif
-  }
-}
-
-DMB_HD uint64_t dmb_io_thread_off(const uint32_t* tq, const dmb_lean_gop& G) {
-  return ((uint64_t)tq[0] << G.gsh[0]) | ((uint64_t)tq[1] << G.gsh[1]) | ((uint64_t)tq[2] << G.gsh[2]) |
-         ((uint64_t)tq[3] << G.gsh[3]);
-}
-
-// thread digits of the two blocks of real thread u: a paired op holds the blocks of virtual threads 2u / 2u + 1 (one set
-// of digits; the blocks differ in the low bit of digit 0), any other op those of virtual threads u / u + 128
-DMB_HD void dmb_io_digits(int u, bool paired, uint32_t (&tq0)[4], uint32_t (&tq1)[4]) {
-  const uint32_t t = paired ? 2u * (uint32_t)u : (uint32_t)u;
-  tq0[0] = t & 3u; tq0[1] = (t >> 2) & 3u; tq0[2] = (t >> 4) & 3u; tq0[3] = (t >> 6) & 3u;
-  tq1[0] = tq0[0]; tq1[1] = tq0[1]; tq1[2] = tq0[2]; tq1[3] = paired ? tq0[3] : tq0[3] + 2u;
-}
-
-DMB_HD uint32_t dmb_io_stage_off(const uint32_t* tq, const dmb_lean_op& op) {
-  return dmb_swz((tq[0] << op.sh[0]) | (tq[1] << op.sh[1]) | (tq[2] << op.sh[2]) | (tq[3] << op.sh[3])) << 3;
-}
-
-template <bool FROM_STATE, bool TO_STATE, class Mem, class Ctx>
-DMB_HD void dmb_io_op(Ctx& cx, int u, const dmb_lean_op& op, const dmb_lean_gop* GL, const dmb_lean_gop* GS,
-                      unsigned char* tile0, const Mem& mem) {
-  const bool paired = op.mode == DMB_MODE_A;
-  double v0[4][4], v1[4][4];
-
-  // ---- source ----
-  if constexpr (FROM_STATE) {
-    uint32_t tq0[4], tq1[4];
-    dmb_io_digits(u, paired, tq0, tq1);
-    const unsigned char* g0 = tile0 + dmb_io_thread_off(tq0, *GL);
-    const unsigned char* g1 = paired ? g0 + GL->gpair : tile0 + dmb_io_thread_off(tq1, *GL);
-    if (GL->axis == DMB_AX_PAIR) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const dmb_d2 p = cx.ldg128(g0 + GL->gij[4 * i + j]);
-          v0[i][j] = p.x; v1[i][j] = p.y;
-        }
-    } else if (GL->axis == DMB_AX_I) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const dmb_d4 p = cx.ldg256(g0 + GL->gij[j]);
-        const dmb_d4 r = cx.ldg256(g1 + GL->gij[j]);
-        v0[0][j] = p.x; v0[1][j] = p.y; v0[2][j] = p.z; v0[3][j] = p.w;
-        v1[0][j] = r.x; v1[1][j] = r.y; v1[2][j] = r.z; v1[3][j] = r.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const dmb_d4 p = cx.ldg256(g0 + GL->gij[4 * i]);
-        const dmb_d4 r = cx.ldg256(g1 + GL->gij[4 * i]);
-        v0[i][0] = p.x; v0[i][1] = p.y; v0[i][2] = p.z; v0[i][3] = p.w;
-        v1[i][0] = r.x; v1[i][1] = r.y; v1[i][2] = r.z; v1[i][3] = r.w;
-      }
-    }
-  } else {
-    uint32_t tq0[4], tq1[4];
-    dmb_io_digits(u, paired, tq0, tq1);
-    const uint32_t sb0 = dmb_io_stage_off(tq0, op), sb1 = dmb_io_stage_off(tq1, op);
-    if (paired) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const dmb_d2 p = mem.ld128(sb0 ^ op.sa[i] ^ op.sj[j]);
-        v0[i][j] = p.x; v1[i][j] = p.y;
-      }
-  } else if (op.mode == DMB_MODE_PAIR_A) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const dmb_d2 p0 = mem.ld128(sb0 ^ op.sj[j]), p1 = mem.ld128(sb0 ^ op.sj[j] ^ 16u);
-      const dmb_d2 r0 = mem.ld128(sb1 ^ op.sj[j]), r1 = mem.ld128(sb1 ^ op.sj[j] ^ 16u);
-      v0[0][j] = p0.x; v0[1][j] = p0.y; v0[2][j] = p1.x; v0[3][j] = p1.y;
-      v1[0][j] = r0.x; v1[1][j] = r0.y; v1[2][j] = r1.x; v1[3][j] = r1.y;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const dmb_d2 p0 = mem.ld128(sb0 ^ op.sa[i]), p1 = mem.ld128(sb0 ^ op.sa[i] ^ 16u);
-      const dmb_d2 r0 = mem.ld128(sb1 ^ op.sa[i]), r1 = mem.ld128(sb1 ^ op.sa[i] ^ 16u);
-      v0[i][0] = p0.x; v0[i][1] = p0.y; v0[i][2] = p1.x; v0[i][3] = p1.y;
-      v1[i][0] = r0.x; v1[i][1] = r0.y; v1[i][2] = r1.x; v1[i][3] = r1.y;
-    }
-  }
-  }
-
-  dmb_io_math(op, v0, v1);
-
-  // ---- destination ---- (the thread digits are recomputed: nothing but the blocks stays live across the arithmetic)
-  uint32_t tq0[4], tq1[4];
-  dmb_io_digits(u, paired, tq0, tq1);
-  if constexpr (TO_STATE) {
-    unsigned char* g0 = tile0 + dmb_io_thread_off(tq0, *GS);
-    unsigned char* g1 = paired ? g0 + GS->gpair : tile0 + dmb_io_thread_off(tq1, *GS);
-    if (GS->axis == DMB_AX_PAIR) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          dmb_d2 p;
-          p.x = v0[i][j]; p.y = v1[i][j];
-          cx.stg128(g0 + GS->gij[4 * i + j], p);
-        }
-    } else if (GS->axis == DMB_AX_LANE) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          cx.stg64(g0 + GS->gij[4 * i + j], v0[i][j]);
-          cx.stg64(g1 + GS->gij[4 * i + j], v1[i][j]);
-        }
-    } else if (GS->axis == DMB_AX_I) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        dmb_d4 p, r;
-        p.x = v0[0][j]; p.y = v0[1][j]; p.z = v0[2][j]; p.w = v0[3][j];
-        r.x = v1[0][j]; r.y = v1[1][j]; r.z = v1[2][j]; r.w = v1[3][j];
-        cx.stg256(g0 + GS->gij[j], p);
-        cx.stg256(g1 + GS->gij[j], r);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        dmb_d4 p, r;
-        p.x = v0[i][0]; p.y = v0[i][1]; p.z = v0[i][2]; p.w = v0[i][3];
-        r.x = v1[i][0]; r.y = v1[i][1]; r.z = v1[i][2]; r.w = v1[i][3];
-        cx.stg256(g0 + GS->gij[4 * i], p);
-        cx.stg256(g1 + GS->gij[4 * i], r);
-      }
-    }
-    return;
-  }
-  const uint32_t sb0 = dmb_io_stage_off(tq0, op), sb1 = dmb_io_stage_off(tq1, op);
-  if (paired) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        dmb_d2 p;
-        p.x = v0[i][j]; p.y = v1[i][j];
-        mem.st128(sb0 ^ op.sa[i] ^ op.sj[j], p);
-      }
-  } else if (op.mode == DMB_MODE_PAIR_A) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      dmb_d2 p0, p1, r0, r1;
-      p0.x = v0[0][j]; p0.y = v0[1][j]; p1.x = v0[2][j]; p1.y = v0[3][j];
-      r0.x = v1[0][j]; r0.y = v1[1][j]; r1.x = v1[2][j]; r1.y = v1[3][j];
-      mem.st128(sb0 ^ op.sj[j], p0); mem.st128(sb0 ^ op.sj[j] ^ 16u, p1);
-      mem.st128(sb1 ^ op.sj[j], r0); mem.st128(sb1 ^ op.sj[j] ^ 16u, r1);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      dmb_d2 p0, p1, r0, r1;
-      p0.x = v0[i][0]; p0.y = v0[i][1]; p1.x = v0[i][2]; p1.y = v0[i][3];
-      r0.x = v1[i][0]; r0.y = v1[i][1]; r1.x = v1[i][2]; r1.y = v1[i][3];
-      mem.st128(sb0 ^ op.sa[i], p0); mem.st128(sb0 ^ op.sa[i] ^ 16u, p1);
-      mem.st128(sb1 ^ op.sa[i], r0); mem.st128(sb1 ^ op.sa[i] ^ 16u, r1);
-    }
-  }
-}
-
 // load / store of one tile (the CUDA kernel replaces the load by cp.async.cg of the same
 // addresses; the store is used as is)
 template <class Mem>
@@ -1128,9 +843,8 @@ DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass&
 // R.tab[idx >> R.shift] that holds it in the old layout; 2 "push": the write-back goes to the peer that owns idx.
 // ---------------------------------------------------------------------------------------
 #define DMB_HALF_THREADS 128
-template <int STMODE, bool PAIRED, int STAGES, int REMOTE, int DIO = 0, class Ctx>
+template <int STMODE, bool PAIRED, int STAGES, int REMOTE, class Ctx>
 DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L, const dmb_remote_src& R) {
-  static_assert(DIO == 0 || (PAIRED && STAGES == 1 && REMOTE == 0), "direct I/O: in-place single-stage passes only");
   dmb_lean_thread S0, S1;
   dmb_lean_thread_init(cx.tid(), L, S0);
   dmb_lean_thread_init(cx.tid() + DMB_HALF_THREADS, L, S1);
@@ -1151,54 +865,31 @@ DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L,
     }
     cx.commit();
   }
-  // direct global I/O of the first (DIO & 1) / last (DIO & 2) op, see dmb_lean_gop; the host launches the
-  // instantiation that matches L.gfirst.enabled / L.glast.enabled
-  constexpr bool first_direct = (DIO & 1) != 0, last_direct = (DIO & 2) != 0;
   uint32_t cur = 0;
   for (uint64_t tile = first; tile < L.n_tiles; tile += stride) {
-    if (!first_direct) {
-      const uint64_t fetch_tile = STAGES == 2 ? tile + stride : tile;
-      if (fetch_tile < L.n_tiles) {
-        const uint64_t tb = dmb_tile_base(fetch_tile, L.td, DMB_LEAN_K);
-        const uint32_t dst = (STAGES == 2 ? (cur ^ 1u) : 0u) * DMB_LEAN_TILE_BYTES;
+    const uint64_t fetch_tile = STAGES == 2 ? tile + stride : tile;
+    if (fetch_tile < L.n_tiles) {
+      const uint64_t tb = dmb_tile_base(fetch_tile, L.td, DMB_LEAN_K);
+      const uint32_t dst = (STAGES == 2 ? (cur ^ 1u) : 0u) * DMB_LEAN_TILE_BYTES;
 #pragma unroll
-        for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
-          cx.copy16(dst + (S0.soff ^ L.pair_soff[i]), src_of(tb + (S0.goff | L.pair_goff[i])));
-          cx.copy16(dst + (S1.soff ^ L.pair_soff[i]), src_of(tb + (S1.goff | L.pair_goff[i])));
-        }
+      for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
+        cx.copy16(dst + (S0.soff ^ L.pair_soff[i]), src_of(tb + (S0.goff | L.pair_goff[i])));
+        cx.copy16(dst + (S1.soff ^ L.pair_soff[i]), src_of(tb + (S1.goff | L.pair_goff[i])));
       }
-      cx.commit();
-      cx.template wait<STAGES - 1>();
-      cx.sync();
     }
+    cx.commit();
+    cx.template wait<STAGES - 1>();
+    cx.sync();
     const auto mem = cx.mem(cur * DMB_LEAN_TILE_BYTES);
-    const uint64_t tb = dmb_tile_base(tile, L.td, DMB_LEAN_K);
     for (int i = 0; i < L.n_ops; ++i) {
-      const bool from_state = first_direct && i == 0, to_state = last_direct && i == L.n_ops - 1;
-      bool done = false;
-      if constexpr (DIO != 0) {
-        unsigned char* tile0 = reinterpret_cast<unsigned char*>(state + tb);
-        if constexpr (DIO == 3) {
-          if (from_state && to_state) { dmb_io_op<true, true>(cx, cx.tid(), L.ops[i], &L.gfirst, &L.glast, tile0, mem); done = true; }
-        }
-        if constexpr ((DIO & 1) != 0) {
-          if (!done && from_state) { dmb_io_op<true, false>(cx, cx.tid(), L.ops[i], &L.gfirst, nullptr, tile0, mem); done = true; }
-        }
-        if constexpr ((DIO & 2) != 0) {
-          if (!done && to_state) { dmb_io_op<false, true>(cx, cx.tid(), L.ops[i], nullptr, &L.glast, tile0, mem); done = true; }
-        }
-      }
-      if (!done) {
-        if (PAIRED) dmb_lean_op_dispatch_pair(P0, S0, L.ops[i], mem);
-        else dmb_lean_op_dispatch_twice(S0, L.ops[i], mem);
-      }
+      if (PAIRED) dmb_lean_op_dispatch_pair(P0, S0, L.ops[i], mem);
+      else dmb_lean_op_dispatch_twice(S0, L.ops[i], mem);
       cx.sync();
     }
-    if (!last_direct) {
-      dmb_lean_store_thread<REMOTE == 2, STMODE>(S0, L, state, tb, R, mem);
-      dmb_lean_store_thread<REMOTE == 2, STMODE>(S1, L, state, tb, R, mem);
-      cx.sync();
-    }
+    const uint64_t tb = dmb_tile_base(tile, L.td, DMB_LEAN_K);
+    dmb_lean_store_thread<REMOTE == 2, STMODE>(S0, L, state, tb, R, mem);
+    dmb_lean_store_thread<REMOTE == 2, STMODE>(S1, L, state, tb, R, mem);
+    cx.sync();
     if (STAGES == 2) cur ^= 1u;
   }
 }

@@ -140,27 +140,6 @@ struct dmb_cuda_cta {
   __device__ __forceinline__ void copy16(uint32_t off, const double* src) const {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem0 + off), "l"(src) : "memory");
   }
-  // direct global I/O of a pass's first / last op (dmb_io_op): L2 only, like the cp.async staging
-  __device__ __forceinline__ dmb_d2 ldg128(const unsigned char* p) const {
-    dmb_d2 v;
-    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
-    return v;
-  }
-  __device__ __forceinline__ dmb_d4 ldg256(const unsigned char* p) const {
-    dmb_d4 v;
-    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];"
-                 : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory");
-    return v;
-  }
-  __device__ __forceinline__ void stg64(unsigned char* p, double v) const {
-    asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-  }
-  __device__ __forceinline__ void stg128(unsigned char* p, dmb_d2 v) const {
-    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
-  }
-  __device__ __forceinline__ void stg256(unsigned char* p, dmb_d4 v) const {
-    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
-  }
   __device__ __forceinline__ void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
   template <int N>
   __device__ __forceinline__ void wait() const { cp_async_wait<N>(); }
@@ -174,15 +153,14 @@ struct dmb_cuda_cta {
 
 // REMOTE: 0 in place, 1 pull (remote loads), 2 push (remote stores); STMODE: DMB_ST_PLAIN, or a relabelling
 // store that realises the pass's trailing digit swaps
-// DIO: bit 0 / bit 1 = the first / last op of the pass reads / writes the state vector directly (dmb_io_op)
-template <int CTAS, int REMOTE, int STMODE, int DIO = 0>
+template <int CTAS, int REMOTE, int STMODE>
 __global__ void __launch_bounds__(DMB_HALF_THREADS, CTAS)
 k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L,
              const __grid_constant__ dmb_remote_src S) {
   extern __shared__ __align__(128) unsigned char lean_smem[];
   dmb_cuda_cta cx;
   cx.smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
-  dmb_half_kernel_body<STMODE, true, 1, REMOTE, DIO>(cx, state, L, S);
+  dmb_half_kernel_body<STMODE, true, 1, REMOTE>(cx, state, L, S);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -368,61 +346,33 @@ static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_p
 }
 
 #define DMB_TILE_CTAS 5      // CTAs per SM of k_tile_pass6 (measured on config 3: 4 -> 232.0 ms, 5 -> 223.0 ms, 6 -> 226.7 ms)
-template <int CTAS, int REMOTE, int STMODE, int DIO = 0>
+template <int CTAS, int REMOTE, int STMODE>
 static int launch_tile6(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, const dmb_remote_src& S = g_no_remote) {
   const size_t smem = DMB_LEAN_TILE_BYTES;
   static std::atomic<uint64_t> attr_done[2];          // one bit per device: the attribute is per device
   const int dev = ctx->device & 127;
   if (!((attr_done[dev >> 6].load() >> (dev & 63)) & 1ull)) {
-    CU_TRY(cudaFuncSetAttribute(k_tile_pass6<CTAS, REMOTE, STMODE, DIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_tile_pass6<CTAS, REMOTE, STMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[dev >> 6].fetch_or(1ull << (dev & 63));
   }
   uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
   if (grid > L.n_tiles) grid = L.n_tiles;
-  k_tile_pass6<CTAS, REMOTE, STMODE, DIO><<<(unsigned)grid, DMB_HALF_THREADS, smem, ctx->stream>>>(state, L, S);
+  k_tile_pass6<CTAS, REMOTE, STMODE><<<(unsigned)grid, DMB_HALF_THREADS, smem, ctx->stream>>>(state, L, S);
   CU_TRY(cudaGetLastError());
   return 0;
 }
 
-template <int CTAS, int DIO>
-static int launch_tile6_store(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
-  if constexpr ((DIO & 2) != 0) {
-    return launch_tile6<CTAS, 0, DMB_ST_PLAIN, DIO>(ctx, state, L);   // no staged write-back
-  } else {
-    if (L.st_mode == DMB_ST_PERM128) return launch_tile6<CTAS, 0, DMB_ST_PERM128, DIO>(ctx, state, L);
-    if (L.st_mode == DMB_ST_SPLIT64) return launch_tile6<CTAS, 0, DMB_ST_SPLIT64, DIO>(ctx, state, L);
-    return launch_tile6<CTAS, 0, DMB_ST_PLAIN, DIO>(ctx, state, L);
-  }
-}
-
-static int dio_ctas() {          // experiment switch: CTAs per SM of the direct-I/O instantiations (DMB_DIO_CTAS=4|5)
-  static const int v = [] { const char* e = getenv("DMB_DIO_CTAS"); return (e && e[0] == '4') ? 4 : 5; }();
-  return v;
-}
-
 template <int CTAS>
 static int launch_tile6_any(dmb_ctx* ctx, double* state, const dmb_lean_pass& L) {
-  const int dio = (L.gfirst.enabled ? 1 : 0) | (L.glast.enabled ? 2 : 0);
-  if (dio && dio_ctas() == 4) {
-    switch (dio) {
-      case 1: return launch_tile6_store<4, 1>(ctx, state, L);
-      case 2: return launch_tile6_store<4, 2>(ctx, state, L);
-      default: return launch_tile6_store<4, 3>(ctx, state, L);
-    }
-  }
-  switch (dio) {
-    case 1: return launch_tile6_store<CTAS, 1>(ctx, state, L);
-    case 2: return launch_tile6_store<CTAS, 2>(ctx, state, L);
-    case 3: return launch_tile6_store<CTAS, 3>(ctx, state, L);
-    default: return launch_tile6_store<CTAS, 0>(ctx, state, L);
-  }
+  if (L.st_mode == DMB_ST_PERM128) return launch_tile6<CTAS, 0, DMB_ST_PERM128>(ctx, state, L);
+  if (L.st_mode == DMB_ST_SPLIT64) return launch_tile6<CTAS, 0, DMB_ST_SPLIT64>(ctx, state, L);
+  return launch_tile6<CTAS, 0, DMB_ST_PLAIN>(ctx, state, L);
 }
 
 static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass& P) {
   static thread_local dmb_lean_pass L;    // 6.5 KB: keep it off the stack; one host thread drives a ctx
-  dmb_make_lean_pass(P, n_bits, L, dmb_fold_swaps_enabled(), dmb_direct_io_mask());
+  dmb_make_lean_pass(P, n_bits, L, dmb_fold_swaps_enabled());
   ctx->stats.folded_swaps += (uint64_t)(P.n_ops - L.n_ops);
-  ctx->stats.direct_io_ops += (uint64_t)(L.gfirst.enabled + L.glast.enabled);
   return launch_tile6_any<DMB_TILE_CTAS>(ctx, state, L);
 }
 

@@ -83,24 +83,11 @@ static int g_variant = 0;
 static thread_local long g_folded_swaps = 0;
 static long g_paired_ops = 0;     // thread-ops that went through dmb_lean_op_pair (test hook)
 extern "C" long dmb_emu_paired_ops(void) { return g_paired_ops; }
-struct emu_global_io {            // the global accesses of dmb_io_op on plain memory
-  dmb_d2 ldg128(const unsigned char* p) const { dmb_d2 v; memcpy(&v, p, 16); return v; }
-  dmb_d4 ldg256(const unsigned char* p) const { dmb_d4 v; memcpy(&v, p, 32); return v; }
-  void stg64(unsigned char* p, double v) const { memcpy(p, &v, 8); }
-  void stg128(unsigned char* p, dmb_d2 v) const { memcpy(p, &v, 16); }
-  void stg256(unsigned char* p, dmb_d4 v) const { memcpy(p, &v, 32); }
-};
-static thread_local long g_direct_io_ops = 0;
-extern "C" long dmb_emu_direct_io_ops(void) { return g_direct_io_ops; }
-
 static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const dmb_remote_src& S = g_no_remote,
                            const dmb_remote_src& D = g_no_remote) {
   static thread_local dmb_lean_pass L;
-  const bool in_place = !S.enabled && !D.enabled;
-  dmb_make_lean_pass(P, n_bits, L, dmb_fold_swaps_enabled() && in_place, in_place ? dmb_direct_io_mask() : 0);
+  dmb_make_lean_pass(P, n_bits, L, dmb_fold_swaps_enabled() && !S.enabled && !D.enabled);
   g_folded_swaps += P.n_ops - L.n_ops;
-  g_direct_io_ops += L.gfirst.enabled + L.glast.enabled;
-  emu_global_io gio;
   alignas(128) static thread_local unsigned char stage[DMB_LEAN_TILE_BYTES];
   static thread_local dmb_lean_thread T[DMB_TILE_THREADS];
   for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_thread_init(t, L, T[t]);
@@ -108,21 +95,12 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const d
   mem.base = stage;
   for (uint64_t tile = 0; tile < L.n_tiles; ++tile) {
     const uint64_t tbase = dmb_tile_base(tile, L.td, DMB_LEAN_K);
-    if (!L.gfirst.enabled)
-      for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, state, tbase, S, mem);
-    for (int i = 0; i < L.n_ops; ++i) {
-      const dmb_lean_gop* from_state = (i == 0 && L.gfirst.enabled) ? &L.gfirst : nullptr;
-      const dmb_lean_gop* to_state = (i == L.n_ops - 1 && L.glast.enabled) ? &L.glast : nullptr;
+    for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, state, tbase, S, mem);
+    for (int i = 0; i < L.n_ops; ++i)
       for (int u = 0; u < DMB_TILE_THREADS / 2; ++u) {   // real thread u plays virtual threads 2u, 2u + 1 or u, u + 128
-        unsigned char* tile0 = reinterpret_cast<unsigned char*>(state + tbase);
-        if (from_state && to_state) { dmb_io_op<true, true>(gio, u, L.ops[i], from_state, to_state, tile0, mem); continue; }
-        if (from_state) { dmb_io_op<true, false>(gio, u, L.ops[i], from_state, to_state, tile0, mem); continue; }
-        if (to_state) { dmb_io_op<false, true>(gio, u, L.ops[i], from_state, to_state, tile0, mem); continue; }
         if (dmb_lean_op_is_paired(L.ops[i])) ++g_paired_ops;
         dmb_lean_op_dispatch_pair(T[2 * u], T[u], L.ops[i], mem);
       }
-    }
-    if (L.glast.enabled) continue;
     for (int t = 0; t < DMB_TILE_THREADS; ++t) {
       if (D.enabled) dmb_lean_store_thread<true, DMB_ST_PLAIN>(T[t], L, state, tbase, D, mem);
       else if (L.st_mode == DMB_ST_PERM128) dmb_lean_store_thread<false, DMB_ST_PERM128>(T[t], L, state, tbase, D, mem);
@@ -171,11 +149,6 @@ struct emu_cta_thread {
     }
   }
   void sync() { bar->wait(); }
-  dmb_d2 ldg128(const unsigned char* p) const { dmb_d2 v; memcpy(&v, p, 16); return v; }
-  dmb_d4 ldg256(const unsigned char* p) const { dmb_d4 v; memcpy(&v, p, 32); return v; }
-  void stg64(unsigned char* p, double v) const { memcpy(p, &v, 8); }
-  void stg128(unsigned char* p, dmb_d2 v) const { memcpy(p, &v, 16); }
-  void stg256(unsigned char* p, dmb_d4 v) const { memcpy(p, &v, 32); }
   dmb_host_mem mem(uint32_t off) const {
     dmb_host_mem m;
     m.base = stages + off;
@@ -183,7 +156,7 @@ struct emu_cta_thread {
   }
 };
 
-template <int STMODE, bool PAIRED, int STAGES, int REMOTE = 0, int DIO = 0>
+template <int STMODE, bool PAIRED, int STAGES, int REMOTE = 0>
 static void run_half_kernel_cta(double* state, const dmb_lean_pass& L, uint64_t block, uint64_t grid,
                                 const dmb_remote_src& R = g_no_remote) {
   std::vector<unsigned char> stages((size_t)STAGES * DMB_LEAN_TILE_BYTES + 128);
@@ -194,31 +167,18 @@ static void run_half_kernel_cta(double* state, const dmb_lean_pass& L, uint64_t 
     threads.emplace_back([&, t] {
       emu_cta_thread cx;
       cx.tid_ = t; cx.block_ = block; cx.grid_ = grid; cx.stages = base; cx.bar = &bar;
-      dmb_half_kernel_body<STMODE, PAIRED, STAGES, REMOTE, DIO>(cx, state, L, R);
+      dmb_half_kernel_body<STMODE, PAIRED, STAGES, REMOTE>(cx, state, L, R);
     });
   for (auto& th : threads) th.join();
 }
 
-template <bool PAIRED, int STAGES, int DIO>
-static void run_half_kernel_dio(double* state, const dmb_lean_pass& L, uint64_t grid) {
-  for (uint64_t block = 0; block < grid; ++block) {
-    if (L.st_mode == DMB_ST_PERM128) run_half_kernel_cta<DMB_ST_PERM128, PAIRED, STAGES, 0, DIO>(state, L, block, grid);
-    else if (L.st_mode == DMB_ST_SPLIT64) run_half_kernel_cta<DMB_ST_SPLIT64, PAIRED, STAGES, 0, DIO>(state, L, block, grid);
-    else run_half_kernel_cta<DMB_ST_PLAIN, PAIRED, STAGES, 0, DIO>(state, L, block, grid);
-  }
-}
-
 template <bool PAIRED, int STAGES>
 static void run_half_kernel(double* state, const dmb_lean_pass& L, uint64_t grid) {
-  if constexpr (PAIRED && STAGES == 1) {        // the shipped configuration: direct I/O as the library launches it
-    switch ((L.gfirst.enabled ? 1 : 0) | (L.glast.enabled ? 2 : 0)) {
-      case 1: return run_half_kernel_dio<PAIRED, STAGES, 1>(state, L, grid);
-      case 2: return run_half_kernel_dio<PAIRED, STAGES, 2>(state, L, grid);
-      case 3: return run_half_kernel_dio<PAIRED, STAGES, 3>(state, L, grid);
-      default: break;
-    }
+  for (uint64_t block = 0; block < grid; ++block) {
+    if (L.st_mode == DMB_ST_PERM128) run_half_kernel_cta<DMB_ST_PERM128, PAIRED, STAGES>(state, L, block, grid);
+    else if (L.st_mode == DMB_ST_SPLIT64) run_half_kernel_cta<DMB_ST_SPLIT64, PAIRED, STAGES>(state, L, block, grid);
+    else run_half_kernel_cta<DMB_ST_PLAIN, PAIRED, STAGES>(state, L, block, grid);
   }
-  run_half_kernel_dio<PAIRED, STAGES, 0>(state, L, grid);
 }
 
 // test hook: run `n_passes` K = 6 passes through the threaded kernel body (paired: 0/1, stages: 1/2, grid CTAs)
@@ -227,26 +187,13 @@ extern "C" int dmb_emu_run_half_kernel(double* state, int n_bits, const dmb_pass
   static thread_local dmb_lean_pass L;
   for (size_t i = 0; i < n_passes; ++i) {
     if (passes[i].n_tile_digits != DMB_LEAN_K) return 1;
-    dmb_make_lean_pass(passes[i], n_bits, L, dmb_fold_swaps_enabled(), (paired && stages == 1) ? dmb_direct_io_mask() : 0);
+    dmb_make_lean_pass(passes[i], n_bits, L, dmb_fold_swaps_enabled());
     uint64_t g = (uint64_t)grid < L.n_tiles ? (uint64_t)grid : L.n_tiles;
     if (paired && stages == 2) run_half_kernel<true, 2>(state, L, g);
     else if (paired) run_half_kernel<true, 1>(state, L, g);
     else if (stages == 2) run_half_kernel<false, 2>(state, L, g);
     else run_half_kernel<false, 1>(state, L, g);
   }
-  return 0;
-}
-
-// test hook: how the library would run a K = 6 pass (op counts, store mode, direct I/O of the first / last op)
-extern "C" int dmb_emu_classify_pass(const dmb_pass* pass, int n_bits, int32_t* out10) {
-  static thread_local dmb_lean_pass L;
-  if (pass->n_tile_digits != DMB_LEAN_K) return 1;
-  dmb_make_lean_pass(*pass, n_bits, L, dmb_fold_swaps_enabled(), dmb_direct_io_mask());
-  out10[0] = L.n_ops; out10[1] = L.st_mode;
-  out10[2] = L.gfirst.enabled; out10[3] = L.gfirst.axis;
-  out10[4] = L.glast.enabled; out10[5] = L.glast.axis;
-  out10[6] = L.n_ops ? L.ops[0].mode : -1; out10[7] = L.n_ops ? L.ops[L.n_ops - 1].mode : -1;
-  out10[8] = L.n_ops ? L.ops[0].variant : -1; out10[9] = L.n_ops ? L.ops[L.n_ops - 1].variant : -1;
   return 0;
 }
 
@@ -335,9 +282,8 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
       case 5: run_tile_pass<5>(state, n_bits, P); break;
       case 6:
         if (g_variant == 1) run_tile_pass<6>(state, n_bits, P);
-        else { const long before = g_folded_swaps, io_before = g_direct_io_ops; run_tile_pass6(state, n_bits, P);
-               ctx->stats.folded_swaps += (uint64_t)(g_folded_swaps - before);
-               ctx->stats.direct_io_ops += (uint64_t)(g_direct_io_ops - io_before); }
+        else { const long before = g_folded_swaps; run_tile_pass6(state, n_bits, P);
+               ctx->stats.folded_swaps += (uint64_t)(g_folded_swaps - before); }
         break;
       default: return fail("dmb_apply_passes", "unsupported tile size");
     }
