@@ -265,25 +265,25 @@ class PauliEngine:
         self.tape_valid = False
 
     def replay(self, tape):
-        """Run a recorded tape on this engine's buffers: the C-ABI calls of the recording run, nothing else.  Work
-        buffers and pinned landing buffers are allocated on the first replay and reused; the readouts are queued
-        without waiting and the stream is synchronised once.  Returns fresh host arrays in recording order."""
+        """Run a recorded tape on this engine's buffers: the C-ABI calls of the recording run, nothing else.  Device
+        work buffers are allocated on the first replay and reused; every readout lands in a fresh pinned host array
+        (PyTorch's caching host allocator recycles the blocks of results that have been dropped, so this is not a
+        cudaHostAlloc per run and the caller owns what it gets); the copies are queued without waiting and the stream
+        is synchronised once.  Returns the host arrays in recording order."""
         ctx = self.ctx
         ctx.set_stream(self.alloc.stream())
         bufs = getattr(self, "_replay_bufs", None)
         if bufs is None or bufs[0] is not tape:
             n, made = self.n, []
-            pin = getattr(self.alloc, "pinned", None) or (lambda count: (None, np.empty(int(count))))
             for entry in tape:
                 if entry[0] == "marginal":
-                    made.append((self.alloc.empty(2 ** entry[4]), None) + pin(2 ** entry[4]))
+                    made.append((self.alloc.empty(2 ** entry[4]), None))
                 elif entry[0] == "to_matrix":
-                    made.append((self.alloc.empty(2 * 4 ** n), self.alloc.empty(2 * 4 ** n)) + pin(2 * 4 ** n))
-                elif entry[0] == "download":
-                    made.append((None, None) + pin(4 ** n))
+                    made.append((self.alloc.empty(2 * 4 ** n), self.alloc.empty(2 * 4 ** n)))
                 else:
                     made.append(None)
             bufs = self._replay_bufs = (tape, made)
+        pin = getattr(self.alloc, "pinned", None) or (lambda count: (None, np.empty(int(count))))
         landed = []
         for entry, b in zip(tape, bufs[1]):
             kind = entry[0]
@@ -294,21 +294,24 @@ class PauliEngine:
             elif kind == "marginal":
                 ctx.marginal(self.sptr, self.n_bits, 0, entry[1], entry[2], entry[3], self.alloc.ptr(b[0]))
                 ctx.fwht(self.alloc.ptr(b[0]), entry[4])
-                ctx.download_async(self.alloc.ptr(b[0]), b[3])
-                landed.append((b[3], None))
+                host = pin(2 ** entry[4])[1]
+                ctx.download_async(self.alloc.ptr(b[0]), host)
+                landed.append(host)
             elif kind == "chop":
                 ctx.chop(self.sptr, self.size, entry[1])
             elif kind == "to_matrix":
                 ctx.to_matrix(self.sptr, self.n, self.alloc.ptr(b[1]), self.alloc.ptr(b[0]))
-                ctx.download_async(self.alloc.ptr(b[0]), b[3])
-                landed.append((b[3], 2 ** self.n))
+                host = pin(2 * 4 ** self.n)[1]
+                ctx.download_async(self.alloc.ptr(b[0]), host)
+                landed.append(host.view(np.complex128).reshape(2 ** self.n, 2 ** self.n))
             elif kind == "download":
-                ctx.download_async(self.sptr, b[3])
-                landed.append((b[3], None))
+                host = pin(4 ** self.n)[1]
+                ctx.download_async(self.sptr, host)
+                landed.append(host)
             else:
                 raise BasicAerError("internal: unknown tape entry %r" % (kind,))
         ctx.sync()
-        return [host.copy() if dim is None else host.copy().view(np.complex128).reshape(dim, dim) for host, dim in landed]
+        return landed
 
     def upload(self, vec):
         self._not_replayable()
