@@ -228,6 +228,61 @@ def test_n14_noisy_invariants_and_schedule_independence(backend):
     assert np.max(np.abs(v1 - v2)) <= 1e-12 and np.max(np.abs(p1 - p2)) <= 1e-12
 
 
+def test_n16_round_trip_at_the_single_gpu_limit():
+    """The largest register one B200 advertises (n = 16: 2^32 coefficients, 34 GB -- byte offsets beyond 32 bits in every
+    kernel): GHZ known answer and U . U^-1 = 1 through the public backend, probabilities only (``SHOW_FINAL_STATE =
+    False``, a reference flag, ``dm_simulator.py:134``: the 34 GB vector stays on the device), plus single coefficients
+    read through ``dmb_read_coeffs``."""
+    import torch
+    from qiskit_aakash_b200 import DmSimulatorB200, assemble, circuits as C, engine
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs 34 GB of free device memory")
+    n = 16
+    engines = []
+
+    def factory(nq):
+        engines.append(engine.PauliEngine(nq))
+        return engines[-1]
+
+    be = DmSimulatorB200(_engine_factory=factory)
+    be.SHOW_FINAL_STATE = False
+    ghz = C.ghz(n)
+    ghz.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="Z")
+    res = be.run(assemble(ghz), backend_options={"compute_densitymatrix": False}).result()["results"][0]
+    p = res["data"]["ensemble_probability"]
+    assert abs(p["0" * n] - 0.5) <= TOL and abs(p["1" * n] - 0.5) <= TOL and abs(sum(p.values()) - 1) <= TOL
+    e = engines[-1]
+    e.flush()
+    pos = e.pos                                             # digit position of qubit q in the current layout
+
+    def index(digits):                                      # Pauli string (digit of qubit q) -> vector index
+        return sum(int(d) << (2 * pos[q]) for q, d in enumerate(digits))
+
+    got = e.ctx.read_coeffs(e.sptr, [index([0] * n), index([3] * n), index([1] * n), index([3, 3] + [0] * (n - 2)),
+                                     index([1] + [0] * (n - 1))])
+    # GHZ: <I..I> = <Z..Z (even n)> = <X..X> = <Z Z I..I> = 1, <X I..I> = 0; coefficients carry 2^-n
+    assert np.max(np.abs(got * 2 ** n - np.array([1, 1, 1, 1, 0]))) <= 1e-12
+    del e
+    engines.clear()
+
+    fwd = C.random_layered(n, 3, 1600, readout=False)
+    c = C.Circuit(n)
+    c.instructions = list(fwd.instructions)
+    for ins in reversed(fwd.instructions):
+        if ins.name == "cx":
+            c.cx(ins.qubits[0], ins.qubits[1])
+        else:
+            th, ph, lam = ins.params
+            c.barrier()
+            c.u3(-th, -lam, -ph, ins.qubits[0])
+    c.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="Z")
+    res = be.run(assemble(c), backend_options={"compute_densitymatrix": False}).result()["results"][0]
+    p = res["data"]["ensemble_probability"]
+    assert abs(p["0" * n] - 1.0) <= 1e-9 and abs(sum(p.values()) - 1) <= 1e-9
+    assert "coeffmatrix" not in res["data"]
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
