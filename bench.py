@@ -535,6 +535,7 @@ def time_e2e(args, world, device, circ_fn, opts, n, n_gates, state_bytes):
         breakdown = {k: round(1e3 * v, 2) for k, v in backend.last_engine_stats.items() if k.startswith("t_")}
         del res
         backend._engine = None
+    backend.release_engines()            # the sharded backend keeps shards + peer mappings for the next job
     dt = sum(times) / len(times)
     if world > 1:
         t = torch.tensor([dt], device="cuda", dtype=torch.float64)

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import functools
 import gc
+import os
 import logging
 import time
 import uuid
@@ -188,9 +189,22 @@ class DmSimulatorB200:
         if _engine_factory is not None:
             self._engine_factory = _engine_factory
         elif self._comm is not None:
+            self._sharded_pool = None
+
             def sharded(n):
+                # consecutive jobs on the same register size reuse the engine: its two shards and the peers' IPC
+                # mappings of them (60 ms to set up at 8 ranks) -- every rank runs the same jobs in the same order,
+                # so all ranks take the same branch.  A different size releases the old shards first.
                 from .distributed import ShardedPauliEngine
-                return ShardedPauliEngine(n, self._comm, device=self._device)
+                pool = self._sharded_pool
+                if pool is not None and pool.n == n and os.environ.get("DMB_ENGINE_POOL", "1") != "0":
+                    return pool.recycle()
+                if pool is not None:
+                    self._sharded_pool = None
+                    pool.close()
+                    del pool
+                self._sharded_pool = ShardedPauliEngine(n, self._comm, device=self._device)
+                return self._sharded_pool
             self._engine_factory = sharded
         else:
             self._engine_factory = lambda n: eng.PauliEngine(n, device=self._device)
@@ -548,6 +562,15 @@ class DmSimulatorB200:
                 "success": True,
                 "time_taken": end - start,
                 "header": _as_dict(getattr(qobj, "header", None))}
+
+    def release_engines(self):
+        """Drop the device state kept for the next job: the last engine and, on a sharded backend, the pooled shards
+        with the peers' mappings of them.  Collective in effect on a sharded backend (call it on every rank)."""
+        self._engine = None
+        pool = getattr(self, "_sharded_pool", None)
+        if pool is not None:
+            self._sharded_pool = None
+            pool.close()
 
     def run_experiment(self, experiment):
         """``run_experiment`` (``:950-1196``)."""

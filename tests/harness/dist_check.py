@@ -111,7 +111,33 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     assert float(t.item()) <= 1e-10, float(t.item())
     for b in backends:
-        b._engine = None
+        b.release_engines()
+    dist.barrier()
+    # consecutive jobs on ONE public backend: the sharded engine is pooled (same register size -> recycle(): shards and
+    # peer mappings kept; another size -> closed and rebuilt)
+    be = DmSimulatorB200(comm=comm, device=local)
+    d_pool, reused = 0.0, []
+    for job, (nq, seed) in enumerate(((9, 81), (9, 82), (9, 83), (8, 84), (9, 85))):
+        circ = cases._rand_circuit(nq, 60, seed)
+        circ.measure(list(range(nq)), list(range(nq)), basis="Ensemble", add_param="XYZ"[seed % 3])
+        c2 = C.Circuit(nq)
+        c2.instructions = copy.deepcopy(circ.instructions)
+        before = be._sharded_pool
+        res = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
+        reused.append(be._sharded_pool is before)
+        ref = dm_oracle.run_oracle(nq, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
+        p_got = np.array(list(res["data"]["ensemble_probability"].values()))
+        p_ref = np.array(list(ref["data"]["ensemble_probability"].values()))
+        d_pool = max(d_pool, float(np.max(np.abs(p_got - p_ref))),
+                     float(np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"]))))
+    assert reused == [False, True, True, False, False], reused
+    worst = max(worst, d_pool)
+    if rank == 0:
+        print(json.dumps({"check": "pooled_engine_jobs", "world": world, "jobs": len(reused), "reused": reused, "d": d_pool}))
+    t = torch.tensor([d_pool], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert float(t.item()) <= 1e-10, float(t.item())
+    be.release_engines()
     dist.barrier()
     # random programs (tests/harness/fuzz_emu.py's generator: every measurement mode mid-circuit, resets, random
     # options) -- includes the pattern that exposed the scratch-shard race after a fused pull (a readout

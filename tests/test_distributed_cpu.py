@@ -110,14 +110,23 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
     engines = []
 
     def factory(nq):
+        if mode == "recycle" and engines:                  # what the product's sharded factory does between jobs
+            return engines[0].recycle()
         e = distributed.ShardedPauliEngine(nq, comm, lib=emu_lib(), allocator=CpuAlloc(), max_ops_per_pass=4)
         engines.append(e)
         return e
 
     be = DmSimulatorB200(_engine_factory=factory, comm=comm)
+    if mode == "recycle":                                  # an earlier job leaves its layout, counters and buffers behind
+        c0 = cases._rand_circuit(n, 30, seed + 50)
+        c0.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="Y")
+        be.run(assemble(c0), backend_options=copy.deepcopy(opts)).result()
+        first_exchanges = engines[0].exchanges
     c2 = C.Circuit(n)
     c2.instructions = copy.deepcopy(circ.instructions)
     res = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
+    if mode == "recycle":
+        assert len(engines) == 1 and first_exchanges >= 0
     ref = dm_oracle.run_oracle(n, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
     d_red = 0.0
     if mode == "reduced":
@@ -151,7 +160,8 @@ def _worker(rank, world, port, n, seed, mode, out_dir):
                                                (2, 5, 7, "expect"), (4, 6, 8, "bell"), (8, 7, 9, "expect"),
                                                (2, 5, 10, "stored"), (8, 7, 11, "stored"),
                                                (4, 6, 15, "matrix"), (2, 5, 16, "reduced"), (8, 7, 17, "reduced"),
-                                               (2, 5, 12, "nbasis"), (4, 6, 13, "nbasis"), (8, 7, 14, "nbasis")])
+                                               (2, 5, 12, "nbasis"), (4, 6, 13, "nbasis"), (8, 7, 14, "nbasis"),
+                                               (4, 6, 18, "recycle"), (8, 7, 19, "recycle")])
 def test_sharded_backend_matches_oracle(world, n, seed, mode, tmp_path):
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(HERE, "emu"))

@@ -63,7 +63,9 @@ class ThreadComm:
         return [[everyone[r][b] for r in range(self.world)] for b in range(len(ptrs))]
 
 
-def _run_world(world, n, circ, opts, fused, mode="pull"):
+def _run_world(world, n, circ, opts, fused, mode="pull", first_job=None):
+    """``first_job``: a circuit that runs BEFORE ``circ`` on the same engines, which are then recycled for ``circ``
+    (``ShardedPauliEngine.recycle``: what the product's sharded factory does between jobs of one register size)."""
     cluster = ThreadCluster(world)
     out, errs = [None] * world, []
 
@@ -73,12 +75,18 @@ def _run_world(world, n, circ, opts, fused, mode="pull"):
             engines = []
 
             def factory(nq):
+                if first_job is not None and engines:
+                    return engines[0].recycle()
                 e = distributed.ShardedPauliEngine(nq, comm, lib=emu_lib(), allocator=NumpyAllocator(), max_ops_per_pass=4)
                 e.exchange_mode = mode
                 engines.append(e)
                 return e
 
             be = DmSimulatorB200(_engine_factory=factory)
+            if first_job is not None:
+                c0 = C.Circuit(n)
+                c0.instructions = copy.deepcopy(first_job.instructions)
+                be.run(assemble(c0), backend_options=copy.deepcopy(opts)).result()
             c2 = C.Circuit(n)
             c2.instructions = copy.deepcopy(circ.instructions)
             res = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
@@ -111,6 +119,27 @@ def test_fused_exchange_matches_oracle(world, n, seed, mode):
         for rank, (res, exchanges, has_peers) in enumerate(outs):
             assert has_peers == fused
             assert exchanges >= 1
+            p = np.array(list(res["data"]["ensemble_probability"].values()))
+            assert np.max(np.abs(p - p_ref)) <= 1e-10
+            assert np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])) <= 1e-10
+
+
+@pytest.mark.parametrize("world,n,seed", [(2, 6, 21), (4, 7, 22), (8, 8, 23)])
+def test_recycled_engine_runs_the_next_job_correctly(world, n, seed):
+    """Two jobs on one set of engines (shards and peer tables kept, ``recycle()`` in between): the second job starts
+    from whichever of the two buffers the first one ended in, possibly while a slower peer still pulls from the other
+    one, and must still match the oracle in every exchange mode."""
+    first = cases._rand_circuit(n, 40, seed + 100)
+    first.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="Y")
+    circ = cases._rand_circuit(n, 50, seed)
+    circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="XYZ"[seed % 3])
+    opts = dict(cases.FULL_NOISE, compute_densitymatrix=False)
+    ref = dm_oracle.run_oracle(n, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
+    p_ref = np.array(list(ref["data"]["ensemble_probability"].values()))
+    for fused, xmode in ((True, "pull"), (True, "push"), (False, "nccl")):
+        outs = _run_world(world, n, circ, opts, fused, xmode, first_job=first)
+        for rank, (res, exchanges, has_peers) in enumerate(outs):
+            assert has_peers == fused
             p = np.array(list(res["data"]["ensemble_probability"].values()))
             assert np.max(np.abs(p - p_ref)) <= 1e-10
             assert np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])) <= 1e-10
