@@ -420,7 +420,8 @@ def run_ours(args):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": pass_ms, "algorithmic_bytes_per_launch": per_launch_bytes,
                 "fused_ops_per_launch": counters["fused_ops"] / launches,
-                "swaps_folded_into_store_per_launch": counters.get("folded_swaps", 0) / launches}
+                "swaps_folded_into_store_per_launch": counters.get("folded_swaps", 0) / launches,
+                "ops_chained_to_their_predecessor_per_launch": counters.get("chained_ops", 0) / launches}
     if world == 1 and n <= 14:
         roofline.update(unfused_launch_points(runner.engine, n, peak))
         roofline["note"] = ("launches that fuse more than ~3 ops are shared-memory-bandwidth bound (one 64 KiB round "
@@ -430,7 +431,7 @@ def run_ours(args):
     # memory reads and writes the whole tile (2 x 8 B per coefficient), staging adds one write (cp.async) and one
     # read (write-back); peak = 128 B/clk/SM x SMs x the SM clock sampled during the run.
     try:
-        smem_ops = (counters["fused_ops"] - counters.get("folded_swaps", 0)) / launches
+        smem_ops = (counters["fused_ops"] - counters.get("folded_swaps", 0) - counters.get("chained_ops", 0)) / launches
         smem_bytes = (smem_ops + 1.0) * 16.0 * 4 ** n / world
         sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
         mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")

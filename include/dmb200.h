@@ -29,7 +29,7 @@ extern "C" {
 
 #define DMB_ABI_VERSION 5   /* 2: dmb_stats.folded_swaps; 3: dmb_schedule; 4: dmb_op.post_swap and
                                dmb_stats.r3_phases removed (measured slower, round 2), dmb_ipc_close;
-                               5: dmb_download_async */
+                               5: dmb_download_async, dmb_stats.chained_ops */
 #define DMB_MAX_TILE_DIGITS 6   /* a tile holds 4^6 = 4096 doubles = 32 KiB of shared memory */
 #define DMB_MAX_OPS 16          /* fused ops per tile pass */
 #define DMB_MAX_QUBITS 32
@@ -89,6 +89,9 @@ typedef struct dmb_stats {
   uint64_t folded_swaps;         /* trailing SWAP ops realised by the relabelling write-back instead */
   uint64_t small_plan_launches;  /* launches that ran a whole pass list (states of <= 16 tiles), counted in
                                     tile_pass_launches too                                   */
+  uint64_t chained_ops;          /* ops that ran in the shared-memory round trip of the op before them (two
+                                    consecutive CNOT-kind ops on the same ordered digit pair, e.g. the two CNOTs
+                                    of a controlled-phase gate; environment DMB_CHAIN_OPS=0 disables this)  */
 } dmb_stats;
 
 /* ---- context ------------------------------------------------------------------------ */

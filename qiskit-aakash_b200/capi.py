@@ -35,7 +35,8 @@ ABI_VERSION = 5          # include/dmb200.h DMB_ABI_VERSION
 class Stats(ctypes.Structure):
     _fields_ = [("tile_pass_launches", ctypes.c_uint64), ("other_launches", ctypes.c_uint64),
                 ("fused_ops", ctypes.c_uint64), ("state_bytes_moved", ctypes.c_uint64),
-                ("folded_swaps", ctypes.c_uint64), ("small_plan_launches", ctypes.c_uint64)]
+                ("folded_swaps", ctypes.c_uint64), ("small_plan_launches", ctypes.c_uint64),
+                ("chained_ops", ctypes.c_uint64)]
 
 
 class DmbError(RuntimeError):

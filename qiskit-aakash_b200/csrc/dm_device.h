@@ -290,7 +290,9 @@ DMB_HD void dmb_tile_op_thread(int t, const dmb_op& op, double* smem, int K) {
 #define DMB_LEAN_TILE_BYTES (DMB_LEAN_TILE * 8u)        // 32 KiB
 #define DMB_LEAN_PAIRS 8                                 // 16-byte pairs per thread per tile
 enum { DMB_MODE_A = 0, DMB_MODE_PAIR_A = 1, DMB_MODE_PAIR_B = 2 };
-enum { DMB_PA_COL0 = 4, DMB_PB_COL0 = 8, DMB_TSP_ZERO_MEAN = 16, DMB_PAIRABLE = 32 };   // extra flag bits (library-internal)
+enum { DMB_PA_COL0 = 4, DMB_PB_COL0 = 8, DMB_TSP_ZERO_MEAN = 16, DMB_PAIRABLE = 32,
+       DMB_CHAIN = 64 };   // extra flag bits (library-internal); DMB_CHAIN: the NEXT op acts on the same digit pair and runs in
+                           // the same shared-memory round trip (dmb_chain_ops below)
 
 struct alignas(16) dmb_lean_op {
   uint32_t sa[4];      // swizzled BYTE offset of digit-a value i
@@ -304,7 +306,7 @@ struct alignas(16) dmb_lean_pass {
   uint64_t n_tiles;
   int32_t n_ops;
   int32_t td[DMB_LEAN_K];
-  int32_t pad_;
+  int32_t n_chained;                    // ops that run chained to their predecessor (DMB_CHAIN): round trips saved
   uint64_t pair_goff[DMB_LEAN_PAIRS];   // element offset of the uniform part (i << 9)
   uint32_t pair_soff[DMB_LEAN_PAIRS];   // swizzled byte offset of the uniform part
   // relabelling store (trailing SWAP ops folded into the write-back, see dmb_make_lean_pass):
@@ -391,10 +393,62 @@ inline bool dmb_fold_swaps_enabled() {         // DMB_FOLD_SWAPS=0 keeps trailin
   return on;
 }
 
+inline bool dmb_chain_ops_enabled() {          // DMB_CHAIN_OPS=0 runs every op in its own shared-memory round trip (A/B switch)
+  static const bool on = [] { const char* e = getenv("DMB_CHAIN_OPS"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+inline int dmb_op_kindx(const dmb_op& o) {     // kind with the zero-mean TSP CNOT as a kind of its own
+  return (o.kind == DMB_OP_CX_TSP && o.coef[1] == 0.0 && o.coef[4] == 0.0) ? DMB_KIND_TSP0 : o.kind;
+}
+
+// kinds whose chained bodies are instantiated (DMB_CHAIN_VARIANTS): the ideal and the zero-mean TSP CNOT
+inline bool dmb_kind_is_chainable(int kindx) { return kindx == DMB_OP_CX || kindx == DMB_KIND_TSP0; }
+
+inline int dmb_op_map_class(const dmb_op& o, int which) {     // 0 no map, 1 map without column 0, 2 full map
+  if (!(o.flags & (which ? DMB_HAS_PB : DMB_HAS_PA))) return 0;
+  const double* m = which ? o.pb : o.pa;
+  return (m[0] != 0.0 || m[4] != 0.0 || m[8] != 0.0) ? 2 : 1;
+}
+
+// Which ops of a pass share a round trip (DMB_CHAIN).  order[k] = index into P.ops of the op at position k;
+// chain[k] = the op at position k + 1 runs chained to the one at k.  A later op on the same ordered digit pair and of
+// the same CNOT kind is hoisted next to its partner when no op in between touches either digit (ops on disjoint
+// digits commute exactly).
+inline void dmb_chain_ops(const dmb_pass& P, int n_ops, int* order, bool* chain) {
+  for (int k = 0; k < n_ops; ++k) { order[k] = k; chain[k] = false; }
+  if (!dmb_chain_ops_enabled()) return;
+  int k = 0;
+  while (k + 1 < n_ops) {
+    const dmb_op& o = P.ops[order[k]];
+    const int kx = dmb_op_kindx(o);
+    int partner = -1;
+    if (dmb_kind_is_chainable(kx)) {
+      for (int t = k + 1; t < n_ops; ++t) {
+        const dmb_op& x = P.ops[order[t]];
+        if (x.a == o.a || x.a == o.b || x.b == o.a || x.b == o.b) {
+          if (x.a == o.a && x.b == o.b && dmb_op_kindx(x) == kx) partner = t;
+          break;
+        }
+      }
+    }
+    if (partner >= 0) {        // at least one of the four maps must exist: the chained bodies are the both-maps variants
+      const dmb_op& x = P.ops[order[partner]];
+      if (dmb_op_map_class(o, 0) + dmb_op_map_class(o, 1) + dmb_op_map_class(x, 0) + dmb_op_map_class(x, 1) == 0) partner = -1;
+    }
+    if (partner < 0) { ++k; continue; }
+    const int moved = order[partner];
+    for (int t = partner; t > k + 1; --t) order[t] = order[t - 1];
+    order[k + 1] = moved;
+    chain[k] = true;
+    k += 2;
+  }
+}
+
 inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, bool fold_swaps = false) {
   L.n_tiles = 1ull << (n_bits - 2 * DMB_LEAN_K);
   L.n_ops = P.n_ops;
-  L.pad_ = 0;
+  L.n_chained = 0;
   for (int j = 0; j < DMB_LEAN_K; ++j) L.td[j] = P.tile_digit[j];
   for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
     const uint32_t l = (uint32_t)i << 9;
@@ -429,8 +483,12 @@ inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, 
     L.st_pair_soff[i] = dmb_swz(dmb_st_source(l2, L.st_perm)) << 3;
     L.st_pair_goff[i] = dmb_tile_off(l2, P.tile_digit, DMB_LEAN_K);
   }
+  int order[DMB_MAX_OPS];
+  bool chain[DMB_MAX_OPS];
+  dmb_chain_ops(P, L.n_ops, order, chain);
+  L.n_chained = 0;
   for (int k = 0; k < L.n_ops; ++k) {
-    const dmb_op& o = P.ops[k];
+    const dmb_op& o = P.ops[order[k]];
     dmb_lean_op& q = L.ops[k];
     for (int i = 0; i < 4; ++i) {
       q.sa[i] = dmb_swz((uint32_t)i << (2 * o.a)) << 3;
@@ -442,12 +500,27 @@ inline void dmb_make_lean_pass(const dmb_pass& P, int n_bits, dmb_lean_pass& L, 
     q.mode = o.a == 0 ? DMB_MODE_PAIR_A : (o.b == 0 ? DMB_MODE_PAIR_B : DMB_MODE_A);
     for (int i = 0; i < 12; ++i) { q.pa[i] = o.pa[i]; q.pb[i] = o.pb[i]; }
     for (int i = 0; i < 16; ++i) q.coef[i] = o.coef[i];
-    if ((o.flags & DMB_HAS_PA) && (o.pa[0] != 0.0 || o.pa[4] != 0.0 || o.pa[8] != 0.0)) q.flags |= DMB_PA_COL0;
-    if ((o.flags & DMB_HAS_PB) && (o.pb[0] != 0.0 || o.pb[4] != 0.0 || o.pb[8] != 0.0)) q.flags |= DMB_PB_COL0;
+    int ma = dmb_op_map_class(o, 0), mb = dmb_op_map_class(o, 1);
+    const bool leads = chain[k], follows = k > 0 && chain[k - 1];
+    if (leads || follows) {
+      // both ops of a chain run the same both-maps variant: the widest map class of the four maps, a missing map
+      // becomes the identity (x * 1 + 0 * ..: exact)
+      const dmb_op& other = P.ops[order[leads ? k + 1 : k - 1]];
+      int c = ma > mb ? ma : mb;
+      const int oa = dmb_op_map_class(other, 0), ob = dmb_op_map_class(other, 1);
+      if (oa > c) c = oa;
+      if (ob > c) c = ob;
+      static const double ident[12] = {0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+      if (ma == 0) for (int i = 0; i < 12; ++i) q.pa[i] = ident[i];
+      if (mb == 0) for (int i = 0; i < 12; ++i) q.pb[i] = ident[i];
+      q.flags |= DMB_HAS_PA | DMB_HAS_PB;
+      ma = mb = c;
+      if (leads) { q.flags |= DMB_CHAIN; ++L.n_chained; }
+    }
+    if (ma == 2) q.flags |= DMB_PA_COL0;
+    if (mb == 2) q.flags |= DMB_PB_COL0;
     if (o.kind == DMB_OP_CX_TSP && o.coef[1] == 0.0 && o.coef[4] == 0.0) q.flags |= DMB_TSP_ZERO_MEAN;
-    const int kx = (o.kind == DMB_OP_CX_TSP && (q.flags & DMB_TSP_ZERO_MEAN)) ? DMB_KIND_TSP0 : o.kind;
-    const int ma = !(q.flags & DMB_HAS_PA) ? 0 : ((q.flags & DMB_PA_COL0) ? 2 : 1);
-    const int mb = !(q.flags & DMB_HAS_PB) ? 0 : ((q.flags & DMB_PB_COL0) ? 2 : 1);
+    const int kx = dmb_op_kindx(o);
     q.variant = dmb_variant_is_specialised(kx, ma, mb) ? dmb_variant_id(kx, ma, mb, q.mode) : -1;
     // thread digit 0 sits on tile digit 0: virtual threads 2u and 2u+1 own the two halves of every 16-byte pair
     if (q.mode == DMB_MODE_A && o.fd[0] == 0) q.flags |= DMB_PAIRABLE;
@@ -620,8 +693,8 @@ DMB_HD void dmb_spec_math(const dmb_lean_op& op, double (&v)[4][4]) {
 // 2 x 16 LDS.64 + 2 x 16 STS.64), with one address computation per pair.  T is the EVEN virtual thread.
 // Bank conflicts: a quarter-warp of real lanes is a half-warp of virtual lanes, whose 16 8-byte slots are 8
 // distinct 16-byte chunks (tests/test_host_logic.py::test_lane_order_is_bank_conflict_free).
-template <int KINDX, int MA, int MB, class Mem>
-DMB_HD void dmb_lean_op_pair(const dmb_lean_thread& T, const dmb_lean_op& op, const Mem& mem) {
+template <int KINDX, int MA, int MB, bool CHAIN = false, class Mem>
+DMB_HD void dmb_lean_op_pair(const dmb_lean_thread& T, const dmb_lean_op& op, const Mem& mem, const dmb_lean_op* op2 = nullptr) {
   const uint32_t bl = (T.tq[0] << op.sh[0]) | (T.tq[1] << op.sh[1]) | (T.tq[2] << op.sh[2]) | (T.tq[3] << op.sh[3]);
   const uint32_t sb = dmb_swz(bl) << 3;
   double v0[4][4], v1[4][4];
@@ -634,6 +707,10 @@ DMB_HD void dmb_lean_op_pair(const dmb_lean_thread& T, const dmb_lean_op& op, co
     }
   dmb_spec_math<KINDX, MA, MB>(op, v0);
   dmb_spec_math<KINDX, MA, MB>(op, v1);
+  if constexpr (CHAIN) {           // the next op: same digit pair, same variant -- the blocks stay in registers
+    dmb_spec_math<KINDX, MA, MB>(*op2, v0);
+    dmb_spec_math<KINDX, MA, MB>(*op2, v1);
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -646,8 +723,8 @@ DMB_HD void dmb_lean_op_pair(const dmb_lean_thread& T, const dmb_lean_op& op, co
 
 // Compile-time specialised op body: KINDX in {MATS, CX, CX_TSP, SWAP, DMB_KIND_TSP0},
 // MA/MB: 0 = no map, 1 = map without column 0, 2 = full map; MODE as in dmb_lean_op.mode.
-template <int KINDX, int MA, int MB, int MODE, class Mem>
-DMB_HD void dmb_lean_op_spec(const dmb_lean_thread& T, const dmb_lean_op& op, const Mem& mem) {
+template <int KINDX, int MA, int MB, int MODE, bool CHAIN = false, class Mem>
+DMB_HD void dmb_lean_op_spec(const dmb_lean_thread& T, const dmb_lean_op& op, const Mem& mem, const dmb_lean_op* op2 = nullptr) {
   const uint32_t bl = (T.tq[0] << op.sh[0]) | (T.tq[1] << op.sh[1]) | (T.tq[2] << op.sh[2]) | (T.tq[3] << op.sh[3]);
   const uint32_t sb = dmb_swz(bl) << 3;
   double v[4][4];
@@ -697,6 +774,7 @@ DMB_HD void dmb_lean_op_spec(const dmb_lean_thread& T, const dmb_lean_op& op, co
 #pragma unroll
       for (int j = i + 1; j < 4; ++j) { const double tmp = v[i][j]; v[i][j] = v[j][i]; v[j][i] = tmp; }
   }
+  if constexpr (CHAIN) dmb_spec_math<KINDX, MA, MB>(*op2, v);    // the next op on the same digit pair (DMB_CHAIN)
   if constexpr (MODE == DMB_MODE_A) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -787,6 +865,63 @@ DMB_HD void dmb_lean_op_dispatch_pair(const dmb_lean_thread& P0, const dmb_lean_
 // true when dmb_lean_op_dispatch_pair takes the paired body for this op
 DMB_HD bool dmb_lean_op_is_paired(const dmb_lean_op& op) {
   return (op.flags & DMB_PAIRABLE) && op.variant >= 0 && (op.variant % 3) == 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Chained ops (DMB_CHAIN): two consecutive ops on the SAME ordered digit pair and of the same specialised variant --
+// the two CNOTs of a controlled-phase / controlled-rotation gate, of an rzz, ... -- keep their 16-blocks in registers:
+// one shared-memory round trip and one barrier for both.  Same statements in the same order as running them one after
+// the other, so the result is bit-identical.  Instantiated for the ideal and the zero-mean TSP CNOT with both maps present
+// (the host pads a missing map with the identity, dmb_chain_ops).
+// ---------------------------------------------------------------------------------------
+#define DMB_CHAIN_VARIANTS(X) X(DMB_OP_CX, 1, 1) X(DMB_OP_CX, 2, 2) X(DMB_KIND_TSP0, 1, 1) X(DMB_KIND_TSP0, 2, 2)
+
+
+#define DMB_CHAIN_SPEC_CASE(K, A, B)                                                                            \
+  case ((K * 3 + A) * 3 + B) * 3 + 0: dmb_lean_op_spec<K, A, B, 0, true>(T, op, mem, &op2); break;              \
+  case ((K * 3 + A) * 3 + B) * 3 + 1: dmb_lean_op_spec<K, A, B, 1, true>(T, op, mem, &op2); break;              \
+  case ((K * 3 + A) * 3 + B) * 3 + 2: dmb_lean_op_spec<K, A, B, 2, true>(T, op, mem, &op2); break;
+#define DMB_CHAIN_PAIR_CASE(K, A, B) \
+  case ((K * 3 + A) * 3 + B) * 3 + 0: dmb_lean_op_pair<K, A, B, true>(P0, op, mem, &op2); return;
+
+// virtual threads u and u + 128 one after the other, like dmb_lean_op_dispatch_twice
+template <class Mem>
+DMB_HD void dmb_lean_op_chain_twice(const dmb_lean_thread& S0, const dmb_lean_op& op, const dmb_lean_op& op2, const Mem& mem) {
+  dmb_lean_thread T = S0;
+#pragma unroll 1
+  for (uint32_t h = 0; h < 2; ++h) {
+    T.tq[3] = S0.tq[3] + 2u * h;
+    switch (op.variant) {
+      DMB_CHAIN_VARIANTS(DMB_CHAIN_SPEC_CASE)
+      default: break;       // the host chains these variants only
+    }
+  }
+}
+
+template <class Mem>
+DMB_HD void dmb_lean_op_chain_pair(const dmb_lean_thread& P0, const dmb_lean_thread& S0, const dmb_lean_op& op,
+                                   const dmb_lean_op& op2, const Mem& mem) {
+  if (op.flags & DMB_PAIRABLE) {
+    switch (op.variant) {
+      DMB_CHAIN_VARIANTS(DMB_CHAIN_PAIR_CASE)
+      default: break;
+    }
+  }
+  dmb_lean_op_chain_twice(S0, op, op2, mem);
+}
+
+// One step of a pass's op loop for real thread u: runs ops[0] (and ops[1] with it when they are chained) and returns
+// the number of ops consumed.  PAIRED: the shipped kernel's dispatch (dmb_lean_op_dispatch_pair).
+template <bool PAIRED, class Mem>
+DMB_HD int dmb_lean_ops_step(const dmb_lean_thread& P0, const dmb_lean_thread& S0, const dmb_lean_op* ops, const Mem& mem) {
+  if (ops[0].flags & DMB_CHAIN) {
+    if (PAIRED) dmb_lean_op_chain_pair(P0, S0, ops[0], ops[1], mem);
+    else dmb_lean_op_chain_twice(S0, ops[0], ops[1], mem);
+    return 2;
+  }
+  if (PAIRED) dmb_lean_op_dispatch_pair(P0, S0, ops[0], mem);
+  else dmb_lean_op_dispatch_twice(S0, ops[0], mem);
+  return 1;
 }
 
 // load / store of one tile (the CUDA kernel replaces the load by cp.async.cg of the same
@@ -881,9 +1016,8 @@ DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L,
     cx.template wait<STAGES - 1>();
     cx.sync();
     const auto mem = cx.mem(cur * DMB_LEAN_TILE_BYTES);
-    for (int i = 0; i < L.n_ops; ++i) {
-      if (PAIRED) dmb_lean_op_dispatch_pair(P0, S0, L.ops[i], mem);
-      else dmb_lean_op_dispatch_twice(S0, L.ops[i], mem);
+    for (int i = 0; i < L.n_ops;) {
+      i += dmb_lean_ops_step<PAIRED>(P0, S0, &L.ops[i], mem);
       cx.sync();
     }
     const uint64_t tb = dmb_tile_base(tile, L.td, DMB_LEAN_K);

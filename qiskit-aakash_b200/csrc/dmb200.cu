@@ -200,8 +200,8 @@ k_small_passes6(double* __restrict__ state, const dmb_lean_pass* __restrict__ pl
     cx.commit();
     cx.wait<0>();
     __syncthreads();
-    for (int i = 0; i < L.n_ops; ++i) {
-      dmb_lean_op_dispatch_pair(P0, S0, L.ops[i], mem);
+    for (int i = 0; i < L.n_ops;) {
+      i += dmb_lean_ops_step<true>(P0, S0, &L.ops[i], mem);
       __syncthreads();
     }
     if (L.st_mode == DMB_ST_PERM128) {
@@ -373,6 +373,7 @@ static int launch_tile_pass6(dmb_ctx* ctx, double* state, int n_bits, const dmb_
   static thread_local dmb_lean_pass L;    // 6.5 KB: keep it off the stack; one host thread drives a ctx
   dmb_make_lean_pass(P, n_bits, L, dmb_fold_swaps_enabled());
   ctx->stats.folded_swaps += (uint64_t)(P.n_ops - L.n_ops);
+  ctx->stats.chained_ops += (uint64_t)L.n_chained;
   return launch_tile6_any<DMB_TILE_CTAS>(ctx, state, L);
 }
 
@@ -550,6 +551,7 @@ static int apply_passes_small(dmb_ctx* ctx, double* state, int n_bits, const dmb
       for (size_t i = 0; i < m; ++i) {
         dmb_make_lean_pass(passes[done + i], n_bits, h[i], dmb_fold_swaps_enabled());
         ctx->stats.folded_swaps += (uint64_t)(passes[done + i].n_ops - h[i].n_ops);
+        ctx->stats.chained_ops += (uint64_t)h[i].n_chained;
       }
     } else {
       memcpy(ctx->h_plan, passes + done, m * item);
@@ -659,6 +661,7 @@ int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb
     case 6: {
       static thread_local dmb_lean_pass L;
       dmb_make_lean_pass(P, n_bits, L);
+      ctx->stats.chained_ops += (uint64_t)L.n_chained;
       rc = push ? launch_tile6<DMB_TILE_CTAS, 2, DMB_ST_PLAIN>(ctx, dst_state, L, S)
                 : launch_tile6<DMB_TILE_CTAS, 1, DMB_ST_PLAIN>(ctx, dst_state, L, S);
       break;

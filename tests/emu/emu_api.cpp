@@ -81,6 +81,7 @@ static void run_tile_pass(double* state, int n_bits, const dmb_pass& P, const dm
 // thread after the other, tiles one after another
 static int g_variant = 0;
 static thread_local long g_folded_swaps = 0;
+static thread_local long g_chained_ops = 0;
 static long g_paired_ops = 0;     // thread-ops that went through dmb_lean_op_pair (test hook)
 extern "C" long dmb_emu_paired_ops(void) { return g_paired_ops; }
 static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const dmb_remote_src& S = g_no_remote,
@@ -88,6 +89,7 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const d
   static thread_local dmb_lean_pass L;
   dmb_make_lean_pass(P, n_bits, L, dmb_fold_swaps_enabled() && !S.enabled && !D.enabled);
   g_folded_swaps += P.n_ops - L.n_ops;
+  g_chained_ops += L.n_chained;
   alignas(128) static thread_local unsigned char stage[DMB_LEAN_TILE_BYTES];
   static thread_local dmb_lean_thread T[DMB_TILE_THREADS];
   for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_thread_init(t, L, T[t]);
@@ -96,11 +98,14 @@ static void run_tile_pass6(double* state, int n_bits, const dmb_pass& P, const d
   for (uint64_t tile = 0; tile < L.n_tiles; ++tile) {
     const uint64_t tbase = dmb_tile_base(tile, L.td, DMB_LEAN_K);
     for (int t = 0; t < DMB_TILE_THREADS; ++t) dmb_lean_load_thread(T[t], L, state, tbase, S, mem);
-    for (int i = 0; i < L.n_ops; ++i)
+    for (int i = 0; i < L.n_ops;) {
+      int used = 1;
       for (int u = 0; u < DMB_TILE_THREADS / 2; ++u) {   // real thread u plays virtual threads 2u, 2u + 1 or u, u + 128
         if (dmb_lean_op_is_paired(L.ops[i])) ++g_paired_ops;
-        dmb_lean_op_dispatch_pair(T[2 * u], T[u], L.ops[i], mem);
+        used = dmb_lean_ops_step<true>(T[2 * u], T[u], &L.ops[i], mem);
       }
+      i += used;
+    }
     for (int t = 0; t < DMB_TILE_THREADS; ++t) {
       if (D.enabled) dmb_lean_store_thread<true, DMB_ST_PLAIN>(T[t], L, state, tbase, D, mem);
       else if (L.st_mode == DMB_ST_PERM128) dmb_lean_store_thread<false, DMB_ST_PERM128>(T[t], L, state, tbase, D, mem);
@@ -197,6 +202,18 @@ extern "C" int dmb_emu_run_half_kernel(double* state, int n_bits, const dmb_pass
   return 0;
 }
 
+// test hook: how many ops of a K = 6 pass the library chains to their predecessor (dmb_chain_ops), and the op order it runs
+extern "C" int dmb_emu_pass_chained(const dmb_pass* pass, int n_bits, int32_t* order_out) {
+  static thread_local dmb_lean_pass L;
+  if (pass->n_tile_digits != DMB_LEAN_K) return -1;
+  dmb_make_lean_pass(*pass, n_bits, L, dmb_fold_swaps_enabled());
+  if (order_out) {
+    bool chain[DMB_MAX_OPS];
+    dmb_chain_ops(*pass, L.n_ops, order_out, chain);
+  }
+  return L.n_chained;
+}
+
 // test hook: thread order chosen for a SPLIT64 store + worst number of half-warp lanes per bank slot
 extern "C" int dmb_emu_split_order(const int32_t* perm, int32_t* tbit_out) {
   int ibit[3];
@@ -282,8 +299,9 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
       case 5: run_tile_pass<5>(state, n_bits, P); break;
       case 6:
         if (g_variant == 1) run_tile_pass<6>(state, n_bits, P);
-        else { const long before = g_folded_swaps; run_tile_pass6(state, n_bits, P);
-               ctx->stats.folded_swaps += (uint64_t)(g_folded_swaps - before); }
+        else { const long before = g_folded_swaps, chained_before = g_chained_ops; run_tile_pass6(state, n_bits, P);
+               ctx->stats.folded_swaps += (uint64_t)(g_folded_swaps - before);
+               ctx->stats.chained_ops += (uint64_t)(g_chained_ops - chained_before); }
         break;
       default: return fail("dmb_apply_passes", "unsupported tile size");
     }

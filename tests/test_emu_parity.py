@@ -103,6 +103,39 @@ def test_trailing_swaps_are_folded_into_the_store(golden, case_dir, monkeypatch)
         assert results["1"][key] == results["0"][key]
 
 
+@pytest.mark.parametrize("name", ["qft8", "grover4_noisy", "layered_n10_d3_noisy"])
+def test_chained_ops_share_a_round_trip_and_change_nothing(name):
+    """dmb_chain_ops: two consecutive CNOT-kind ops on the same ordered digit pair (the two CNOTs of a controlled-phase
+    gate, ...) keep their 16-blocks in registers -- one shared-memory round trip for both; a partner that is separated
+    by ops on other digits is hoisted next to it.  Same arithmetic on the same values (hoisting reorders commuting ops,
+    which may move the last bit), and the counter shows it happened where the circuit has such pairs."""
+    import json
+    import subprocess
+    import sys
+    if name not in cases.CASES:
+        pytest.skip("no such case")
+    results = {}
+    for chain in ("1", "0"):
+        code = ("import os, sys, json; os.environ['DMB_CHAIN_OPS']=%r; sys.path[:0]=%r; import numpy as np; "
+                "import cases, emu_backend; from qiskit_aakash_b200 import assemble, circuits as C; "
+                "from qiskit_aakash_b200.dm_simulator import DmSimulatorB200; "
+                "case=cases.get(%r); c=C.Circuit(case['n']); c.instructions=case['instrs']; "
+                "es=[]; f=lambda n: (es.append(emu_backend.emu_engine(n)) or es[-1]); "
+                "r=DmSimulatorB200(_engine_factory=f).run(assemble(c), backend_options=case['options']).result(); "
+                "v=r['results'][0]['data']['coeffmatrix']; st=es[0].stats(); "
+                "print(json.dumps({'chained': st['chained_ops'], 'ops': st['fused_ops'], "
+                "'all': [float(x) for x in v[::(1 if v.size < 70000 else 257)]]}))"
+                % (chain, sys.path, name))
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        results[chain] = json.loads(out.stdout.strip().splitlines()[-1])
+    assert results["0"]["chained"] == 0 and results["0"]["ops"] == results["1"]["ops"]
+    if name == "qft8":                                   # every cu1 is two CNOTs on one pair
+        assert results["1"]["chained"] >= 20
+    a, b = np.array(results["1"]["all"]), np.array(results["0"]["all"])
+    assert np.max(np.abs(a - b)) <= 1e-15
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_kernel_variants_match_golden(variant, golden, case_dir):
     """The shipped tile kernel (variant 0: one thread plays virtual threads 2u and 2u + 1, ops that leave tile digit 0

@@ -128,6 +128,30 @@ def test_baseline_configs_at_oracle_sizes(backend):
     _compare_with_oracle(backend, g.n_qubits, g.instructions, dict(C.grover_options(), compute_densitymatrix=False))
 
 
+@pytest.mark.parametrize("n,noisy", [(10, False), (11, False), (9, True)])
+def test_chained_cnots_of_controlled_phase_gates_on_cuda(backend, n, noisy):
+    """QFT above one tile: the two CNOTs of every cu1 act on one ordered digit pair and share a shared-memory round trip
+    in k_tile_pass6 (DMB_CHAIN, dmb_stats.chained_ops); ideal CNOTs and, with the noise options, TSP CNOTs with full
+    maps.  Against the oracle."""
+    from oracle import dm_oracle
+    from qiskit_aakash_b200 import assemble, circuits as C
+    circ = C.qft(n)
+    opts = dict(C.noisy_options() if noisy else {}, compute_densitymatrix=False)
+    if noisy:
+        opts.update(C.grover_options())
+    be = backend()
+    c2 = C.Circuit(n)
+    c2.instructions = copy.deepcopy(circ.instructions)
+    got = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
+    st = be.last_engine_stats
+    assert st["chained_ops"] >= n * (n - 1) // 4, st          # at least half of the n (n - 1) / 2 controlled phases
+    ref = dm_oracle.run_oracle(n, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
+    assert np.max(np.abs(got["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])) <= TOL
+    p = np.array(list(got["data"]["ensemble_probability"].values()))
+    q = np.array(list(ref["data"]["ensemble_probability"].values()))
+    assert np.max(np.abs(p - q)) <= TOL and abs(got["data"]["coeffmatrix"][0] * 2 ** n - 1) <= TRACE_TOL
+
+
 @pytest.mark.parametrize("name", ["grover12_noisy", "layered_n12_d6_noisy"])
 def test_full_circuits_at_n12_match_the_reference(backend, name):
     """north_star: results within 1e-10 of the reference at n <= 12.  FULL circuits at n = 12 -- Grover-12

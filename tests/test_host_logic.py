@@ -393,3 +393,55 @@ def test_relabelling_store_is_an_exact_digit_permutation():
     import store_cases
     folded, total = store_cases.check_relabelling_store(emu_engine)
     assert folded == total
+
+
+def test_chained_op_order_keeps_every_dependency():
+    """dmb_chain_ops hoists the second CNOT of a same-pair couple next to the first one.  Random K = 6 passes: the order
+    the library runs is a permutation of the ops in front of the folded swaps, any two ops that share a tile digit keep
+    their relative order (ops on disjoint digits commute), and exactly the adjacent same-pair, same-kind couples with
+    at least one map are chained."""
+    import ctypes
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "emu"))
+    import build_emu
+    from qiskit_aakash_b200 import capi, schedule
+    lib = ctypes.CDLL(build_emu.build())
+    lib.dmb_emu_pass_chained.restype = ctypes.c_int
+    rng = np.random.default_rng(7)
+    total_chained = 0
+    for trial in range(300):
+        P = np.zeros(1, dtype=capi.PASS_DTYPE)
+        n_ops = int(rng.integers(1, capi.MAX_OPS + 1))
+        P[0]["n_tile_digits"] = 6
+        P[0]["n_ops"] = n_ops
+        P[0]["tile_digit"][:6] = [0, 1, 2, 3, 4, 5]
+        pairs = []
+        for k in range(n_ops):
+            if pairs and rng.random() < 0.35:
+                a, b = pairs[int(rng.integers(len(pairs)))]          # revisit an earlier pair (same orientation)
+            else:
+                a, b = (int(x) for x in rng.choice(6, 2, replace=False))
+            pairs.append((a, b))
+            op = P[0]["ops"][k]
+            op["kind"] = capi.OP_CX if rng.random() < 0.8 else capi.OP_MATS
+            op["a"], op["b"] = a, b
+            op["fd"][:4] = schedule.lane_order(6, a, b)
+            if rng.random() < 0.8:
+                op["flags"] |= capi.HAS_PA
+                op["pa"][:] = [0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]
+            if rng.random() < 0.6:
+                op["flags"] |= capi.HAS_PB
+                op["pb"][:] = [0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]
+        order = (ctypes.c_int32 * capi.MAX_OPS)()
+        chained = lib.dmb_emu_pass_chained(ctypes.c_void_p(P.ctypes.data), 12, order)
+        assert chained >= 0
+        total_chained += chained
+        got = list(order[:n_ops])
+        assert sorted(got) == list(range(n_ops))
+        where = {op_index: position for position, op_index in enumerate(got)}
+        for i in range(n_ops):
+            for j in range(i + 1, n_ops):
+                if set(pairs[i]) & set(pairs[j]):
+                    assert where[i] < where[j], (trial, pairs, got)
+    assert total_chained > 100
