@@ -912,12 +912,16 @@ DMB_HD void dmb_lean_op_chain_pair(const dmb_lean_thread& P0, const dmb_lean_thr
 
 // One step of a pass's op loop for real thread u: runs ops[0] (and ops[1] with it when they are chained) and returns
 // the number of ops consumed.  PAIRED: the shipped kernel's dispatch (dmb_lean_op_dispatch_pair).
-template <bool PAIRED, class Mem>
+// CHAINS = false: an instantiation without the chained bodies, for passes whose L.n_chained is 0 (the host picks; keeps
+// the instruction footprint of the common kernel what it was).
+template <bool PAIRED, bool CHAINS = true, class Mem>
 DMB_HD int dmb_lean_ops_step(const dmb_lean_thread& P0, const dmb_lean_thread& S0, const dmb_lean_op* ops, const Mem& mem) {
-  if (ops[0].flags & DMB_CHAIN) {
-    if (PAIRED) dmb_lean_op_chain_pair(P0, S0, ops[0], ops[1], mem);
-    else dmb_lean_op_chain_twice(S0, ops[0], ops[1], mem);
-    return 2;
+  if constexpr (CHAINS) {
+    if (ops[0].flags & DMB_CHAIN) {
+      if (PAIRED) dmb_lean_op_chain_pair(P0, S0, ops[0], ops[1], mem);
+      else dmb_lean_op_chain_twice(S0, ops[0], ops[1], mem);
+      return 2;
+    }
   }
   if (PAIRED) dmb_lean_op_dispatch_pair(P0, S0, ops[0], mem);
   else dmb_lean_op_dispatch_twice(S0, ops[0], mem);
@@ -978,7 +982,7 @@ DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass&
 // R.tab[idx >> R.shift] that holds it in the old layout; 2 "push": the write-back goes to the peer that owns idx.
 // ---------------------------------------------------------------------------------------
 #define DMB_HALF_THREADS 128
-template <int STMODE, bool PAIRED, int STAGES, int REMOTE, class Ctx>
+template <int STMODE, bool PAIRED, int STAGES, int REMOTE, bool CHAINS = true, class Ctx>
 DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L, const dmb_remote_src& R) {
   dmb_lean_thread S0, S1;
   dmb_lean_thread_init(cx.tid(), L, S0);
@@ -1017,7 +1021,7 @@ DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L,
     cx.sync();
     const auto mem = cx.mem(cur * DMB_LEAN_TILE_BYTES);
     for (int i = 0; i < L.n_ops;) {
-      i += dmb_lean_ops_step<PAIRED>(P0, S0, &L.ops[i], mem);
+      i += dmb_lean_ops_step<PAIRED, CHAINS>(P0, S0, &L.ops[i], mem);
       cx.sync();
     }
     const uint64_t tb = dmb_tile_base(tile, L.td, DMB_LEAN_K);

@@ -153,14 +153,16 @@ struct dmb_cuda_cta {
 
 // REMOTE: 0 in place, 1 pull (remote loads), 2 push (remote stores); STMODE: DMB_ST_PLAIN, or a relabelling
 // store that realises the pass's trailing digit swaps
-template <int CTAS, int REMOTE, int STMODE>
+// CHAINS: the instantiation that also carries the chained op bodies (passes with L.n_chained > 0, dmb_chain_ops); the
+// common one is kept free of them
+template <int CTAS, int REMOTE, int STMODE, bool CHAINS = false>
 __global__ void __launch_bounds__(DMB_HALF_THREADS, CTAS)
 k_tile_pass6(double* __restrict__ state, const __grid_constant__ dmb_lean_pass L,
              const __grid_constant__ dmb_remote_src S) {
   extern __shared__ __align__(128) unsigned char lean_smem[];
   dmb_cuda_cta cx;
   cx.smem0 = (uint32_t)__cvta_generic_to_shared(lean_smem);
-  dmb_half_kernel_body<STMODE, true, 1, REMOTE>(cx, state, L, S);
+  dmb_half_kernel_body<STMODE, true, 1, REMOTE, CHAINS>(cx, state, L, S);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -346,20 +348,26 @@ static int launch_tile_pass(dmb_ctx* ctx, double* state, int n_bits, const dmb_p
 }
 
 #define DMB_TILE_CTAS 5      // CTAs per SM of k_tile_pass6 (measured on config 3: 4 -> 232.0 ms, 5 -> 223.0 ms, 6 -> 226.7 ms)
-template <int CTAS, int REMOTE, int STMODE>
-static int launch_tile6(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, const dmb_remote_src& S = g_no_remote) {
+template <int CTAS, int REMOTE, int STMODE, bool CHAINS>
+static int launch_tile6_inst(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, const dmb_remote_src& S) {
   const size_t smem = DMB_LEAN_TILE_BYTES;
   static std::atomic<uint64_t> attr_done[2];          // one bit per device: the attribute is per device
   const int dev = ctx->device & 127;
   if (!((attr_done[dev >> 6].load() >> (dev & 63)) & 1ull)) {
-    CU_TRY(cudaFuncSetAttribute(k_tile_pass6<CTAS, REMOTE, STMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_tile_pass6<CTAS, REMOTE, STMODE, CHAINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[dev >> 6].fetch_or(1ull << (dev & 63));
   }
   uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
   if (grid > L.n_tiles) grid = L.n_tiles;
-  k_tile_pass6<CTAS, REMOTE, STMODE><<<(unsigned)grid, DMB_HALF_THREADS, smem, ctx->stream>>>(state, L, S);
+  k_tile_pass6<CTAS, REMOTE, STMODE, CHAINS><<<(unsigned)grid, DMB_HALF_THREADS, smem, ctx->stream>>>(state, L, S);
   CU_TRY(cudaGetLastError());
   return 0;
+}
+
+template <int CTAS, int REMOTE, int STMODE>
+static int launch_tile6(dmb_ctx* ctx, double* state, const dmb_lean_pass& L, const dmb_remote_src& S = g_no_remote) {
+  return L.n_chained > 0 ? launch_tile6_inst<CTAS, REMOTE, STMODE, true>(ctx, state, L, S)
+                         : launch_tile6_inst<CTAS, REMOTE, STMODE, false>(ctx, state, L, S);
 }
 
 template <int CTAS>
