@@ -444,7 +444,7 @@ def run_ours(args):
     except Exception:
         pass
     # DRAM bytes per launch from the latest committed `ncu --set full` capture of this kernel
-    for fname in ("r02_tile_pass_ncu_summary.json", "r01b_tile_pass_ncu_summary.json"):
+    for fname in ("r02f_tile_pass_ncu_summary.json", "r02_tile_pass_ncu_summary.json", "r01b_tile_pass_ncu_summary.json"):
         prof = os.path.join(ROOT, "profiles", fname)
         if os.path.exists(prof) and world == 1 and n == 14:
             try:
