@@ -28,8 +28,11 @@ def main():
     comm = distributed.TorchCommunicator()
     worst = 0.0
     for n, seed, mode in ((8, 1, "rand"), (9, 2, "layered"), (10, 3, "rand"), (10, 4, "layered"), (9, 5, "nbasis"),
-                          (8, 6, "matrix")):
-        circ = cases._rand_circuit(n, 60, seed) if mode != "layered" else C.random_layered(n, 6, seed, readout=False)
+                          (8, 6, "matrix"), (10, 7, "qft"), (10, 8, "qft_noisy")):
+        if mode.startswith("qft"):               # every cu1 = two chained CNOTs (dmb_chain_ops), also in the pull pass
+            circ = C.qft(n, readout=False)
+        else:
+            circ = cases._rand_circuit(n, 60, seed) if mode != "layered" else C.random_layered(n, 6, seed, readout=False)
         if mode == "nbasis":                     # N-basis ensemble readout with pending maps on global qubits
             for q in range(n):
                 circ.u3(0.4 + q, 0.1, 0.2, q)
@@ -40,7 +43,7 @@ def main():
             circ.barrier()
         else:
             circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="XYZ"[seed % 3])
-        opts = dict(cases.FULL_NOISE, compute_densitymatrix=(mode == "matrix"))
+        opts = dict({} if mode == "qft" else cases.FULL_NOISE, compute_densitymatrix=(mode == "matrix"))
         engines = []
 
         def factory(nq):
@@ -63,7 +66,10 @@ def main():
             worst = max(worst, d_p, d_c)
             print(json.dumps({"check": "sharded_vs_oracle", "world": world, "n": n, "mode": mode, "d_prob": d_p,
                               "d_coeff": d_c, "exchanges": engines[0].exchanges, "fused_exchange": engines[0].peers is not None,
-                              "nvlink_bytes_sent_per_rank": engines[0].nvlink_bytes_sent}))
+                              "nvlink_bytes_sent_per_rank": engines[0].nvlink_bytes_sent,
+                              "chained_ops": engines[0].stats().get("chained_ops")}))
+            if mode.startswith("qft"):
+                assert engines[0].stats().get("chained_ops", 0) > 0
         dist.barrier()
     # sharded dumps: store -> per-rank slice files (no gather), compare and restart from them, canonical layout;
     # through the PUBLIC constructor (DmSimulatorB200(comm=...): what get_backend returns inside a process group)

@@ -143,3 +143,20 @@ def test_recycled_engine_runs_the_next_job_correctly(world, n, seed):
             p = np.array(list(res["data"]["ensemble_probability"].values()))
             assert np.max(np.abs(p - p_ref)) <= 1e-10
             assert np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])) <= 1e-10
+
+
+@pytest.mark.parametrize("world,n", [(2, 7), (4, 8), (8, 8)])
+def test_sharded_qft_with_chained_cnots_matches_oracle(world, n):
+    """QFT on a sharded state: the two CNOTs of a cu1 are chained (one shared-memory round trip, dmb_chain_ops) also in
+    the pass that pulls its tiles from the peers, and cu1 gates on global qubits force exchanges in between."""
+    circ = C.qft(n)
+    opts = {"compute_densitymatrix": False}
+    ref = dm_oracle.run_oracle(n, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
+    p_ref = np.array(list(ref["data"]["ensemble_probability"].values()))
+    for fused, xmode in ((True, "pull"), (True, "push"), (False, "nccl")):
+        outs = _run_world(world, n, circ, opts, fused, xmode)
+        for rank, (res, exchanges, has_peers) in enumerate(outs):
+            assert exchanges >= 1
+            p = np.array(list(res["data"]["ensemble_probability"].values()))
+            assert np.max(np.abs(p - p_ref)) <= 1e-10
+            assert np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])) <= 1e-10
