@@ -402,8 +402,8 @@ inline int dmb_op_kindx(const dmb_op& o) {     // kind with the zero-mean TSP CN
   return (o.kind == DMB_OP_CX_TSP && o.coef[1] == 0.0 && o.coef[4] == 0.0) ? DMB_KIND_TSP0 : o.kind;
 }
 
-// kinds whose chained bodies are instantiated (DMB_CHAIN_VARIANTS): the ideal and the zero-mean TSP CNOT
-inline bool dmb_kind_is_chainable(int kindx) { return kindx == DMB_OP_CX || kindx == DMB_KIND_TSP0; }
+// kinds whose chained bodies are instantiated (DMB_CHAIN_VARIANTS): the ideal CNOT and both TSP CNOTs
+inline bool dmb_kind_is_chainable(int kindx) { return kindx == DMB_OP_CX || kindx == DMB_KIND_TSP0 || kindx == DMB_OP_CX_TSP; }
 
 inline int dmb_op_map_class(const dmb_op& o, int which) {     // 0 no map, 1 map without column 0, 2 full map
   if (!(o.flags & (which ? DMB_HAS_PB : DMB_HAS_PA))) return 0;
@@ -871,10 +871,11 @@ DMB_HD bool dmb_lean_op_is_paired(const dmb_lean_op& op) {
 // Chained ops (DMB_CHAIN): two consecutive ops on the SAME ordered digit pair and of the same specialised variant --
 // the two CNOTs of a controlled-phase / controlled-rotation gate, of an rzz, ... -- keep their 16-blocks in registers:
 // one shared-memory round trip and one barrier for both.  Same statements in the same order as running them one after
-// the other, so the result is bit-identical.  Instantiated for the ideal and the zero-mean TSP CNOT with both maps present
+// the other, so the result is bit-identical.  Instantiated for the ideal CNOT and the TSP CNOTs with both maps present
 // (the host pads a missing map with the identity, dmb_chain_ops).
 // ---------------------------------------------------------------------------------------
-#define DMB_CHAIN_VARIANTS(X) X(DMB_OP_CX, 1, 1) X(DMB_OP_CX, 2, 2) X(DMB_KIND_TSP0, 1, 1) X(DMB_KIND_TSP0, 2, 2)
+#define DMB_CHAIN_VARIANTS(X) \
+  X(DMB_OP_CX, 1, 1) X(DMB_OP_CX, 2, 2) X(DMB_KIND_TSP0, 1, 1) X(DMB_KIND_TSP0, 2, 2) X(DMB_OP_CX_TSP, 1, 1) X(DMB_OP_CX_TSP, 2, 2)
 
 
 #define DMB_CHAIN_SPEC_CASE(K, A, B)                                                                            \
