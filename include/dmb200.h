@@ -29,7 +29,8 @@ extern "C" {
 
 #define DMB_ABI_VERSION 5   /* 2: dmb_stats.folded_swaps; 3: dmb_schedule; 4: dmb_op.post_swap and
                                dmb_stats.r3_phases removed (measured slower, round 2), dmb_ipc_close;
-                               5: dmb_download_async, dmb_stats.chained_ops */
+                               5: dmb_download_async, dmb_stats.chained_ops,
+                               dmb_apply_pass_remote_sel */
 #define DMB_MAX_TILE_DIGITS 6   /* a tile holds 4^6 = 4096 doubles = 32 KiB of shared memory */
 #define DMB_MAX_OPS 16          /* fused ops per tile pass */
 #define DMB_MAX_QUBITS 32
@@ -195,6 +196,11 @@ int dmb_schedule(const dmb_qop* ops, size_t n_ops, int32_t* pos, int n_qubits, i
  * i.e. into the buffers of the ranks that own the data after the swap (remote stores). */
 int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb_pass* pass,
                           const uint64_t* src_tab, int tab_bits, int block_shift, int push);
+/* The same with the table index gathered from n_sel <= 5 SELECTED bits of the element index (bit sel_bits[j] of idx is
+ * bit j of the table index) instead of its high bits: a global slot swapped with an ARBITRARY local slot, so that the
+ * evicted qubit need not be parked on the top local slots by a pass of its own (distributed.py).                   */
+int dmb_apply_pass_remote_sel(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb_pass* pass,
+                              const uint64_t* src_tab, int n_sel, const int32_t* sel_bits, int push);
 int dmb_ipc_export(dmb_ctx* ctx, const void* dev_ptr, unsigned char* handle64, uint64_t* offset);
 int dmb_ipc_open(dmb_ctx* ctx, const unsigned char* handle64, uint64_t offset, void** out_ptr);
 int dmb_ipc_close(dmb_ctx* ctx, const unsigned char* handle64);

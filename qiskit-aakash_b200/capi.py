@@ -65,6 +65,7 @@ _SIGNATURES = {
     "dmb_init_product": (_i, [_vp, _vp, _i, _u64, _i, _vp, _vp, _vp, _d]),
     "dmb_apply_passes": (_i, [_vp, _vp, _i, _vp, _sz]),
     "dmb_apply_pass_remote": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i]),
+    "dmb_apply_pass_remote_sel": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _i]),
     "dmb_ipc_export": (_i, [_vp, _vp, _vp, _vp]),
     "dmb_ipc_open": (_i, [_vp, _vp, _u64, _vp]),
     "dmb_ipc_close": (_i, [_vp, _vp]),
@@ -209,6 +210,16 @@ class Context:
         assert (1 << tab_bits) == len(tab)
         self._check(self.lib.dmb_apply_pass_remote(self._h, dst_ptr, int(n_bits), _ptr(one_pass), _ptr(tab),
                                                    tab_bits, int(block_shift), 1 if push else 0))
+
+    def apply_pass_remote_sel(self, dst_ptr, n_bits, one_pass, src_tab, sel_bits, push=False):
+        """The same with the table index gathered from the selected bits ``sel_bits`` of the element index (a global slot
+        swapped with an arbitrary local slot)."""
+        assert one_pass.dtype == PASS_DTYPE and len(one_pass) == 1
+        tab = np.ascontiguousarray(src_tab, dtype=np.uint64)
+        sel = np.ascontiguousarray(sel_bits, dtype=np.int32)
+        assert len(tab) == 1 << len(sel)
+        self._check(self.lib.dmb_apply_pass_remote_sel(self._h, dst_ptr, int(n_bits), _ptr(one_pass), _ptr(tab),
+                                                       len(sel), _ptr(sel), 1 if push else 0))
 
     def ipc_export(self, dev_ptr):
         handle = (ctypes.c_ubyte * 64)()

@@ -67,19 +67,33 @@ DMB_HD uint64_t dmb_tile_off(uint32_t l, const int32_t* td, int K) {
 
 // Fused exchange ("pull"): in the pass that follows a global<->local slot swap, element idx of
 // the NEW local layout is read straight from the rank that holds it in the OLD layout --
-// tab[idx >> shift] is that rank's (peer-mapped) buffer address, pre-offset so that the
+// tab[dmb_remote_index(idx)] is that rank's (peer-mapped) buffer address, pre-offset so that the
 // element sits at tab[..] + idx -- and the result is written to the local destination buffer.
 // One kernel does the all-to-all and the first fused ops; enabled == 0 means in place.
+// The table index is gathered from up to DMB_REMOTE_BITS SELECTED bits of the element index (sel[j] = position of the
+// bit that becomes bit j of the table index): the high bits when the global slots are swapped with the top local slots,
+// scattered bits when a global slot is swapped with an arbitrary local slot (no parking pass, distributed.py).
 #define DMB_REMOTE_MAX 32
+#define DMB_REMOTE_BITS 5
 struct dmb_remote_src {
   uint64_t tab[DMB_REMOTE_MAX];
-  int32_t shift;
+  int32_t n_sel;
   int32_t enabled;
+  int32_t sel[DMB_REMOTE_BITS];
+  int32_t pad_;
 };
+
+DMB_HD uint32_t dmb_remote_index(const dmb_remote_src& S, uint64_t idx) {
+  uint32_t k = 0;
+#pragma unroll
+  for (int j = 0; j < DMB_REMOTE_BITS; ++j)
+    if (j < S.n_sel) k |= (uint32_t)((idx >> S.sel[j]) & 1ull) << j;
+  return k;
+}
 
 DMB_HD const double* dmb_src_ptr(const dmb_remote_src& S, const double* local, uint64_t idx) {
   if (!S.enabled) return local + idx;
-  return reinterpret_cast<const double*>(S.tab[idx >> S.shift]) + idx;
+  return reinterpret_cast<const double*>(S.tab[dmb_remote_index(S, idx)]) + idx;
 }
 
 // Load phase: thread t moves the 16-byte pairs p = t, t+256, ... (tile_digit[0] == 0, so the
@@ -108,7 +122,7 @@ DMB_HD void dmb_tile_load_thread(int t, const double* __restrict__ state, uint64
 // into the buffer of the rank that owns it in the new layout (same table convention).
 DMB_HD double* dmb_dst_ptr(const dmb_remote_src& D, double* local, uint64_t idx) {
   if (!D.enabled) return local + idx;
-  return reinterpret_cast<double*>(D.tab[idx >> D.shift]) + idx;
+  return reinterpret_cast<double*>(D.tab[dmb_remote_index(D, idx)]) + idx;
 }
 
 template <int MAXPAIRS>
@@ -959,7 +973,7 @@ DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass&
 #pragma unroll
   for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
     const uint64_t idx = tile_base + (STMODE == DMB_ST_SPLIT64 ? (T.st_goff | L.st_pair_goff[i]) : (T.goff | L.pair_goff[i]));
-    double* dst = PUSH ? reinterpret_cast<double*>(D.tab[idx >> D.shift]) + idx : state + idx;
+    double* dst = PUSH ? reinterpret_cast<double*>(D.tab[dmb_remote_index(D, idx)]) + idx : state + idx;
     *reinterpret_cast<dmb_d2*>(dst) = w[i];
   }
 }
@@ -980,7 +994,7 @@ DMB_HD void dmb_lean_store_thread(const dmb_lean_thread& T, const dmb_lean_pass&
 // SM); STAGES = 2: the next tile of this CTA streams in during the op phase (measured slower on B200, kept for the
 // CPU control-flow test of the ring).
 // REMOTE (fused exchange, distributed.py): 0 in place; 1 "pull": pair idx of the tile is loaded from the peer buffer
-// R.tab[idx >> R.shift] that holds it in the old layout; 2 "push": the write-back goes to the peer that owns idx.
+// R.tab[dmb_remote_index(R, idx)] that holds it in the old layout; 2 "push": the write-back goes to the peer that owns idx.
 // ---------------------------------------------------------------------------------------
 #define DMB_HALF_THREADS 128
 template <int STMODE, bool PAIRED, int STAGES, int REMOTE, bool CHAINS = true, class Ctx>
@@ -993,7 +1007,7 @@ DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L,
   const uint64_t first = cx.block(), stride = cx.grid();
   if (first >= L.n_tiles) return;
   auto src_of = [&](uint64_t idx) -> const double* {
-    if (REMOTE == 1) return reinterpret_cast<const double*>(R.tab[idx >> R.shift]) + idx;
+    if (REMOTE == 1) return reinterpret_cast<const double*>(R.tab[dmb_remote_index(R, idx)]) + idx;
     return state + idx;
   };
   if (STAGES == 2) {

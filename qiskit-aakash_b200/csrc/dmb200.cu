@@ -647,16 +647,27 @@ int dmb_apply_passes(dmb_ctx* ctx, double* state, int n_bits, const dmb_pass* pa
 
 int dmb_apply_pass_remote(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb_pass* pass,
                           const uint64_t* src_tab, int tab_bits, int block_shift, int push) {
-  if (!ctx || !dst_state || !pass || !src_tab) return fail("dmb_apply_pass_remote", "null argument");
-  if (tab_bits < 0 || (1 << tab_bits) > DMB_REMOTE_MAX) return fail("dmb_apply_pass_remote", "table too large");
+  if (tab_bits < 0 || tab_bits > DMB_REMOTE_BITS) return fail("dmb_apply_pass_remote", "table too large");
   if (block_shift + tab_bits != n_bits) return fail("dmb_apply_pass_remote", "block_shift + tab_bits != n_bits");
+  int32_t sel[DMB_REMOTE_BITS];
+  for (int j = 0; j < tab_bits; ++j) sel[j] = block_shift + j;       // the table index = the high bits of the element index
+  return dmb_apply_pass_remote_sel(ctx, dst_state, n_bits, pass, src_tab, tab_bits, sel, push);
+}
+
+int dmb_apply_pass_remote_sel(dmb_ctx* ctx, double* dst_state, int n_bits, const dmb_pass* pass,
+                              const uint64_t* src_tab, int n_sel, const int32_t* sel_bits, int push) {
+  if (!ctx || !dst_state || !pass || !src_tab || (!sel_bits && n_sel)) return fail("dmb_apply_pass_remote", "null argument");
+  if (n_sel < 0 || n_sel > DMB_REMOTE_BITS) return fail("dmb_apply_pass_remote", "table too large");
+  for (int j = 0; j < n_sel; ++j)
+    if (sel_bits[j] < 0 || sel_bits[j] >= n_bits) return fail("dmb_apply_pass_remote", "selected bit outside the local index");
   DMB_ON_DEVICE(ctx);
   if (validate_pass(*pass, n_bits)) return 1;
   const dmb_pass& P = *pass;
   dmb_remote_src S;
   memset(&S, 0, sizeof(S));
-  for (int i = 0; i < (1 << tab_bits); ++i) S.tab[i] = src_tab[i];
-  S.shift = block_shift;
+  for (int i = 0; i < (1 << n_sel); ++i) S.tab[i] = src_tab[i];
+  S.n_sel = n_sel;
+  for (int j = 0; j < n_sel; ++j) S.sel[j] = sel_bits[j];
   S.enabled = 1;
   int rc = 0;
   const dmb_remote_src& ld = push ? g_no_remote : S;     // pull: table drives the loads

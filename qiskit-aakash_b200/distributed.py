@@ -215,6 +215,7 @@ class ShardedPauliEngine(PauliEngine):
         self.relabel_local = bool(int(os.environ.get("DMB_RELABEL", "1")))
         self.park_in_last_pass = bool(int(os.environ.get("DMB_PARK_IN_LAST_PASS", "1")))
         self.exchanges = 0
+        self.direct_exchanges = 0        # exchanges that swapped a global slot with the evictee's own slot (no parking)
         self.nvlink_bytes_sent = 0
         # fused exchange: the pass after a slot swap pulls its tiles from the peers' buffers
         self.peers, self._ipc_handles = None, []
@@ -227,6 +228,10 @@ class ShardedPauliEngine(PauliEngine):
         self.plain_exchange = bool(int(os.environ.get("DMB_EXCHANGE_PLAIN", "0")))   # op-free pull pass
         if self.exchange_mode == "nccl":
             self.peers = None
+        # fused pull only: a global slot is swapped with the evicted qubit's OWN local slot (the pull pass gathers its
+        # source table index from scattered index bits), so no pass is spent on parking the evictee on the top local
+        # slots first.  DMB_DIRECT_SLOTS=0: always park (what the push / NCCL exchanges need).
+        self.direct_slots = bool(int(os.environ.get("DMB_DIRECT_SLOTS", "1")))
 
     def recycle(self):
         """Make the engine ready for the next job on the same register size: the two shards and -- what costs 60 ms at
@@ -241,6 +246,7 @@ class ShardedPauliEngine(PauliEngine):
         self.passes_run = 0
         self.h2d_bytes = 0
         self.exchanges = 0
+        self.direct_exchanges = 0
         self.nvlink_bytes_sent = 0
         if self.exchange_events is not None:
             self.exchange_events = []
@@ -290,6 +296,46 @@ class ShardedPauliEngine(PauliEngine):
 
     # -- scheduling with exchanges ------------------------------------------------------------
     def compile(self, final=True):
+        """Queue -> steps (see ``_compile_one``).  With the fused pull available the schedule is compiled up to three
+        ways -- evictees parked on the top local slots (what every exchange mode can run), global slots swapped with the
+        evictees' own slots, the same with the evictees chosen after the stretch is scheduled -- and the cheapest one
+        by (passes + exchanges x their relative cost) is kept: which one wins depends on how the layout the exchange
+        leaves behind suits the rest of the circuit (config 5: 25 -> 23 passes; QFT-16 on 8 ranks: parking wins).  An
+        extra variant is only compiled while one compile (estimated from the op count, so that every rank decides
+        alike) costs less than 1 % of the estimated device time."""
+        forced = getattr(self, "force_exchange_variant", None) or os.environ.get("DMB_EXCHANGE_VARIANT")
+        if forced:                                   # tests / A-B runs: "parked" | "direct" | "direct_late"
+            self.last_compile_mode = forced
+            return self._compile_one(final, forced)
+        modes = ["parked"]
+        if self._direct_exchange():
+            modes += ["direct", "direct_late"]
+        if len(modes) == 1:
+            self.last_compile_mode = "parked"
+            return self._compile_one(final, "parked")
+        saved = (list(self.queue), list(self.pos), list(self.pending))
+        pass_ms = 16.0 * 2.0 ** self.n_bits / 2.6e12 * 1e3            # a fused pass at ~0.4 of the HBM roofline
+        ex_cost = 2.5 * (self.world - 1) / self.world                 # an exchange, in passes (NVLink ~600 GB/s)
+        best = None
+        for k, mode in enumerate(modes):
+            self.queue, self.pos, self.pending = list(saved[0]), list(saved[1]), list(saved[2])
+            steps = self._compile_one(final, mode)
+            n_pass = sum(len(st[1]) for st in steps if st[0] == "passes")
+            n_ex = sum(1 for st in steps if st[0] == "exchange")
+            cost = n_pass + ex_cost * n_ex
+            if best is None or cost < best[0]:
+                best = (cost, steps, self.pos, self.pending, mode)
+            # the decision must be the same on every rank: it depends on the schedule only, never on a measured time
+            # (a compile takes ~10 us per op on the host; an extra one has to stay below ~1 % of the device time)
+            n_ops = sum(int(p["n_ops"]) for st in steps if st[0] == "passes" for p in st[1])
+            if n_ex == 0 or 0.010 * n_ops > 0.01 * cost * pass_ms:
+                break
+        self.queue = []
+        self.pos, self.pending = best[2], best[3]
+        self.last_compile_mode = best[4]
+        return best[1]
+
+    def _compile_one(self, final, exchange_variant):
         """Queue (+ pending maps of LOCAL qubits if ``final``) -> list of steps
         ``("passes", PASS array)`` / ``("exchange",)``; updates ``self.pos`` to the layout
         after the last step and clears the queue.  Pending maps of qubits that end up global
@@ -298,7 +344,11 @@ class ShardedPauliEngine(PauliEngine):
         queue = list(self.queue)
         pos = list(self.pos)
         n_loc, m = self.n_loc, self.m
+        rounds = 0
         while True:
+            rounds += 1
+            if rounds > 2 * len(self.queue) + 8:          # every exchange must unblock at least one op
+                raise BasicAerError("internal: sharded compile makes no progress")
             # ops runnable in the current layout: all qubits local, none blocked by a skipped op
             blocked, run, keep = set(), [], []
             for item in queue:
@@ -320,7 +370,8 @@ class ShardedPauliEngine(PauliEngine):
                 local = [q for q in range(self.n) if pos[q] < n_loc]
                 local.sort(key=lambda q: (-next_use.get(q, len(keep) + 1), pos[q]))
                 victims = local[:m]
-            moves = [(v, n_loc - m + i) for i, v in enumerate(victims)]
+            direct = bool(keep) and exchange_variant != "parked" and self._direct_exchange()
+            moves = [] if direct else [(v, n_loc - m + i) for i, v in enumerate(victims)]
             if use_relabel:
                 qops = [schedule.DevOp(kind, qa, qb, pa, pb, coef) for (_, kind, qa, qb, pa, pb, coef) in run]
                 if not keep and final:
@@ -339,7 +390,7 @@ class ShardedPauliEngine(PauliEngine):
                     P, moves = schedule.relabel_passes(self.lib, qops, pos, self.nd, max_ops=self.max_ops_per_pass,
                                                        final_moves=moves if self.park_in_last_pass else [],
                                                        strategy=self.strategy)
-                    if not self.park_in_last_pass:
+                    if not self.park_in_last_pass and not direct:
                         moves = [(v, n_loc - m + i) for i, v in enumerate(victims)]
                     chunks.append(P)
                 devops = []
@@ -372,6 +423,39 @@ class ShardedPauliEngine(PauliEngine):
                 steps.append(("passes", np.concatenate(chunks) if len(chunks) > 1 else chunks[0]))
             if not queue:
                 break
+            # Slots 0 / 1 carry the 128-byte runs and cannot be swapped in place, and a qubit of the FIRST blocked op must
+            # never be evicted (the exchange would not unblock it: no progress).  Nothing was parked, so evictees can
+            # still be (re)chosen by the layout the stretch ended in.
+            if direct and exchange_variant == "direct_late":
+                late = [q for q in range(self.n) if 2 <= pos[q] < n_loc and next_use.get(q, 1) != 0]
+                late.sort(key=lambda q: (-next_use.get(q, len(keep) + 1), pos[q]))
+                if len(late) >= m:
+                    victims = late[:m]
+            elif direct and any(pos[v] < 2 for v in victims):
+                spare = [q for q in range(self.n) if 2 <= pos[q] < n_loc and q not in victims and next_use.get(q, 1) != 0]
+                spare.sort(key=lambda q: (-next_use.get(q, len(keep) + 1), pos[q]))
+                victims = [v if pos[v] >= 2 else (spare.pop(0) if spare else v) for v in victims]
+            if direct and all(pos[v] >= 2 for v in victims):
+                # global slot n_loc + j <-> the slot victim j sits in (slots 0 and 1 hold the 128-byte runs: never)
+                slots = [pos[v] for v in victims]
+                steps.append(("exchange", slots))
+                incoming = {pos[q] - n_loc: q for q in range(self.n) if pos[q] >= n_loc}
+                for j, v in enumerate(victims):
+                    pos[incoming[j]], pos[v] = slots[j], n_loc + j
+                continue
+            if direct:                           # a victim on slot 0 / 1: park this one time after all
+                devops = []
+                slot_owner = {pos[q]: q for q in range(self.n)}
+                for i, v in enumerate(victims):
+                    target = n_loc - m + i
+                    if pos[v] != target:
+                        other = slot_owner[target]
+                        devops.append(schedule.DevOp(capi.OP_SWAP, pos[v], target))
+                        slot_owner[pos[v]], slot_owner[target] = other, v
+                        pos[other], pos[v] = pos[v], target
+                if devops:
+                    steps.append(("passes", schedule.build_passes(devops, self.nd, max_ops=self.max_ops_per_pass,
+                                                                  reserve_low=self.reserve_low)))
             steps.append(("exchange",))
             for q in range(self.n):              # global slot s <-> local slot s - m
                 if pos[q] >= n_loc:
@@ -402,17 +486,48 @@ class ShardedPauliEngine(PauliEngine):
                 rp(P)
                 i += 1
                 continue
+            slots = st[1] if len(st) > 1 else None
             if mode == "pull" and not self.plain_exchange and i + 1 < n and steps[i + 1][0] == "passes" \
                     and len(steps[i + 1][1]):
                 nxt = steps[i + 1][1]
-                self.exchange(fused_pass=nxt[:1])
+                self.exchange(fused_pass=nxt[:1], slots=slots)
                 rp(nxt[1:])
                 i += 2
                 continue
-            self.exchange()
+            self.exchange(slots=slots)
             i += 1
 
-    def exchange(self, fused_pass=None):
+    def _direct_exchange(self):
+        """True when slot swaps run as the fused pull (peer-mapped buffers) and may therefore address arbitrary slots."""
+        return (getattr(self, "direct_slots", False) and getattr(self, "peers", None) is not None
+                and getattr(self, "exchange_mode", "pull") == "pull")
+
+    def slot_swap_table(self, slots, bases):
+        """Source table of a pull that swaps global slot n_loc + j with local slot slots[j].  Returns (sel_bits, tab,
+        elements pulled from other ranks): element idx of the NEW local layout lies at  tab[k] + 8 * idx  where bit j of
+        k is bit sel_bits[j] of idx -- the local index bits the swap moves; all other bits keep their place, so the
+        source rank and the offset between old and new index depend on those bits only."""
+        n_bits, n_loc = self.n_bits, self.n_loc
+        sigma = {}
+        for j, p in enumerate(slots):
+            for half in (0, 1):
+                a, b = 2 * (n_loc + j) + half, 2 * p + half
+                sigma[a], sigma[b] = b, a
+        sel = sorted(b for b in sigma if b < n_bits)
+        tab = np.zeros(1 << len(sel), dtype=np.uint64)
+        remote = 0
+        for k in range(1 << len(sel)):
+            idx = sum(((k >> j) & 1) << b for j, b in enumerate(sel))
+            g_new = (self.rank << n_bits) | idx
+            g_old = g_new
+            for b, sb in sigma.items():          # bit b of the old index = bit sigma(b) of the new one
+                g_old = (g_old & ~(1 << b)) | (((g_new >> sb) & 1) << b)
+            src_rank, src_idx = g_old >> n_bits, g_old & ((1 << n_bits) - 1)
+            tab[k] = (bases[src_rank] + 8 * (src_idx - idx)) % (1 << 64)
+            remote += src_rank != self.rank
+        return sel, tab, remote << (n_bits - len(sel))
+
+    def exchange(self, fused_pass=None, slots=None):
         """Swap the m global slots with the m top local slots.  With peer-mapped buffers this is
         ONE tile-kernel launch: in ``pull`` mode it reads every tile from the rank holding it in
         the old layout (NVLink loads), applies ``fused_pass``'s ops and writes the new layout
@@ -435,12 +550,20 @@ class ShardedPauliEngine(PauliEngine):
                 self.comm.barrier()          # every rank's old buffer is final
                 self._peers_may_read_scratch = False
                 old = self.peers[self._cur]
-                for d in range(1 << px.block_bits):
-                    sr, sb = px.image(self.rank, d)
-                    tab[d] = (old[sr] + ((sb - d) << px.B) * 8) % (1 << 64)
-                ev = self._event_pair()
-                self.ctx.apply_pass_remote(self.alloc.ptr(self.scratch), self.n_bits, fused_pass, tab, px.B)
-                self._event_done(ev)
+                if slots is not None:        # global slots <-> the evictees' own slots
+                    self.direct_exchanges += 1
+                    sel, tab, pulled = self.slot_swap_table(slots, old)
+                    ev = self._event_pair()
+                    self.ctx.apply_pass_remote_sel(self.alloc.ptr(self.scratch), self.n_bits, fused_pass, tab, sel)
+                    self._event_done(ev)
+                    self.nvlink_bytes_sent += 8 * pulled - px.bytes_sent()     # (the common tail adds px.bytes_sent())
+                else:
+                    for d in range(1 << px.block_bits):
+                        sr, sb = px.image(self.rank, d)
+                        tab[d] = (old[sr] + ((sb - d) << px.B) * 8) % (1 << 64)
+                    ev = self._event_pair()
+                    self.ctx.apply_pass_remote(self.alloc.ptr(self.scratch), self.n_bits, fused_pass, tab, px.B)
+                    self._event_done(ev)
             else:
                 new = self.peers[self._cur ^ 1]      # the peers' idle buffers (free since the last barrier)
                 for s_blk in range(1 << px.block_bits):

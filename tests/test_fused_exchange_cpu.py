@@ -63,11 +63,13 @@ class ThreadComm:
         return [[everyone[r][b] for r in range(self.world)] for b in range(len(ptrs))]
 
 
-def _run_world(world, n, circ, opts, fused, mode="pull", first_job=None):
+def _run_world(world, n, circ, opts, fused, mode="pull", first_job=None, direct_slots=None):
     """``first_job``: a circuit that runs BEFORE ``circ`` on the same engines, which are then recycled for ``circ``
     (``ShardedPauliEngine.recycle``: what the product's sharded factory does between jobs of one register size)."""
     cluster = ThreadCluster(world)
     out, errs = [None] * world, []
+    direct_seen = [0] * world
+    _run_world.direct_seen = direct_seen
 
     def work(rank):
         try:
@@ -79,6 +81,8 @@ def _run_world(world, n, circ, opts, fused, mode="pull", first_job=None):
                     return engines[0].recycle()
                 e = distributed.ShardedPauliEngine(nq, comm, lib=emu_lib(), allocator=NumpyAllocator(), max_ops_per_pass=4)
                 e.exchange_mode = mode
+                if direct_slots is not None:     # "parked" | "direct" | "direct_late": force that schedule variant
+                    e.force_exchange_variant = direct_slots
                 engines.append(e)
                 return e
 
@@ -91,6 +95,7 @@ def _run_world(world, n, circ, opts, fused, mode="pull", first_job=None):
             c2.instructions = copy.deepcopy(circ.instructions)
             res = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
             out[rank] = (res, engines[0].exchanges, engines[0].peers is not None)
+            direct_seen[rank] = engines[0].direct_exchanges
         except Exception as exc:                     # pragma: no cover - surfaced below
             errs.append(exc)
             cluster.bar.abort()
@@ -157,6 +162,28 @@ def test_sharded_qft_with_chained_cnots_matches_oracle(world, n):
         outs = _run_world(world, n, circ, opts, fused, xmode)
         for rank, (res, exchanges, has_peers) in enumerate(outs):
             assert exchanges >= 1
+            p = np.array(list(res["data"]["ensemble_probability"].values()))
+            assert np.max(np.abs(p - p_ref)) <= 1e-10
+            assert np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])) <= 1e-10
+
+
+@pytest.mark.parametrize("world,n,seed,kind", [(2, 7, 31, "rand"), (4, 8, 32, "rand"), (8, 8, 33, "rand"), (8, 9, 34, "layered"),
+                                               (4, 9, 35, "layered"), (2, 8, 36, "layered")])
+def test_direct_slot_exchange_needs_no_parking_and_matches_oracle(world, n, seed, kind):
+    """Fused pull with the global slots swapped with the evictees' OWN local slots (scattered-bit source table,
+    ``dmb_apply_pass_remote_sel``): same results as the oracle and as the parking variant, the direct path is the one
+    that ran, and it never runs more passes than parking."""
+    circ = cases._rand_circuit(n, 60, seed) if kind == "rand" else C.random_layered(n, 8, seed, readout=False)
+    circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="XYZ"[seed % 3])
+    opts = dict(cases.FULL_NOISE, compute_densitymatrix=False)
+    ref = dm_oracle.run_oracle(n, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
+    p_ref = np.array(list(ref["data"]["ensemble_probability"].values()))
+    for variant in ("direct", "direct_late", "parked"):
+        outs = _run_world(world, n, circ, opts, True, "pull", direct_slots=variant)
+        seen = list(_run_world.direct_seen)
+        for rank, (res, exchanges, has_peers) in enumerate(outs):
+            assert has_peers and exchanges >= 1
+            assert (seen[rank] >= 1) == (variant != "parked"), (variant, seen)
             p = np.array(list(res["data"]["ensemble_probability"].values()))
             assert np.max(np.abs(p - p_ref)) <= 1e-10
             assert np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])) <= 1e-10

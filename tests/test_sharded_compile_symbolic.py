@@ -25,6 +25,7 @@ def _bare_engine(n, world):
     e.plan_x = distributed.ExchangePlan(n, world, 0)
     e.g, e.m, e.n_loc = e.plan_x.g, e.plan_x.m, e.plan_x.n_loc
     e.n, e.nd = n, e.plan_x.n_loc
+    e.n_bits = e.plan_x.n_bits_local
     e.lib = capi.load_library()
     e.pos = [n - 1 - q for q in range(n)]
     e.pending = [None] * n
@@ -37,12 +38,21 @@ def _bare_engine(n, world):
     return e
 
 
+def e_queue_copy(pairs):
+    return [("2q", capi.OP_CX, a, b, None, None, [float(k + 1)]) for k, (a, b) in enumerate(pairs)]
+
+
 def _replay_steps(steps, tagged, pos0, pos_end, n, n_loc, m):
     owner = {p: q for q, p in enumerate(pos0)}          # slot -> qubit
     last, seen, n_x = {}, [], 0
     for st in steps:
         if st[0] == "exchange":
             n_x += 1
+            if len(st) > 1:                              # direct: global slot n_loc + j <-> local slot st[1][j]
+                for j, p in enumerate(st[1]):
+                    assert 2 <= p < n_loc
+                    owner[n_loc + j], owner[p] = owner.get(p), owner.get(n_loc + j)
+                continue
             new = {}
             for s, q in owner.items():
                 new[s - m if s >= n_loc else s + m if s >= n_loc - m else s] = q
@@ -70,9 +80,10 @@ def _replay_steps(steps, tagged, pos0, pos_end, n, n_loc, m):
     return n_x
 
 
+@pytest.mark.parametrize("direct", [False, True])
 @pytest.mark.parametrize("n,world,shape", [(16, 2, "qft"), (16, 4, "qft"), (16, 8, "qft"), (18, 8, "layered"),
                                            (17, 8, "random"), (18, 4, "random"), (12, 8, "random"), (7, 8, "layered")])
-def test_sharded_compile_runs_every_op_once_on_the_right_slots(n, world, shape):
+def test_sharded_compile_runs_every_op_once_on_the_right_slots(n, world, shape, direct):
     if shape == "qft":
         circ = C.qft(n)
     elif shape == "layered":
@@ -82,12 +93,30 @@ def test_sharded_compile_runs_every_op_once_on_the_right_slots(n, world, shape):
         circ = cases._rand_circuit(n, 400, n * 10 + world, two_qubit_frac=0.6)
     pairs = [tuple(i.qubits) for i in circ.instructions if i.name == "cx"]
     e = _bare_engine(n, world)
+    if direct:                 # the fused pull: global slots are swapped with the evictees' own slots, nothing is parked
+        e.direct_slots, e.peers, e.exchange_mode = True, [[0] * world] * 2, "pull"
     for k, (a, b) in enumerate(pairs):
         e.queue.append(("2q", capi.OP_CX, a, b, None, None, [float(k + 1)]))      # coef[0] carries the tag
     pos0 = list(e.pos)
     steps = e.compile(final=True)
     n_x = _replay_steps(steps, pairs, pos0, e.pos, n, e.n_loc, e.m)
     assert n_x >= 1            # every shape touches the global qubits
+    if direct:
+        # the schedule kept is never costlier than the parked one (passes + exchanges x their relative cost), and every
+        # variant on its own is a valid schedule too
+        parked = _bare_engine(n, world)
+        parked.queue = list(e_queue_copy(pairs))
+        cost = lambda ss: (sum(len(st[1]) for st in ss if st[0] == "passes")
+                           + 2.5 * (world - 1) / world * sum(1 for st in ss if st[0] == "exchange"))
+        assert cost(steps) <= cost(parked.compile(final=True)) + 1e-9
+        for variant in ("direct", "direct_late"):
+            v = _bare_engine(n, world)
+            v.direct_slots, v.peers, v.exchange_mode = True, [[0] * world] * 2, "pull"
+            v.queue = list(e_queue_copy(pairs))
+            pos_v = list(v.pos)
+            steps_v = v._compile_one(True, variant)
+            _replay_steps(steps_v, pairs, pos_v, v.pos, n, v.n_loc, v.m)
+            assert any(st[0] == "exchange" and len(st) > 1 for st in steps_v)
     # the layered n = 18 benchmark shape needs only a handful of slot swaps (2 at depth 20)
     if (n, world, shape) == (18, 8, "layered"):
         assert n_x <= 3
