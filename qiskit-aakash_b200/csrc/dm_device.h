@@ -1078,8 +1078,8 @@ DMB_HD double dmb_init_value(uint64_t idx, const dmb_init_params& p) {
 // Marginal gather (see dmb_marginal in dmb200.h).  Qubits are split by the host into
 // "simple" ones (at most one non-zero weight per result bit value: the usual I / B pick)
 // and up to DMB_MAX_MULTI "multi" ones whose weights mix several digit values (pending
-// single-qubit maps on sharded qubits).
-#define DMB_MAX_MULTI 3
+// single-qubit maps: on sharded qubits, and the few a readout-only job leaves on local ones).
+#define DMB_MAX_MULTI 4
 struct dmb_marginal_params {
   dmb_qubit_map map;
   double wt[DMB_MAX_QUBITS][2][4];

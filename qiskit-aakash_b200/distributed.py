@@ -611,9 +611,44 @@ class ShardedPauliEngine(PauliEngine):
             self.comm.barrier()
             self._peers_may_read_scratch = False
 
-    def flush(self):
+    MAX_FOLDED_MAPS = 4      # DMB_MAX_MULTI of the marginal kernel: qubits whose pending map a readout can fold in
+
+    def _drop_map_only_tail(self, steps, pending_before):
+        """A flush that ends with a pass of single-qubit maps only (the pending maps no earlier pass had room for) pays
+        a full round trip of the shard for them.  The I/B-marginal readout folds pending maps into its weights -- it
+        does so for the global qubits anyway -- so when that readout comes next and at most MAX_FOLDED_MAPS qubits
+        would carry one, the pass is dropped and its maps stay pending."""
+        if not getattr(self, "fold_tail_maps", True) or not steps or steps[-1][0] != "passes" or not len(steps[-1][1]):
+            return steps
+        P = steps[-1][1]
+        last = P[-1]
+        ops = last["ops"][:int(last["n_ops"])]
+        if any(int(o["kind"]) != capi.OP_MATS for o in ops):
+            return steps
+        owner = {self.pos[q]: q for q in range(self.n)}      # no swap in this pass: its layout is the final one
+        restored = {}
+        for o in ops:
+            for flag, digit, rows in ((capi.HAS_PA, o["a"], o["pa"]), (capi.HAS_PB, o["b"], o["pb"])):
+                if not (int(o["flags"]) & flag):
+                    continue
+                q = owner.get(int(last["tile_digit"][int(digit)]))
+                before = None if q is None else pending_before[q]
+                if before is None or q in restored or not np.array_equal(np.asarray(before)[1:4, :].reshape(12), rows):
+                    return steps
+                restored[q] = before
+        carrying = sum(1 for q in range(self.n) if self.pending[q] is not None)
+        if not restored or carrying + len(restored) > self.MAX_FOLDED_MAPS:
+            return steps
+        for q, M in restored.items():
+            self.pending[q] = M
+        return steps[:-1] + ([("passes", P[:-1])] if len(P) > 1 else [])
+
+    def flush(self, keep_tail_maps=False):
         saved = list(self.pos)
+        before = list(self.pending)
         steps = self.compile(final=True)
+        if keep_tail_maps:
+            steps = self._drop_map_only_tail(steps, before)
         final_pos = self.pos
         self.pos = saved                         # run_steps does not depend on pos; keep it coherent on error
         self.run_steps(steps)
@@ -624,7 +659,7 @@ class ShardedPauliEngine(PauliEngine):
 
     # -- readouts -----------------------------------------------------------------------------
     def marginal_probabilities(self, basis, err):
-        self.flush()
+        self.flush(keep_tail_maps=True)
         b = {"X": 1, "Y": 2, "Z": 3}[basis]
         n = self.n
         hi, lo, wt = [], [], np.zeros((n, 2, 4))
@@ -951,7 +986,8 @@ class ShardedCircuitRunner:
             be._run_level(e, level, None, {})
             if noisy:
                 e.apply_1q_all(noise)
-        self.steps = e.compile(final=True)
+        before = list(e.pending)
+        self.steps = e._drop_map_only_tail(e.compile(final=True), before)      # what flush() does ahead of the marginal
         self.final_pos = list(e.pos)
         self.final_pending = list(e.pending)
         self.err = be._error_params["measurement"]

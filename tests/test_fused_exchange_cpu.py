@@ -187,3 +187,60 @@ def test_direct_slot_exchange_needs_no_parking_and_matches_oracle(world, n, seed
             p = np.array(list(res["data"]["ensemble_probability"].values()))
             assert np.max(np.abs(p - p_ref)) <= 1e-10
             assert np.max(np.abs(res["data"]["coeffmatrix"] - ref["data"]["coeffmatrix"])) <= 1e-10
+
+
+@pytest.mark.parametrize("world,n", [(2, 7), (4, 8), (8, 8)])
+def test_map_only_tail_pass_is_folded_into_the_marginal_readout(world, n):
+    """A job whose last pass would only apply pending single-qubit maps (here: a u3 on two qubits after the last CNOT) and
+    that ends in an X / Y / Z ensemble readout: the pass is dropped, the maps stay pending and the readout folds them into
+    its weights (``_drop_map_only_tail``) -- same probabilities, one round trip of the shard less."""
+    circ = C.Circuit(n)
+    for q in range(n):
+        circ.u3(0.3 + 0.1 * q, 0.2, 0.5, q)
+    for q in range(0, n - 1, 2):
+        circ.cx(q, q + 1)
+    circ.cx(n - 1, 0)
+    circ.u3(0.7, -0.4, 1.1, 2)
+    circ.u3(-0.2, 0.9, 0.3, 3)
+    circ.measure(list(range(n)), list(range(n)), basis="Ensemble", add_param="Y")
+    opts = {"compute_densitymatrix": False}
+    ref = dm_oracle.run_oracle(n, copy.deepcopy(circ.instructions), copy.deepcopy(opts))
+    p_ref = np.array(list(ref["data"]["ensemble_probability"].values()))
+    passes = {}
+    for fold in (True, False):
+        cluster_out = []
+
+        def run(fold=fold):
+            cluster = ThreadCluster(world)
+            out, errs = [None] * world, []
+
+            def work(rank):
+                try:
+                    comm = ThreadComm(cluster, rank, True)
+                    e = distributed.ShardedPauliEngine(n, comm, lib=emu_lib(), allocator=NumpyAllocator(), max_ops_per_pass=4)
+                    e.fold_tail_maps = fold
+                    be = DmSimulatorB200(_engine_factory=lambda nq: e)
+                    be.SHOW_FINAL_STATE = False
+                    c2 = C.Circuit(n)
+                    c2.instructions = copy.deepcopy(circ.instructions)
+                    res = be.run(assemble(c2), backend_options=copy.deepcopy(opts)).result()["results"][0]
+                    out[rank] = (res, e.passes_run)
+                except Exception as exc:                 # pragma: no cover
+                    errs.append(exc)
+                    cluster.bar.abort()
+
+            threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            if errs:
+                raise errs[0]
+            return out
+
+        outs = run()
+        for res, n_passes in outs:
+            p = np.array(list(res["data"]["ensemble_probability"].values()))
+            assert np.max(np.abs(p - p_ref)) <= 1e-10
+        passes[fold] = outs[0][1]
+    assert passes[True] <= passes[False]
