@@ -1043,7 +1043,11 @@ class ShardedCircuitRunner:
             return {"exchanges": 0}
         out = {"exchanges": e.exchanges, "mode": e.exchange_mode if e.peers is not None else "nccl",
                "bytes_per_gpu_per_exchange": e.nvlink_bytes_sent // e.exchanges,
-               "nvlink_bytes_sent_per_gpu": e.nvlink_bytes_sent}
+               "nvlink_bytes_sent_per_gpu": e.nvlink_bytes_sent,
+               # which schedule compile() kept: evictees parked on the top local slots, or global slots swapped with
+               # the evictees' own slots (direct / direct_late), and how many of the exchanges ran that way
+               "schedule_variant": getattr(e, "last_compile_mode", "parked"),
+               "direct_slot_exchanges": getattr(e, "direct_exchanges", 0)}
         evs = getattr(e, "exchange_events", None)
         if evs:
             import torch
