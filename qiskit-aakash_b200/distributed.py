@@ -305,13 +305,14 @@ class ShardedPauliEngine(PauliEngine):
         alike) costs less than 1 % of the estimated device time."""
         forced = getattr(self, "force_exchange_variant", None) or os.environ.get("DMB_EXCHANGE_VARIANT")
         if forced:                                   # tests / A-B runs: "parked" | "direct" | "direct_late"
-            self.last_compile_mode = forced
-            return self._compile_one(final, forced)
+            steps = self._compile_one(final, forced)
+            if any(st[0] == "exchange" for st in steps):
+                self.last_compile_mode = forced
+            return steps
         modes = ["parked"]
         if self._direct_exchange():
             modes += ["direct", "direct_late"]
         if len(modes) == 1:
-            self.last_compile_mode = "parked"
             return self._compile_one(final, "parked")
         saved = (list(self.queue), list(self.pos), list(self.pending))
         pass_ms = 16.0 * 2.0 ** self.n_bits / 2.6e12 * 1e3            # a fused pass at ~0.4 of the HBM roofline
@@ -332,7 +333,8 @@ class ShardedPauliEngine(PauliEngine):
                 break
         self.queue = []
         self.pos, self.pending = best[2], best[3]
-        self.last_compile_mode = best[4]
+        if any(st[0] == "exchange" for st in best[1]):       # (a flush without exchanges says nothing about the choice)
+            self.last_compile_mode = best[4]
         return best[1]
 
     def _compile_one(self, final, exchange_variant):
