@@ -202,6 +202,25 @@ extern "C" int dmb_emu_run_half_kernel(double* state, int n_bits, const dmb_pass
   return 0;
 }
 
+// test hook: ONE K = 6 pass through the threaded kernel body in pull mode (REMOTE = 1: every 16-byte pair is read through
+// the source table, whose index is gathered from the selected index bits and composed from per-tile / per-thread /
+// per-pair parts) -- the path the CUDA kernel takes for a fused exchange; compared with dmb_apply_pass_remote_sel
+extern "C" int dmb_emu_run_half_kernel_pull(double* dst_state, int n_bits, const dmb_pass* pass, const uint64_t* tab,
+                                            int n_sel, const int32_t* sel, int grid) {
+  static thread_local dmb_lean_pass L;
+  if (pass->n_tile_digits != DMB_LEAN_K || n_sel < 0 || n_sel > DMB_REMOTE_BITS) return 1;
+  dmb_make_lean_pass(*pass, n_bits, L);
+  dmb_remote_src R;
+  memset(&R, 0, sizeof(R));
+  for (int i = 0; i < (1 << n_sel); ++i) R.tab[i] = tab[i];
+  R.n_sel = n_sel;
+  for (int j = 0; j < n_sel; ++j) R.sel[j] = sel[j];
+  R.enabled = 1;
+  const uint64_t g = (uint64_t)grid < L.n_tiles ? (uint64_t)grid : L.n_tiles;
+  for (uint64_t block = 0; block < g; ++block) run_half_kernel_cta<DMB_ST_PLAIN, true, 1, 1>(dst_state, L, block, g, R);
+  return 0;
+}
+
 // test hook: how many ops of a K = 6 pass the library chains to their predecessor (dmb_chain_ops), and the op order it runs
 extern "C" int dmb_emu_pass_chained(const dmb_pass* pass, int n_bits, int32_t* order_out) {
   static thread_local dmb_lean_pass L;
