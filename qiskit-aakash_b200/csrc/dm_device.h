@@ -1006,24 +1006,16 @@ DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L,
   dmb_lean_thread_init(2 * cx.tid(), L, P0);
   const uint64_t first = cx.block(), stride = cx.grid();
   if (first >= L.n_tiles) return;
-  // REMOTE == 1: the source-table index of pair i of a tile is gathered from selected index bits; tile base, thread part
-  // and pair part occupy disjoint bits, so it is the OR of three gathers -- per thread once, per tile once, per pair
-  // uniform -- instead of a gather per 16-byte copy
-  const uint32_t k_thr0 = REMOTE == 1 ? dmb_remote_index(R, S0.goff) : 0u;
-  const uint32_t k_thr1 = REMOTE == 1 ? dmb_remote_index(R, S1.goff) : 0u;
-  auto src_of = [&](uint64_t tb, uint32_t k_tile, uint32_t k_thread, uint64_t goff, int i) -> const double* {
-    const uint64_t idx = tb + (goff | L.pair_goff[i]);
-    if (REMOTE == 1)
-      return reinterpret_cast<const double*>(R.tab[k_tile | k_thread | dmb_remote_index(R, L.pair_goff[i])]) + idx;
+  auto src_of = [&](uint64_t idx) -> const double* {
+    if (REMOTE == 1) return reinterpret_cast<const double*>(R.tab[dmb_remote_index(R, idx)]) + idx;
     return state + idx;
   };
   if (STAGES == 2) {
     const uint64_t tb = dmb_tile_base(first, L.td, DMB_LEAN_K);
-    const uint32_t k_tile = REMOTE == 1 ? dmb_remote_index(R, tb) : 0u;
 #pragma unroll
     for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
-      cx.copy16(S0.soff ^ L.pair_soff[i], src_of(tb, k_tile, k_thr0, S0.goff, i));
-      cx.copy16(S1.soff ^ L.pair_soff[i], src_of(tb, k_tile, k_thr1, S1.goff, i));
+      cx.copy16(S0.soff ^ L.pair_soff[i], src_of(tb + (S0.goff | L.pair_goff[i])));
+      cx.copy16(S1.soff ^ L.pair_soff[i], src_of(tb + (S1.goff | L.pair_goff[i])));
     }
     cx.commit();
   }
@@ -1032,12 +1024,11 @@ DMB_HD void dmb_half_kernel_body(Ctx& cx, double* state, const dmb_lean_pass& L,
     const uint64_t fetch_tile = STAGES == 2 ? tile + stride : tile;
     if (fetch_tile < L.n_tiles) {
       const uint64_t tb = dmb_tile_base(fetch_tile, L.td, DMB_LEAN_K);
-      const uint32_t k_tile = REMOTE == 1 ? dmb_remote_index(R, tb) : 0u;
       const uint32_t dst = (STAGES == 2 ? (cur ^ 1u) : 0u) * DMB_LEAN_TILE_BYTES;
 #pragma unroll
       for (int i = 0; i < DMB_LEAN_PAIRS; ++i) {
-        cx.copy16(dst + (S0.soff ^ L.pair_soff[i]), src_of(tb, k_tile, k_thr0, S0.goff, i));
-        cx.copy16(dst + (S1.soff ^ L.pair_soff[i]), src_of(tb, k_tile, k_thr1, S1.goff, i));
+        cx.copy16(dst + (S0.soff ^ L.pair_soff[i]), src_of(tb + (S0.goff | L.pair_goff[i])));
+        cx.copy16(dst + (S1.soff ^ L.pair_soff[i]), src_of(tb + (S1.goff | L.pair_goff[i])));
       }
     }
     cx.commit();
