@@ -46,14 +46,16 @@ class Op:
 
 
 def _to_op(ins, order):
-    name = ins["name"] if isinstance(ins, dict) else ins.name
-    get = (lambda k: ins.get(k)) if isinstance(ins, dict) else (lambda k: getattr(ins, k, None))
-    params = get("params")
-    if params is not None:
-        params = list(params)
-    mem, reg = get("memory"), get("register")
-    return Op(name, get("qubits") or [], params, list(mem) if mem is not None else None,
-              list(reg) if reg is not None else None, order, get("conditional"))
+    if isinstance(ins, dict):
+        get = ins.get
+        name, params, mem, reg = ins["name"], get("params"), get("memory"), get("register")
+        qubits, cond = get("qubits"), get("conditional")
+    else:
+        name, params = ins.name, getattr(ins, "params", None)
+        mem, reg = getattr(ins, "memory", None), getattr(ins, "register", None)
+        qubits, cond = getattr(ins, "qubits", None), getattr(ins, "conditional", None)
+    return Op(name, qubits or [], list(params) if params is not None else None, list(mem) if mem is not None else None,
+              list(reg) if reg is not None else None, order, cond)
 
 
 def zyz_from_yzy(xi, theta1, theta2):
